@@ -1,0 +1,377 @@
+"""Drop-in mix consoles backed by the sm_100a kernels.
+
+``AdvancedMixConsole`` mirrors ``mst.modules.AdvancedMixConsole`` (reference
+mst/modules.py:100-487): same constructor arguments, attributes (``sample_rate``,
+``param_ranges``, ``num_*_control_params``), ``forward`` / ``forward_mix_console``
+signatures (note that the two order ``use_master_bus`` / ``use_fx_bus`` differently, as
+upstream does), return tuples, nested parameter-dict keys and the out-of-range
+``ValueError`` (mst/modules.py:86-89).  The module has no parameters or buffers, so the
+strict ``load_state_dict({})`` of mst/utils.py:245-249 keeps working.
+
+``BasicMixConsole`` does not exist at the reference commit; it is reconstructed from
+README.md:14 and mst/mixing.py:122-164, 935-945 (gain + pan per track, bus sum).
+
+All arithmetic on audio runs in libdiffmst_b200.so; torch is used for memory, streams and
+the autograd graph.  The denormalised parameter dictionaries returned to the caller are
+produced with the same torch expressions as upstream (they are tiny and callers may
+differentiate through them).
+"""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+EQ_BANDS = ["low_shelf", "band0", "band1", "band2", "band3", "high_shelf"]
+EQ_KEYS = [f"{b}_{p}" for b in EQ_BANDS for p in ("gain_db", "cutoff_freq", "q_factor")]
+COMP_KEYS = ["threshold_db", "ratio", "attack_ms", "release_ms", "knee_db", "makeup_gain_db"]
+TRACK_LOOKAHEAD = 2048   # mst/modules.py:250
+MASTER_LOOKAHEAD = 1024  # mst/modules.py:304
+
+
+def denormalize(norm_val, max_val, min_val):
+    """mst/modules.py:71-72."""
+    return (norm_val * (max_val - min_val)) + min_val
+
+
+def _first_out_of_range(flat_params: torch.Tensor):
+    """Index of the first column holding a value outside [0, 1], or None; one device sync
+    instead of the reference's two per parameter (mst/modules.py:86)."""
+    if flat_params.numel() == 0:
+        return None
+    bad = ((flat_params < 0) | (flat_params > 1)).any(dim=0)
+    idx = torch.nonzero(bad)
+    return int(idx[0]) if idx.numel() else None
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"diffmst_b200: {what} must be a CUDA tensor; there is no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"diffmst_b200: {what} must be float32 (got {t.dtype})")
+
+
+class _ConsoleFunction(torch.autograd.Function):
+    """tracks (B,N,T), track_params (B,N,P), master_params (B,26)|None -> mix, mixed."""
+
+    @staticmethod
+    def forward(ctx, tracks, track_params, master_params, ranges, sample_rate, flags, la_t, la_m,
+                want_mixed):
+        lib = _lib.lib()
+        _require_cuda(tracks, "tracks")
+        _require_cuda(track_params, "track_params")
+        B, N, T = tracks.shape
+        if tracks.stride(2) != 1 or tracks.stride(0) < 0 or tracks.stride(1) < 0:
+            tracks = tracks.contiguous()
+        track_params = track_params.contiguous()
+        if master_params is not None:
+            _require_cuda(master_params, "master_bus_params")
+            master_params = master_params.contiguous()
+        dev = tracks.device
+        flags = int(flags) | (_lib.WANT_MIXED_TRACKS if want_mixed else 0)
+        with torch.cuda.device(dev):
+            nbytes = lib.dmst_console_workspace_bytes(B, N, T, flags)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            mix = torch.empty(B, 2, T, dtype=torch.float32, device=dev)
+            mixed = torch.empty(B, 2, N, T, dtype=torch.float32, device=dev) if want_mixed else None
+            status = torch.empty(4, dtype=torch.int32, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.dmst_console_forward(
+                _ptr(tracks), tracks.stride(0), tracks.stride(1), _ptr(track_params), _ptr(master_params),
+                ctypes.byref(ranges), float(sample_rate), B, N, T, flags, la_t, la_m, _ptr(mix),
+                _ptr(mixed), _ptr(status), _ptr(ws), nbytes, ctypes.c_void_p(stream))
+        _lib.check(rc, "dmst_console_forward")
+        ctx.save_for_backward(tracks, track_params, master_params if master_params is not None else torch.empty(0, device=dev))
+        ctx.has_master = master_params is not None
+        ctx.ws, ctx.nbytes, ctx.ranges = ws, nbytes, ranges
+        ctx.cfg = (float(sample_rate), flags, la_t, la_m)
+        ctx.mark_non_differentiable(status)
+        if mixed is None:
+            mixed = torch.empty(0, device=dev)
+        return mix, mixed, status
+
+    @staticmethod
+    def backward(ctx, gmix, gmixed, _gstatus):
+        lib = _lib.lib()
+        tracks, track_params, master_params = ctx.saved_tensors
+        master_params = master_params if ctx.has_master else None
+        sample_rate, flags, la_t, la_m = ctx.cfg
+        B, N, T = tracks.shape
+        dev = tracks.device
+        want_gtracks = ctx.needs_input_grad[0]
+        if want_gtracks:
+            flags |= _lib.WANT_GRAD_TRACKS
+        if gmix is None:
+            gmix = torch.zeros(B, 2, T, dtype=torch.float32, device=dev)
+        gmix = gmix.contiguous()
+        use_gmixed = gmixed is not None and gmixed.numel() > 0 and (flags & _lib.WANT_MIXED_TRACKS)
+        gmixed = gmixed.contiguous() if use_gmixed else None
+        with torch.cuda.device(dev):
+            gtp = torch.empty_like(track_params)
+            gmp = torch.empty_like(master_params) if master_params is not None else None
+            gtr = torch.empty(B, N, T, dtype=torch.float32, device=dev) if want_gtracks else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.dmst_console_backward(
+                _ptr(tracks), tracks.stride(0), tracks.stride(1), _ptr(track_params), _ptr(master_params),
+                ctypes.byref(ctx.ranges), sample_rate, B, N, T, flags, la_t, la_m, _ptr(gmix), _ptr(gmixed),
+                _ptr(gtp), _ptr(gmp), _ptr(gtr), _ptr(ctx.ws), ctx.nbytes, ctypes.c_void_p(stream))
+        _lib.check(rc, "dmst_console_backward")
+        return gtr, gtp, gmp, None, None, None, None, None, None
+
+
+def _flags(use_track_input_fader, use_track_eq, use_track_compressor, use_track_panner,
+           use_fx_bus, use_master_bus, use_output_fader):
+    f = 0
+    f |= _lib.USE_TRACK_INPUT_FADER if use_track_input_fader else 0
+    f |= _lib.USE_TRACK_EQ if use_track_eq else 0
+    f |= _lib.USE_TRACK_COMPRESSOR if use_track_compressor else 0
+    f |= _lib.USE_TRACK_PANNER if use_track_panner else 0
+    f |= _lib.USE_MASTER_BUS if use_master_bus else 0
+    f |= _lib.USE_OUTPUT_FADER if use_output_fader else 0
+    if use_fx_bus:
+        raise NotImplementedError(
+            "use_fx_bus=True: the fx bus (stereo_bus + noise_shaped_reverberation, "
+            "mst/modules.py:275-284) is outside the accelerated hot path; every shipped config "
+            "keeps it off (configs/models/naive.yaml:7). Pass use_fx_bus=False.")
+    if not use_track_panner:
+        # upstream's else-branch calls .repeat(1, 2, 1) on a 4-D tensor (mst/modules.py:269)
+        raise RuntimeError(
+            "Number of dimensions of repeat dims can not be smaller than number of dimensions of "
+            "tensor (use_track_panner=False is broken upstream, mst/modules.py:269)")
+    return f
+
+
+class AdvancedMixConsole(torch.nn.Module):
+    def __init__(
+        self,
+        sample_rate: float,
+        input_min_gain_db: float = -48.0,
+        input_max_gain_db: float = 48.0,
+        output_min_gain_db: float = -48.0,
+        output_max_gain_db: float = 48.0,
+        min_send_db: float = -80.0,
+        max_send_db: float = +12.0,
+        eq_min_gain_db: float = -12.0,
+        eq_max_gain_db: float = 12.0,
+        min_pan: float = 0.0,
+        max_pan: float = 1.0,
+        reverb_min_band_gain: float = 0.0,
+        reverb_max_band_gain: float = 1.0,
+        reverb_min_band_decay: float = 0.0,
+        reverb_max_band_decay: float = 1.0,
+    ):
+        super().__init__()
+        self.sample_rate = sample_rate
+        hi_cut = (sample_rate // 2) - 1000
+        cut = {"low_shelf": (20, 2000), "band0": (80, 2000), "band1": (2000, 8000),
+               "band2": (8000, 12000), "band3": (12000, hi_cut), "high_shelf": (6000, hi_cut)}
+        eq = {}
+        for b in EQ_BANDS:
+            eq[f"{b}_gain_db"] = (eq_min_gain_db, eq_max_gain_db)
+            eq[f"{b}_cutoff_freq"] = cut[b]
+            eq[f"{b}_q_factor"] = (0.1, 5.0)
+        rev = {f"band{i}_gain": (reverb_min_band_gain, reverb_max_band_gain) for i in range(12)}
+        rev.update({f"band{i}_decay": (reverb_min_band_decay, reverb_max_band_decay) for i in range(12)})
+        rev["mix"] = (0.0, 1.0)
+        self.param_ranges = {
+            "input_fader": {"gain_db": (input_min_gain_db, input_max_gain_db)},
+            "output_fader": {"gain_db": (output_min_gain_db, output_max_gain_db)},
+            "parametric_eq": eq,
+            "compressor": {"threshold_db": (-60.0, 0.0), "ratio": (1.0, 10.0), "attack_ms": (5.0, 250.0),
+                           "release_ms": (10.0, 250.0), "knee_db": (3.0, 12.0), "makeup_gain_db": (0.0, 6.0)},
+            "reverberation": rev,
+            "fx_bus": {"send_db": (min_send_db, max_send_db)},
+            "stereo_panner": {"pan": (min_pan, max_pan)},
+        }
+        self.num_track_control_params = 27
+        self.num_fx_bus_control_params = 25
+        self.num_master_bus_control_params = 26
+        # Not part of the upstream interface: set False to skip materialising the
+        # (bs, 2, num_tracks, seq_len) tensor that forward returns first (an empty tensor is
+        # returned instead); set check_ranges False to skip the device sync of the range test.
+        self.materialize_tracks = True
+        self.check_ranges = True
+
+    # ---- parameter plumbing (mst/modules.py:353-466) ----
+    def _track_ranges(self):
+        pr = self.param_ranges
+        return ([pr["input_fader"]["gain_db"]] + [pr["parametric_eq"][k] for k in EQ_KEYS]
+                + [pr["compressor"][k] for k in COMP_KEYS]
+                + [pr["stereo_panner"]["pan"], pr["fx_bus"]["send_db"]])
+
+    def _master_ranges(self):
+        pr = self.param_ranges
+        return ([pr["parametric_eq"][k] for k in EQ_KEYS] + [pr["compressor"][k] for k in COMP_KEYS]
+                + [pr["output_fader"]["gain_db"], pr["input_fader"]["gain_db"]])
+
+    def _c_ranges(self):
+        r = _lib.Ranges()
+        for i, (lo, hi) in enumerate(self._track_ranges()):
+            r.track_lo[i], r.track_hi[i] = lo, hi
+        for i, (lo, hi) in enumerate(self._master_ranges()):
+            r.master_lo[i], r.master_hi[i] = lo, hi
+        return r
+
+    @staticmethod
+    def _split_track(p):
+        d = {"input_fader": {"gain_db": p[..., 0]},
+             "parametric_eq": {k: p[..., 1 + i] for i, k in enumerate(EQ_KEYS)},
+             "compressor": {k: p[..., 19 + i] for i, k in enumerate(COMP_KEYS)},
+             "stereo_panner": {"pan": p[..., 25]},
+             "fx_bus": {"send_db": p[..., 26]}}
+        return d
+
+    @staticmethod
+    def _split_fx(p):
+        rev = {f"band{i}_gain": p[..., i] for i in range(12)}
+        rev.update({f"band{i}_decay": p[..., 12 + i] for i in range(12)})
+        rev["mix"] = torch.ones_like(p[..., 24])
+        return {"reverberation": rev}
+
+    @staticmethod
+    def _split_master(p):
+        return {"parametric_eq": {k: p[..., i] for i, k in enumerate(EQ_KEYS)},
+                "compressor": {k: p[..., 18 + i] for i, k in enumerate(COMP_KEYS)},
+                "output_fader": {"gain_db": p[..., 24]},
+                "input_fader": {"gain_db": p[..., 25]}}
+
+    def _denormalize(self, param_dict):
+        out = {}
+        for effect, params in param_dict.items():
+            out[effect] = {}
+            for name, t in params.items():
+                lo, hi = self.param_ranges[effect][name]
+                out[effect][name] = denormalize(t, hi, lo)
+        return out
+
+    def _raise_if_out_of_range(self, track_params, fx_bus_params, master_bus_params):
+        # same traversal order as three denormalize_parameters calls (mst/modules.py:462-466)
+        flat = torch.cat([track_params.reshape(-1, 27).amin(0), track_params.reshape(-1, 27).amax(0),
+                          fx_bus_params.reshape(-1, 25).amin(0), fx_bus_params.reshape(-1, 25).amax(0),
+                          master_bus_params.reshape(-1, 26).amin(0), master_bus_params.reshape(-1, 26).amax(0)])
+        flat = flat.detach().cpu()
+        tmin, tmax, fmin, fmax, mmin, mmax = torch.split(flat, [27, 27, 25, 25, 26, 26])
+        track_names = [("input_fader", "gain_db")] + [("parametric_eq", k) for k in EQ_KEYS] + \
+            [("compressor", k) for k in COMP_KEYS] + [("stereo_panner", "pan"), ("fx_bus", "send_db")]
+        fx_names = [("reverberation", f"band{i}_gain") for i in range(12)] + \
+            [("reverberation", f"band{i}_decay") for i in range(12)]  # "mix" is forced to ones
+        master_names = [("parametric_eq", k) for k in EQ_KEYS] + [("compressor", k) for k in COMP_KEYS] + \
+            [("output_fader", "gain_db"), ("input_fader", "gain_db")]
+        for names, lo, hi in ((track_names, tmin, tmax), (fx_names, fmin, fmax), (master_names, mmin, mmax)):
+            for i, (effect, name) in enumerate(names):
+                if lo[i] < 0 or hi[i] > 1:
+                    raise ValueError(f"Parameter {name} of effect {effect} is out of range.")
+
+    # ---- the chain (mst/modules.py:186-314) ----
+    def _run(self, tracks, track_params_norm, master_params_norm, flags):
+        mix, mixed, _ = _ConsoleFunction.apply(
+            tracks, track_params_norm, master_params_norm, self._c_ranges(), self.sample_rate, flags,
+            TRACK_LOOKAHEAD, MASTER_LOOKAHEAD, self.materialize_tracks)
+        return mixed, mix
+
+    @staticmethod
+    def _normalize_dict(denorm_dict, ranges, keys):
+        cols = []
+        for effect, name in keys:
+            lo, hi = ranges[effect][name]
+            cols.append((denorm_dict[effect][name] - lo) / (hi - lo))
+        return torch.stack(cols, dim=-1)
+
+    def forward_mix_console(
+        self,
+        tracks: torch.Tensor,
+        track_param_dict: dict,
+        fx_bus_param_dict: dict,
+        master_bus_param_dict: dict,
+        use_track_input_fader: bool = True,
+        use_track_eq: bool = True,
+        use_track_compressor: bool = True,
+        use_track_panner: bool = True,
+        use_fx_bus: bool = True,
+        use_master_bus: bool = True,
+        use_output_fader: bool = True,
+    ):
+        """Same contract as mst/modules.py:186-314: takes DENORMALISED parameter dicts and
+        returns (tracks (bs, 2, num_tracks, seq_len), master_bus (bs, 2, seq_len)).  The
+        kernels consume normalised parameters, so the dicts are mapped back with the inverse
+        affine (exact up to float32 rounding)."""
+        flags = _flags(use_track_input_fader, use_track_eq, use_track_compressor, use_track_panner,
+                       use_fx_bus, use_master_bus, use_output_fader)
+        tkeys = [("input_fader", "gain_db")] + [("parametric_eq", k) for k in EQ_KEYS] + \
+            [("compressor", k) for k in COMP_KEYS] + [("stereo_panner", "pan"), ("fx_bus", "send_db")]
+        mkeys = [("parametric_eq", k) for k in EQ_KEYS] + [("compressor", k) for k in COMP_KEYS] + \
+            [("output_fader", "gain_db"), ("input_fader", "gain_db")]
+        tp = self._normalize_dict(track_param_dict, self.param_ranges, tkeys).clamp(0, 1)
+        mp = self._normalize_dict(master_bus_param_dict, self.param_ranges, mkeys).clamp(0, 1)
+        return self._run(tracks, tp, mp, flags)
+
+    def forward(
+        self,
+        tracks: torch.Tensor,
+        track_params: torch.Tensor,
+        fx_bus_params: torch.Tensor,
+        master_bus_params: torch.Tensor,
+        use_track_input_fader: bool = True,
+        use_track_eq: bool = True,
+        use_track_compressor: bool = True,
+        use_track_panner: bool = True,
+        use_master_bus: bool = True,
+        use_fx_bus: bool = True,
+        use_output_fader: bool = True,
+    ):
+        """Create a mix from tracks and mixing parameters in (0, 1); mst/modules.py:316-487."""
+        flags = _flags(use_track_input_fader, use_track_eq, use_track_compressor, use_track_panner,
+                       use_fx_bus, use_master_bus, use_output_fader)
+        if self.check_ranges:
+            self._raise_if_out_of_range(track_params, fx_bus_params, master_bus_params)
+        track_param_dict = self._denormalize(self._split_track(track_params))
+        fx_bus_param_dict = self._denormalize(self._split_fx(fx_bus_params))
+        master_bus_param_dict = self._denormalize(self._split_master(master_bus_params))
+        mixed_tracks, mix = self._run(tracks, track_params, master_bus_params, flags)
+        return mixed_tracks, mix, track_param_dict, fx_bus_param_dict, master_bus_param_dict
+
+
+class BasicMixConsole(torch.nn.Module):
+    """Gain + pan per track, stereo bus sum (reconstruction, see module docstring).
+    Track parameters: [..., 0] gain_db, [..., 1] pan, both normalised to (0, 1)."""
+
+    def __init__(self, sample_rate: float, min_gain_db: float = -48.0, max_gain_db: float = 48.0,
+                 min_pan: float = 0.0, max_pan: float = 1.0):
+        super().__init__()
+        self.sample_rate = sample_rate
+        self.param_ranges = {"input_gain": {"gain_db": (min_gain_db, max_gain_db)},
+                             "stereo_panner": {"pan": (min_pan, max_pan)}}
+        self.num_track_control_params = 2
+        self.num_fx_bus_control_params = 0
+        self.num_master_bus_control_params = 0
+        self.materialize_tracks = True
+        self.check_ranges = True
+
+    def _c_ranges(self):
+        r = _lib.Ranges()
+        r.track_lo[0], r.track_hi[0] = self.param_ranges["input_gain"]["gain_db"]
+        r.track_lo[25], r.track_hi[25] = self.param_ranges["stereo_panner"]["pan"]
+        return r
+
+    def forward(self, tracks, track_params, fx_bus_params=None, master_bus_params=None, **flags):
+        if self.check_ranges:
+            lo = track_params.reshape(-1, 2).amin(0).detach().cpu()
+            hi = track_params.reshape(-1, 2).amax(0).detach().cpu()
+            for i, (effect, name) in enumerate((("input_gain", "gain_db"), ("stereo_panner", "pan"))):
+                if lo[i] < 0 or hi[i] > 1:
+                    raise ValueError(f"Parameter {name} of effect {effect} is out of range.")
+        pr = self.param_ranges
+        track_param_dict = {
+            "input_gain": {"gain_db": denormalize(track_params[..., 0], pr["input_gain"]["gain_db"][1],
+                                                  pr["input_gain"]["gain_db"][0])},
+            "stereo_panner": {"pan": denormalize(track_params[..., 1], pr["stereo_panner"]["pan"][1],
+                                                 pr["stereo_panner"]["pan"][0])}}
+        f = (_lib.BASIC_CONSOLE | _lib.USE_TRACK_INPUT_FADER | _lib.USE_TRACK_PANNER)
+        mix, mixed, _ = _ConsoleFunction.apply(tracks, track_params, None, self._c_ranges(),
+                                               self.sample_rate, f, 0, 0, self.materialize_tracks)
+        return mixed, mix, track_param_dict, {}, {}

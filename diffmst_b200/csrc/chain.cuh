@@ -1,0 +1,107 @@
+// Argument blocks and device helpers shared by the forward and backward chain kernels.
+//
+// A "row" is one mono track (NCH = 1, the per-track chain gain -> EQ -> compressor of
+// mst/modules.py:230-251) or one stereo master bus (NCH = 2, mst/modules.py:286-312, both
+// channels share coefficients and the compressor side-chain is their sum).  Time is cut
+// into tiles of NT*L samples; one CTA owns one (row, tile); thread t owns samples
+// [t*L, t*L+L) of the tile in registers.  Linear recurrences are solved exactly across
+// threads by a scan whose combine operator is a constant matrix power (tables in RowTab),
+// and across tiles by chaining CTAs through global memory (per-section wavefront).
+#pragma once
+#include "common.cuh"
+
+namespace dmst {
+
+constexpr int kStateStride = 32;   // floats per (row, tile): [sec][ch][2] (24) + smoother (1)
+constexpr int kStateSmooth = 24;
+constexpr int kTail2Stride = 32;   // floats per (row, tile): [stage 0..6][ch][2]
+constexpr int kFlagSmooth = 7;     // flag value meaning "EQ sections 1..6 and smoother published"
+
+struct ChainArgs {
+    // ---- geometry ----
+    int nrows;        // B*N (tracks) or B (master)
+    int N;            // tracks per batch item
+    int T;            // samples per row
+    int Tp;           // padded row length of internal scratch rows (multiple of 4)
+    int ntiles;
+    unsigned flags;   // kChain*
+    int lookahead;
+    int want_mixed;
+    int want_grad_src;
+    // ---- forward source / sinks ----
+    const float* src;            // tracks: caller's (B,N,T); master: y scratch (B*N, Tp)
+    long long src_batch_stride;  // elements
+    long long src_row_stride;
+    int src_vec_ok;
+    int user_vec_ok;             // user-owned outputs 16B-aligned with T % 4 == 0
+    const RowTab* tab;           // [nrows]
+    const RowTab* track_tab;     // master only: [B*N], pan gains
+    float* y;                    // tracks: (B*N, Tp) post-compressor mono scratch
+    float* mixed;                // tracks: caller's (B,2,N,T) or null
+    float* mix;                  // master: caller's (B,2,T)
+    float* bus_pre;              // master: (B*2, Tp) bus before the master chain
+    // ---- chain workspace (kept for backward) ----
+    int* ticket;
+    int* flag;                   // [nrows*ntiles]
+    float* state;                // [nrows*ntiles*kStateStride] end-of-tile states
+    float* tail2;                // [nrows*ntiles*kTail2Stride] last two samples of each stage
+    float* etail;                // [nrows*ntiles*NCH*lookahead] last `lookahead` EQ outputs
+    // ---- backward only ----
+    const float* gout;           // tracks: dbus (B*2, Tp); master: caller's grad_mix (B,2,T)
+    const float* gmixed;         // tracks: caller's grad of mixed_tracks (B,2,N,T) or null
+    float* gsrc;                 // tracks: caller's grad_tracks (B,N,T) or null; master: dbus (B*2,Tp)
+    float* partial;              // [nrows*ntiles*kGradCount]
+    int* bflag;                  // [nrows*ntiles] reverse-chain flags
+    float* bstate;               // [nrows*ntiles*kStateStride] reverse states at tile start
+    float* dhead;                // [nrows*ntiles*NCH*lookahead] first `lookahead` of dy*G
+};
+
+__device__ __forceinline__ void mat2_apply_acc(const float* m, float t1, float t2, float& s1, float& s2) {
+    s1 = fmaf(m[0], t1, fmaf(m[1], t2, s1));
+    s2 = fmaf(m[2], t1, fmaf(m[3], t2, s2));
+}
+// transposed matrix (reverse-time all-pole recursion uses A^T)
+__device__ __forceinline__ void mat2T_apply_acc(const float* m, float t1, float t2, float& s1, float& s2) {
+    s1 = fmaf(m[0], t1, fmaf(m[2], t2, s1));
+    s2 = fmaf(m[1], t1, fmaf(m[3], t2, s2));
+}
+
+// Load L consecutive floats starting at p[0] (global), zero beyond `valid` elements.
+template <int L>
+__device__ __forceinline__ void load_chunk(const float* p, int valid, bool vec_ok, float (&v)[L]) {
+    if (vec_ok && valid >= L) {
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < L / 4; ++i) {
+            float4 q = __ldg(p4 + i);
+            v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < L; ++i) v[i] = (i < valid) ? __ldg(p + i) : 0.0f;
+    }
+}
+template <int L>
+__device__ __forceinline__ void store_chunk(float* p, int valid, bool vec_ok, const float (&v)[L]) {
+    if (vec_ok && valid >= L) {
+        float4* p4 = reinterpret_cast<float4*>(p);
+#pragma unroll
+        for (int i = 0; i < L / 4; ++i) p4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < L; ++i)
+            if (i < valid) p[i] = v[i];
+    }
+}
+
+// Static-curve gain computer of the dasp compressor, branch-free:
+// t = x_db - (thr - knee/2); g_c = slope * (clamp(t,0,W)^2/(2W) + max(t-W,0)).
+__device__ __forceinline__ float gain_computer(float side, const RowTab& tb, float& tc, float& lin) {
+    float d = kDbPerLog2 * __log2f(fmaxf(fabsf(side), kCompEps));
+    float t = d - tb.thr_lo;
+    tc = fminf(fmaxf(t, 0.0f), tb.knee);
+    lin = fmaxf(t - tb.knee, 0.0f);
+    return tb.slope * fmaf(tc * tc, tb.inv_2knee, lin);
+}
+
+}  // namespace dmst

@@ -1,0 +1,118 @@
+// Shared definitions for the diffmst_b200 kernels (sm_100a).
+//
+// The same sources also compile with g++ -DDMST_EMULATE against tests/emul/cuda_emul.h,
+// which is test infrastructure for debugging kernel logic on a machine without a GPU.
+#pragma once
+
+#ifdef DMST_EMULATE
+#include "cuda_emul.h"
+#define DMST_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emul::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+#define DMST_DYN_SMEM(name) unsigned char* name = emul::dynamic_smem()
+#define DMST_DEVICE_BUILD 0
+#else
+#include <cuda_runtime.h>
+#define DMST_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define DMST_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define DMST_SHARED_ARRAY(type, name, count) __shared__ type name[count]
+#define DMST_DEVICE_BUILD 1
+#endif
+
+#include <stdint.h>
+
+namespace dmst {
+
+constexpr int kNumSections = 6;   // low_shelf, band0..3, high_shelf (mst/modules.py:124-143)
+constexpr int kMaxL = 32;         // samples per thread chunk upper bound
+constexpr float kDbPerLog2 = 6.020599913279624f;     // 20*log10(2)
+constexpr float kLog2Per20Db = 0.16609640474436813f;  // log2(10)/20
+constexpr float kLn10Over20 = 0.11512925464970229f;   // ln(10)/20
+constexpr float k20OverLn10 = 8.685889638065035f;     // 20/ln(10)
+constexpr float kCompEps = 1e-8f;                      // dasp compressor eps (Appendix A)
+
+// ---------------------------------------------------------------------------------
+// Per-row (track or master bus) table, produced in float64 by the prepare kernel and
+// stored as float32.  One per (row, chunk length L).
+//
+// A biquad section in transposed direct form II has the 2-vector state s and the
+// transition s' = A s + B x with A = [[-a1, 1], [-a2, 0]].  With each thread owning L
+// consecutive samples, P = A^L advances the state across one thread chunk:
+//   P2[j] = P^(2^j)  (warp Kogge-Stone steps),  Q = P^32 (across a warp),
+//   Ppow[l] = P^l    (warp carry-in -> lane carry-in).
+// Matrices are row-major {m00, m01, m10, m11}.
+// ---------------------------------------------------------------------------------
+struct SectionTab {
+    float b0, b1, b2, a1, a2, inv_b0, pad0, pad1;
+    float P2[5][4];
+    float Q[4];
+    float Ppow[32][4];
+};
+
+struct RowTab {
+    SectionTab sec[kNumSections];
+    // input gain (linear), output gain (linear; master only), pan gains (tracks only)
+    float g_in, g_out, gL, gR;
+    // compressor: y = x_delayed * 10^((g_s + makeup)/20)
+    float alpha, beta;      // one-pole smoother g_s[n] = beta*g_c[n] + alpha*g_s[n-1]
+    float thr_lo;           // threshold - knee/2
+    float knee, inv_knee, inv_2knee;
+    float slope;            // 1/ratio - 1
+    float makeup;
+    float inv_ratio2;       // 1/ratio^2 (backward)
+    float pad[3];
+    float a2pow[5];         // alpha^(L*2^j)
+    float aQ;               // alpha^(32 L)
+    float pad2[2];
+    float a_lane[32];       // alpha^(L*l)
+    float a_i[kMaxL];       // alpha^(i+1)
+};
+
+// Flags understood by the chain kernels
+constexpr unsigned kChainGain = 1u, kChainEq = 2u, kChainComp = 4u, kChainOutGain = 8u;
+
+// Gradient partial layout (per row, per tile), see console_bwd.cu
+constexpr int kGradEq = 0;        // 30 values: section*5 + {b0,b1,b2,a1,a2}
+constexpr int kGradAlpha = 30, kGradThr = 31, kGradRatio = 32, kGradKnee = 33, kGradMakeup = 34;
+constexpr int kGradGin = 35, kGradGout = 36, kGradGL = 37, kGradGR = 38;
+constexpr int kGradCount = 40;
+
+// ---------------------------------------------------------------------------------
+// Inter-CTA signalling (tile k waits for tile k-1 of the same row).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release(int* p, int v) {
+#ifdef DMST_EMULATE
+    reinterpret_cast<std::atomic<int>*>(p)->store(v, std::memory_order_release);
+#else
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+#ifdef DMST_EMULATE
+    return reinterpret_cast<const std::atomic<int>*>(p)->load(std::memory_order_acquire);
+#else
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void wait_flag_ge(const int* p, int v) {
+    while (ld_acquire(p) < v) {
+#ifndef DMST_EMULATE
+        __nanosleep(64);
+#else
+        __nanosleep(0);
+#endif
+    }
+}
+
+// padded shared-memory index: conflict-free when lane l touches element l*L + i
+__host__ __device__ __forceinline__ int pidx(int i) { return i + (i >> 5); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace dmst

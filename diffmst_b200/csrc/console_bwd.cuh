@@ -1,0 +1,516 @@
+// Backward chain kernel (adjoint of console_fwd.cuh), one CTA per (row, time tile), tiles
+// claimed in REVERSE time order.  Per tile it
+//   1. recomputes the forward chain from the tile carry-in states the forward pass left in
+//      the workspace (no forward chaining needed),
+//   2. runs the adjoint of the compressor (reverse one-pole recursion for the smoothed
+//      gain, piecewise derivatives of the static curve, look-ahead halo taken from the
+//      successor tile),
+//   3. runs the adjoint of each biquad section in reverse order: reverse-time all-pole
+//      recursion g = (1/A)^T u solved with the same matrix-power scan (transposed
+//      matrices), coefficient gradients db_j = sum g[n] x[n-j], da_j = -sum g[n] y[n-j] (accumulated in a
+//      differenced basis, see below),
+//      input gradient B^T g.  The section input x is recovered from its output with the
+//      inverse recursion that shares the section's state trajectory, so only two signals
+//      live in registers at a time,
+//   4. writes per-tile partial sums; console_prepare.cuh's epilogue chains them through the
+//      parameter Jacobian.
+// Gradient definitions follow the float64 autograd of the oracle (tests/golden).
+#pragma once
+#include "chain.cuh"
+
+namespace dmst {
+
+constexpr int kBFlagComp = 1;  // reverse smoother state + dhead published
+// section k (5..0) published <=> bflag >= 2 + (5 - k)
+
+template <int NCH, int L, int NT, bool MASTER>
+__global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
+    constexpr int NW = NT / 32;
+    constexpr int TILE = NT * L;
+    static_assert(L % 4 == 0 && L <= kMaxL, "chunk length");
+
+    DMST_DYN_SMEM(smem_raw);
+    DMST_SHARED_ARRAY(float, s_W, 8 * NW * NCH * 2);       // warp aggregates, slot 7 = reverse smoother
+    DMST_SHARED_ARRAY(float, s_nb, NW * NCH * 2);           // last two section-input samples of each warp
+    DMST_SHARED_ARRAY(float, s_in, 8 * NCH * 2);
+    DMST_SHARED_ARRAY(float, s_part, NW * kGradCount);
+    DMST_SHARED_ARRAY(int, s_ticket, 1);
+    DMST_SHARED_ARRAY(float, s_tabf, sizeof(RowTab) / 4);
+    const RowTab& tb = *reinterpret_cast<const RowTab*>(s_tabf);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket[0] = atomicAdd(a.ticket, 1);
+    __syncthreads();
+    const int ticket = s_ticket[0];
+    const int tile = a.ntiles - 1 - ticket / a.nrows;
+    const int row = ticket % a.nrows;
+    const int LA = a.lookahead;
+    const int buf_stride = pidx(LA + TILE) + 1;
+    float* ebuf = reinterpret_cast<float*>(smem_raw);          // [NCH][buf_stride]  e delay line
+    float* dbuf = ebuf + NCH * buf_stride;                      // [NCH][buf_stride]  dy*G, future halo
+    float* sE = dbuf + NCH * buf_stride;                        // [6*NCH*2][NT] forward lane carry-ins
+
+    {
+        const float* src = reinterpret_cast<const float*>(a.tab + row);
+        for (int i = tid; i < int(sizeof(RowTab) / 4); i += NT) s_tabf[i] = __ldg(src + i);
+        for (int i = tid; i < NW * kGradCount; i += NT) s_part[i] = 0.0f;
+    }
+    const int t0 = tile * TILE + tid * L;
+    const bool has_pred = tile > 0, has_succ = tile < a.ntiles - 1;
+    const long long rt = (long long)row * a.ntiles + tile;
+    const float* state_in = a.state + (rt - 1) * kStateStride;  // forward carry-in
+    const float* tail_in = a.tail2 + (rt - 1) * kTail2Stride;
+    float* bstate_out = a.bstate + rt * kStateStride;
+    const float* bstate_in = a.bstate + (rt + 1) * kStateStride;
+    int* my_flag = a.bflag + rt;
+    const int* succ_flag = my_flag + 1;
+
+    float v[NCH][L];
+    if constexpr (!MASTER) {
+        const int b = row / a.N, n = row - b * a.N;
+        load_chunk<L>(a.src + (long long)b * a.src_batch_stride + (long long)n * a.src_row_stride + t0,
+                      a.T - t0, a.src_vec_ok != 0, v[0]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+            load_chunk<L>(a.src + (long long)(row * NCH + c) * a.Tp + t0, a.Tp - t0, true, v[c]);
+    }
+    __syncthreads();
+    if (a.flags & kChainGain) {
+        const float g = tb.g_in;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < L; ++i) v[c][i] *= g;
+    }
+
+    // ---------------- forward recompute of the EQ cascade ----------------
+    if (a.flags & kChainEq) {
+#pragma unroll 1
+        for (int k = 0; k < kNumSections; ++k) {
+            const SectionTab& st = tb.sec[k];
+            const float b0 = st.b0, b1 = st.b1, b2 = st.b2, na1 = -st.a1, na2 = -st.a2;
+            float s1[NCH], s2[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float z1 = 0.0f, z2 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < L; ++i) {
+                    const float x = v[c][i];
+                    const float yv = fmaf(b0, x, z1);
+                    z1 = fmaf(b1, x, fmaf(na1, yv, z2));
+                    z2 = fmaf(b2, x, na2 * yv);
+                    v[c][i] = yv;
+                }
+                s1[c] = z1; s2[c] = z2;
+            }
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const float t1 = __shfl_up_sync(0xffffffffu, s1[c], 1 << j);
+                    const float t2 = __shfl_up_sync(0xffffffffu, s2[c], 1 << j);
+                    if (lane >= (1 << j)) mat2_apply_acc(st.P2[j], t1, t2, s1[c], s2[c]);
+                }
+            }
+            float e1[NCH], e2[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                e1[c] = __shfl_up_sync(0xffffffffu, s1[c], 1);
+                e2[c] = __shfl_up_sync(0xffffffffu, s2[c], 1);
+                if (lane == 0) { e1[c] = 0.0f; e2[c] = 0.0f; }
+                if (lane == 31) {
+                    s_W[((k * NW + warp) * NCH + c) * 2 + 0] = s1[c];
+                    s_W[((k * NW + warp) * NCH + c) * 2 + 1] = s2[c];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float c1 = has_pred ? __ldg(state_in + (k * NCH + c) * 2 + 0) : 0.0f;
+                float c2 = has_pred ? __ldg(state_in + (k * NCH + c) * 2 + 1) : 0.0f;
+                for (int u = 0; u < warp; ++u) {
+                    float n1 = s_W[((k * NW + u) * NCH + c) * 2 + 0], n2 = s_W[((k * NW + u) * NCH + c) * 2 + 1];
+                    mat2_apply_acc(st.Q, c1, c2, n1, n2);
+                    c1 = n1; c2 = n2;
+                }
+                mat2_apply_acc(st.Ppow[lane], c1, c2, e1[c], e2[c]);
+                sE[((k * NCH + c) * 2 + 0) * NT + tid] = e1[c];
+                sE[((k * NCH + c) * 2 + 1) * NT + tid] = e2[c];
+                float h1 = e1[c], h2 = e2[c];
+#pragma unroll
+                for (int i = 0; i < L; ++i) {
+                    const float t = h1;
+                    v[c][i] += t;
+                    h1 = fmaf(na1, t, h2);
+                    h2 = na2 * t;
+                }
+            }
+        }
+    }
+
+    // ---------------- upstream gradient w.r.t. the chain output ----------------
+    float u[NCH][L];
+    float acc_gout = 0.0f, acc_gl = 0.0f, acc_gr = 0.0f;
+    float dbl[L], dbr[L];
+    if constexpr (!MASTER) {
+        const int b = row / a.N, n = row - b * a.N;
+        load_chunk<L>(a.gout + (long long)(b * 2 + 0) * a.Tp + t0, a.Tp - t0, true, dbl);
+        load_chunk<L>(a.gout + (long long)(b * 2 + 1) * a.Tp + t0, a.Tp - t0, true, dbr);
+        if (a.gmixed) {
+            float t[L];
+            load_chunk<L>(a.gmixed + ((long long)(b * 2 + 0) * a.N + n) * a.T + t0, a.T - t0, a.user_vec_ok != 0, t);
+#pragma unroll
+            for (int i = 0; i < L; ++i) dbl[i] += t[i];
+            load_chunk<L>(a.gmixed + ((long long)(b * 2 + 1) * a.N + n) * a.T + t0, a.T - t0, a.user_vec_ok != 0, t);
+#pragma unroll
+            for (int i = 0; i < L; ++i) dbr[i] += t[i];
+        }
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            if (t0 + i >= a.T) { dbl[i] = 0.0f; dbr[i] = 0.0f; }
+            u[0][i] = fmaf(tb.gL, dbl[i], tb.gR * dbr[i]);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+            load_chunk<L>(a.gout + (long long)(row * NCH + c) * a.T + t0, a.T - t0, a.user_vec_ok != 0, u[c]);
+    }
+
+    float acc_comp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // alpha, thr, ratio, knee, makeup
+    if (a.flags & kChainComp) {
+        // ---- forward recompute: delay line, smoothed gain ----
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < L; ++i) ebuf[c * buf_stride + pidx(LA + tid * L + i)] = v[c][i];
+        {
+            const float* etail_in = a.etail + (rt - 1) * NCH * LA;
+            for (int idx = tid; idx < NCH * LA; idx += NT) {
+                const int c = idx / LA, j = idx - c * LA;
+                ebuf[c * buf_stride + pidx(j)] = has_pred ? __ldg(etail_in + idx) : 0.0f;
+            }
+        }
+        float gs[L];
+        float gz = 0.0f;
+        const float alpha = tb.alpha, beta = tb.beta;
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            float side = v[0][i];
+            if (NCH > 1) side += v[NCH - 1][i];
+            float tc, lin;
+            const float gc = gain_computer(side, tb, tc, lin);
+            gz = fmaf(alpha, gz, beta * gc);
+            gs[i] = gz;
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float t = __shfl_up_sync(0xffffffffu, gz, 1 << j);
+            if (lane >= (1 << j)) gz = fmaf(tb.a2pow[j], t, gz);
+        }
+        float ex = __shfl_up_sync(0xffffffffu, gz, 1);
+        if (lane == 0) ex = 0.0f;
+        if (lane == 31) s_W[(6 * NW + warp) * NCH * 2] = gz;
+        __syncthreads();  // ebuf + smoother aggregates visible
+        float cw = has_pred ? __ldg(state_in + kStateSmooth) : 0.0f;
+        for (int w = 0; w < warp; ++w) cw = fmaf(tb.aQ, cw, s_W[(6 * NW + w) * NCH * 2]);
+        const float gcarry = fmaf(tb.a_lane[lane], cw, ex);  // g_s just before this chunk
+#pragma unroll
+        for (int i = 0; i < L; ++i) gs[i] = fmaf(tb.a_i[i], gcarry, gs[i]);
+
+        // ---- adjoint: output -> (delayed signal path, gain path) ----
+        float q[L];
+        float* dhead_out = a.dhead + rt * NCH * LA;
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            const float G = exp2f(kLog2Per20Db * (gs[i] + tb.makeup));
+            float r = 0.0f;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float o = ebuf[c * buf_stride + pidx(tid * L + i)] * G;  // chain output (pre out-gain)
+                float dcomp = u[c][i];
+                if constexpr (MASTER) {
+                    if (a.flags & kChainOutGain) { acc_gout = fmaf(dcomp, o * tb.g_out, acc_gout); dcomp *= tb.g_out; }
+                } else {
+                    acc_gl = fmaf(dbl[i], o, acc_gl);
+                    acc_gr = fmaf(dbr[i], o, acc_gr);
+                }
+                r = fmaf(dcomp, o, r);
+                const float dyG = dcomp * G;
+                dbuf[c * buf_stride + pidx(tid * L + i)] = dyG;
+                if (tid * L + i < LA) dhead_out[c * LA + tid * L + i] = dyG;
+            }
+            q[i] = r * kLn10Over20;
+            acc_comp[4] += q[i];
+        }
+        // ---- reverse one-pole: p[n] = q[n] + alpha p[n+1] ----
+        float pz = 0.0f;
+#pragma unroll
+        for (int i = L - 1; i >= 0; --i) { pz = fmaf(alpha, pz, q[i]); q[i] = pz; }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float t = __shfl_down_sync(0xffffffffu, pz, 1 << j);
+            if (lane + (1 << j) < 32) pz = fmaf(tb.a2pow[j], t, pz);
+        }
+        float px = __shfl_down_sync(0xffffffffu, pz, 1);
+        if (lane == 31) px = 0.0f;
+        if (lane == 0) s_W[(7 * NW + warp) * NCH * 2] = pz;
+        if (tid == 0) {
+            if (has_succ) {
+                wait_flag_ge(succ_flag, kBFlagComp);
+                s_in[7 * NCH * 2] = __ldcg(bstate_in + kStateSmooth);
+            } else {
+                s_in[7 * NCH * 2] = 0.0f;
+            }
+        }
+        __syncthreads();  // dbuf (own tile), reverse aggregates, successor state visible
+        float pc = s_in[7 * NCH * 2];
+        for (int w = NW - 1; w > warp; --w) pc = fmaf(tb.aQ, pc, s_W[(7 * NW + w) * NCH * 2]);
+        if (tid == 0) {
+            bstate_out[kStateSmooth] = fmaf(tb.aQ, pc, s_W[(7 * NW + 0) * NCH * 2]);
+            __threadfence();  // also orders every thread's dhead stores (made before the barrier)
+            st_release(my_flag, kBFlagComp);
+        }
+        const float pcarry = fmaf(tb.a_lane[31 - lane], pc, px);  // p at the first sample after this chunk
+        // halo of dy*G from the successor tile
+        {
+            const float* dhead_in = a.dhead + (rt + 1) * NCH * LA;
+            for (int idx = tid; idx < NCH * LA; idx += NT) {
+                const int c = idx / LA, j = idx - c * LA;
+                dbuf[c * buf_stride + pidx(TILE + j)] = has_succ ? __ldcg(dhead_in + idx) : 0.0f;
+            }
+        }
+        __syncthreads();
+        float gprev = gcarry;
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            const float p = fmaf(tb.a_i[L - 1 - i], pcarry, q[i]);
+            float side = v[0][i];
+            if (NCH > 1) side += v[NCH - 1][i];
+            float tc, lin;
+            const float gc = gain_computer(side, tb, tc, lin);
+            acc_comp[0] = fmaf(p, gprev - gc, acc_comp[0]);
+            gprev = gs[i];
+            const float dgc = beta * p;
+            const float dcurve = tb.slope * tc * tb.inv_knee;                 // d g_c / d x_db
+            acc_comp[1] = fmaf(dgc, -dcurve, acc_comp[1]);                    // threshold
+            acc_comp[2] = fmaf(dgc, -fmaf(tc * tc, tb.inv_2knee, lin) * tb.inv_ratio2, acc_comp[2]);  // ratio
+            acc_comp[3] = fmaf(dgc, tb.slope * tc * tb.inv_2knee * (1.0f - tc * tb.inv_knee), acc_comp[3]);  // knee
+            const float dside = (fabsf(side) > kCompEps) ? dgc * dcurve * k20OverLn10 / side : 0.0f;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) u[c][i] = dbuf[c * buf_stride + pidx(tid * L + i + LA)] + dside;
+        }
+    } else {
+        // no compressor: chain output = EQ output
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if constexpr (MASTER) {
+                    if (a.flags & kChainOutGain) { acc_gout = fmaf(u[c][i], v[c][i] * tb.g_out, acc_gout); u[c][i] *= tb.g_out; }
+                } else {
+                    acc_gl = fmaf(dbl[i], v[c][i], acc_gl);
+                    acc_gr = fmaf(dbr[i], v[c][i], acc_gr);
+                }
+            }
+        }
+    }
+    {
+        float t;
+        t = warp_sum(acc_comp[0]); if (lane == 0) s_part[warp * kGradCount + kGradAlpha] = t;
+        t = warp_sum(acc_comp[1]); if (lane == 0) s_part[warp * kGradCount + kGradThr] = t;
+        t = warp_sum(acc_comp[2]); if (lane == 0) s_part[warp * kGradCount + kGradRatio] = t;
+        t = warp_sum(acc_comp[3]); if (lane == 0) s_part[warp * kGradCount + kGradKnee] = t;
+        t = warp_sum(acc_comp[4]); if (lane == 0) s_part[warp * kGradCount + kGradMakeup] = t;
+        t = warp_sum(acc_gout); if (lane == 0) s_part[warp * kGradCount + kGradGout] = t;
+        t = warp_sum(acc_gl); if (lane == 0) s_part[warp * kGradCount + kGradGL] = t;
+        t = warp_sum(acc_gr); if (lane == 0) s_part[warp * kGradCount + kGradGR] = t;
+    }
+
+    // ---------------- adjoint of the EQ cascade, sections 5..0 ----------------
+    if (a.flags & kChainEq) {
+        // y[n-1], y[n-2] at the chunk start for the last section's output
+        float ym1[NCH], ym2[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            ym1[c] = __shfl_up_sync(0xffffffffu, v[c][L - 1], 1);
+            ym2[c] = __shfl_up_sync(0xffffffffu, v[c][L - 2], 1);
+            if (lane == 31) { s_nb[(warp * NCH + c) * 2 + 0] = v[c][L - 1]; s_nb[(warp * NCH + c) * 2 + 1] = v[c][L - 2]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            if (lane == 0) {
+                if (warp > 0) { ym1[c] = s_nb[((warp - 1) * NCH + c) * 2 + 0]; ym2[c] = s_nb[((warp - 1) * NCH + c) * 2 + 1]; }
+                else if (has_pred) { ym1[c] = __ldg(tail_in + (6 * NCH + c) * 2 + 1); ym2[c] = __ldg(tail_in + (6 * NCH + c) * 2 + 0); }
+                else { ym1[c] = 0.0f; ym2[c] = 0.0f; }
+            }
+        }
+        __syncthreads();  // s_nb is rewritten per section below
+
+#pragma unroll 1
+        for (int k = kNumSections - 1; k >= 0; --k) {
+            const SectionTab& st = tb.sec[k];
+            const float b0 = st.b0, b1 = st.b1, b2 = st.b2, na1 = -st.a1, na2 = -st.a2, inv_b0 = st.inv_b0;
+            float xin[NCH][L];
+            float r1[NCH], r2[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                // (a) recover the section input from its output along the shared state trajectory
+                float s1 = sE[((k * NCH + c) * 2 + 0) * NT + tid], s2 = sE[((k * NCH + c) * 2 + 1) * NT + tid];
+#pragma unroll
+                for (int i = 0; i < L; ++i) {
+                    const float yv = v[c][i];
+                    const float x = (yv - s1) * inv_b0;
+                    s1 = fmaf(b1, x, fmaf(na1, yv, s2));
+                    s2 = fmaf(b2, x, na2 * yv);
+                    xin[c][i] = x;
+                }
+                if (lane == 31) { s_nb[(warp * NCH + c) * 2 + 0] = xin[c][L - 1]; s_nb[(warp * NCH + c) * 2 + 1] = xin[c][L - 2]; }
+                // (b) reverse-time all-pole recursion, zero right-hand state
+                float g1 = 0.0f, g2 = 0.0f;
+#pragma unroll
+                for (int i = L - 1; i >= 0; --i) {
+                    const float gh = fmaf(na1, g1, fmaf(na2, g2, u[c][i]));
+                    g2 = g1; g1 = gh;
+                    u[c][i] = gh;
+                }
+                r1[c] = g1; r2[c] = g2;
+            }
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const float t1 = __shfl_down_sync(0xffffffffu, r1[c], 1 << j);
+                    const float t2 = __shfl_down_sync(0xffffffffu, r2[c], 1 << j);
+                    if (lane + (1 << j) < 32) mat2T_apply_acc(st.P2[j], t1, t2, r1[c], r2[c]);
+                }
+            }
+            float x1[NCH], x2[NCH], xm1[NCH], xm2[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                x1[c] = __shfl_down_sync(0xffffffffu, r1[c], 1);
+                x2[c] = __shfl_down_sync(0xffffffffu, r2[c], 1);
+                if (lane == 31) { x1[c] = 0.0f; x2[c] = 0.0f; }
+                if (lane == 0) {
+                    s_W[((k * NW + warp) * NCH + c) * 2 + 0] = r1[c];
+                    s_W[((k * NW + warp) * NCH + c) * 2 + 1] = r2[c];
+                }
+                xm1[c] = __shfl_up_sync(0xffffffffu, xin[c][L - 1], 1);
+                xm2[c] = __shfl_up_sync(0xffffffffu, xin[c][L - 2], 1);
+            }
+            const int need = 2 + (kNumSections - 1 - k);
+            if (tid == 0) {
+                if (has_succ) {
+                    wait_flag_ge(succ_flag, need);
+#pragma unroll
+                    for (int qq = 0; qq < NCH * 2; ++qq) s_in[k * NCH * 2 + qq] = __ldcg(bstate_in + k * NCH * 2 + qq);
+                } else {
+#pragma unroll
+                    for (int qq = 0; qq < NCH * 2; ++qq) s_in[k * NCH * 2 + qq] = 0.0f;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                // warp right-carry: C_{NW-1} = successor tile state, C_w = W_{w+1} + Q^T C_{w+1}
+                float c1 = s_in[(k * NCH + c) * 2 + 0], c2 = s_in[(k * NCH + c) * 2 + 1];
+                for (int w = NW - 1; w > warp; --w) {
+                    float n1 = s_W[((k * NW + w) * NCH + c) * 2 + 0], n2 = s_W[((k * NW + w) * NCH + c) * 2 + 1];
+                    mat2T_apply_acc(st.Q, c1, c2, n1, n2);
+                    c1 = n1; c2 = n2;
+                }
+                if (tid == 0) {
+                    float n1 = s_W[((k * NW + 0) * NCH + c) * 2 + 0], n2 = s_W[((k * NW + 0) * NCH + c) * 2 + 1];
+                    mat2T_apply_acc(st.Q, c1, c2, n1, n2);
+                    bstate_out[(k * NCH + c) * 2 + 0] = n1;
+                    bstate_out[(k * NCH + c) * 2 + 1] = n2;
+                }
+                mat2T_apply_acc(st.Ppow[31 - lane], c1, c2, x1[c], x2[c]);  // (g[L], g[L+1]) of this chunk
+                if (lane == 0) {
+                    if (warp > 0) { xm1[c] = s_nb[((warp - 1) * NCH + c) * 2 + 0]; xm2[c] = s_nb[((warp - 1) * NCH + c) * 2 + 1]; }
+                    else if (has_pred) { xm1[c] = __ldg(tail_in + (k * NCH + c) * 2 + 1); xm2[c] = __ldg(tail_in + (k * NCH + c) * 2 + 0); }
+                    else { xm1[c] = 0.0f; xm2[c] = 0.0f; }
+                }
+            }
+            if (tid == 0) {  // publish before the heavy part so the predecessor tile can proceed
+                __threadfence();
+                st_release(my_flag, need);
+            }
+            float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                // add the homogeneous reverse response, then FIR B^T and the correlations
+                float h1 = x1[c], h2 = x2[c];
+#pragma unroll
+                for (int i = L - 1; i >= 0; --i) {
+                    const float t = fmaf(na1, h1, na2 * h2);
+                    u[c][i] += t;
+                    h2 = h1; h1 = t;
+                }
+                float gp1 = x1[c], gp2 = x2[c];  // g[i+1], g[i+2]
+#pragma unroll
+                for (int i = L - 1; i >= 0; --i) {
+                    const float gh = u[c][i];
+                    const float xa = xin[c][i];
+                    const float xb = (i >= 1) ? xin[c][i - 1] : xm1[c];
+                    const float xc = (i >= 2) ? xin[c][i - 2] : (i == 1 ? xm1[c] : xm2[c]);
+                    const float ya = (i >= 1) ? v[c][i - 1] : ym1[c];
+                    const float yb = (i >= 2) ? v[c][i - 2] : (i == 1 ? ym1[c] : ym2[c]);
+                    // Coefficient gradients in the basis r0 = b0+b1+b2, r1 = b1+2 b2, r2 = b2,
+                    // p = a1+a2, q = a2: for poles/zeros near z = 1 the plain (b, a) gradients
+                    // are huge and cancel in the parameter Jacobian; differencing the signals
+                    // per sample before accumulating keeps float32 sums well conditioned.
+                    acc[0] = fmaf(gh, xa, acc[0]);
+                    acc[1] = fmaf(gh, xb - xa, acc[1]);
+                    acc[2] = fmaf(gh, (xa - xb) - (xb - xc), acc[2]);
+                    acc[3] = fmaf(-gh, ya, acc[3]);
+                    acc[4] = fmaf(-gh, yb - ya, acc[4]);
+                    u[c][i] = fmaf(b0, gh, fmaf(b1, gp1, b2 * gp2));
+                    gp2 = gp1; gp1 = gh;
+                }
+#pragma unroll
+                for (int i = 0; i < L; ++i) v[c][i] = xin[c][i];
+                ym1[c] = xm1[c]; ym2[c] = xm2[c];
+            }
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float t = warp_sum(acc[j]);
+                if (lane == 0) s_part[warp * kGradCount + kGradEq + 5 * k + j] = t;
+            }
+            __syncthreads();  // s_nb / s_in reuse by the next section
+        }
+    }
+
+    // ---------------- input gain and source gradient ----------------
+    {
+        float acc_gin = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < L; ++i) acc_gin = fmaf(u[c][i], v[c][i], acc_gin);
+        const float t = warp_sum(acc_gin);
+        if (lane == 0) s_part[warp * kGradCount + kGradGin] = t;
+        const float g = (a.flags & kChainGain) ? tb.g_in : 1.0f;
+        if constexpr (MASTER) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                for (int i = 0; i < L; ++i) u[c][i] *= g;
+                store_chunk<L>(a.gsrc + (long long)(row * NCH + c) * a.Tp + t0, a.Tp - t0, true, u[c]);
+            }
+        } else if (a.gsrc) {
+#pragma unroll
+            for (int i = 0; i < L; ++i) u[0][i] *= g;
+            store_chunk<L>(a.gsrc + (long long)row * a.T + t0, a.T - t0, a.user_vec_ok != 0, u[0]);
+        }
+    }
+    __syncthreads();
+    if (tid < kGradCount) {
+        float s = 0.0f;
+        for (int w = 0; w < NW; ++w) s += s_part[w * kGradCount + tid];
+        a.partial[rt * kGradCount + tid] = s;
+    }
+}
+
+}  // namespace dmst

@@ -1,0 +1,292 @@
+// Forward chain kernel: gain -> 6-section biquad cascade -> compressor (-> output gain),
+// one CTA per (row, time tile).  Replaces the dasp_pytorch calls at mst/modules.py:230-251
+// (tracks, NCH = 1) and :286-312 (master bus, NCH = 2, fed by the pan + bus sum of
+// :262-272).  See chain.cuh for the decomposition.
+#pragma once
+#include "chain.cuh"
+
+namespace dmst {
+
+template <int NCH, int L, int NT, bool MASTER>
+__global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
+    constexpr int NW = NT / 32;
+    constexpr int TILE = NT * L;
+    static_assert(L % 4 == 0 && L <= kMaxL, "chunk length");
+
+    DMST_DYN_SMEM(smem_raw);
+    float* ebuf = reinterpret_cast<float*>(smem_raw);  // [NCH][pidx(LA + TILE) + 1]
+    DMST_SHARED_ARRAY(float, s_W, 7 * NW * NCH * 2);
+    DMST_SHARED_ARRAY(float, s_in, 7 * NCH * 2);
+    DMST_SHARED_ARRAY(int, s_ticket, 1);
+    DMST_SHARED_ARRAY(float, s_tabf, sizeof(RowTab) / 4);
+    const RowTab& tb = *reinterpret_cast<const RowTab*>(s_tabf);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // Tiles are claimed in time-major order so that the predecessor tile of any running
+    // CTA has already been claimed by a CTA that is running or finished (no deadlock).
+    if (tid == 0) s_ticket[0] = atomicAdd(a.ticket, 1);
+    __syncthreads();
+    const int ticket = s_ticket[0];
+    const int tile = ticket / a.nrows;
+    const int row = ticket - tile * a.nrows;
+    const int LA = a.lookahead;
+    const int ebuf_stride = pidx(LA + TILE) + 1;
+
+    {
+        const float* src = reinterpret_cast<const float*>(a.tab + row);
+        for (int i = tid; i < int(sizeof(RowTab) / 4); i += NT) s_tabf[i] = __ldg(src + i);
+    }
+
+    const int t0 = tile * TILE + tid * L;  // first sample of this thread's chunk
+    float v[NCH][L];
+
+    if constexpr (!MASTER) {
+        const int b = row / a.N, n = row - b * a.N;
+        const float* p = a.src + (long long)b * a.src_batch_stride + (long long)n * a.src_row_stride + t0;
+        load_chunk<L>(p, a.T - t0, a.src_vec_ok != 0, v[0]);
+    } else {
+        // pan + bus sum (mst/modules.py:262-272): bus_c = sum_n g_c[n] * y[n]
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < L; ++i) v[c][i] = 0.0f;
+        for (int n = 0; n < a.N; ++n) {
+            const int trow = row * a.N + n;
+            const float gl = __ldg(&a.track_tab[trow].gL), gr = __ldg(&a.track_tab[trow].gR);
+            float yv[L];
+            load_chunk<L>(a.src + (long long)trow * a.Tp + t0, a.Tp - t0, true, yv);
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+                v[0][i] = fmaf(gl, yv[i], v[0][i]);
+                if (NCH > 1) v[NCH - 1][i] = fmaf(gr, yv[i], v[NCH - 1][i]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+            store_chunk<L>(a.bus_pre + (long long)(row * NCH + c) * a.Tp + t0, a.Tp - t0, true, v[c]);
+    }
+    __syncthreads();  // table in shared memory
+
+    float* tail2 = a.tail2 + ((long long)row * a.ntiles + tile) * kTail2Stride;
+    float* state_out = a.state + ((long long)row * a.ntiles + tile) * kStateStride;
+    const float* state_in = a.state + ((long long)row * a.ntiles + tile - 1) * kStateStride;
+    int* my_flag = a.flag + (long long)row * a.ntiles + tile;
+    const int* pred_flag = my_flag - 1;
+
+    if (a.flags & kChainGain) {
+        const float g = tb.g_in;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < L; ++i) v[c][i] *= g;
+    }
+    if (tid == NT - 1) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            tail2[(0 * NCH + c) * 2 + 0] = v[c][L - 2];
+            tail2[(0 * NCH + c) * 2 + 1] = v[c][L - 1];
+        }
+    }
+
+    // ------------------------------ EQ cascade ------------------------------
+    if (a.flags & kChainEq) {
+#pragma unroll 1
+        for (int k = 0; k < kNumSections; ++k) {
+            const SectionTab& st = tb.sec[k];
+            const float b0 = st.b0, b1 = st.b1, b2 = st.b2, na1 = -st.a1, na2 = -st.a2;
+            float s1[NCH], s2[NCH];
+            // zero-state pass over the thread chunk (transposed direct form II)
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float z1 = 0.0f, z2 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < L; ++i) {
+                    const float x = v[c][i];
+                    const float yv = fmaf(b0, x, z1);
+                    z1 = fmaf(b1, x, fmaf(na1, yv, z2));
+                    z2 = fmaf(b2, x, na2 * yv);
+                    v[c][i] = yv;
+                }
+                s1[c] = z1; s2[c] = z2;
+            }
+            // warp inclusive scan of end states, combine operator = P^(2^j)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float* m = st.P2[j];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const float t1 = __shfl_up_sync(0xffffffffu, s1[c], 1 << j);
+                    const float t2 = __shfl_up_sync(0xffffffffu, s2[c], 1 << j);
+                    if (lane >= (1 << j)) mat2_apply_acc(m, t1, t2, s1[c], s2[c]);
+                }
+            }
+            float e1[NCH], e2[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                e1[c] = __shfl_up_sync(0xffffffffu, s1[c], 1);
+                e2[c] = __shfl_up_sync(0xffffffffu, s2[c], 1);
+                if (lane == 0) { e1[c] = 0.0f; e2[c] = 0.0f; }
+                if (lane == 31) {
+                    s_W[((k * NW + warp) * NCH + c) * 2 + 0] = s1[c];
+                    s_W[((k * NW + warp) * NCH + c) * 2 + 1] = s2[c];
+                }
+            }
+            if (tid == 0) {
+                if (tile > 0) {
+                    wait_flag_ge(pred_flag, k + 1);
+#pragma unroll
+                    for (int q = 0; q < NCH * 2; ++q) s_in[k * NCH * 2 + q] = __ldcg(state_in + k * NCH * 2 + q);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NCH * 2; ++q) s_in[k * NCH * 2 + q] = 0.0f;
+                }
+            }
+            __syncthreads();
+            // warp carry-in: C_0 = tile carry-in, C_{w+1} = Q C_w + W_w
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float c1 = s_in[(k * NCH + c) * 2 + 0], c2 = s_in[(k * NCH + c) * 2 + 1];
+                for (int u = 0; u < warp; ++u) {
+                    float n1 = s_W[((k * NW + u) * NCH + c) * 2 + 0], n2 = s_W[((k * NW + u) * NCH + c) * 2 + 1];
+                    mat2_apply_acc(st.Q, c1, c2, n1, n2);
+                    c1 = n1; c2 = n2;
+                }
+                if (warp == NW - 1 && lane == 0) {
+                    float n1 = s_W[((k * NW + warp) * NCH + c) * 2 + 0], n2 = s_W[((k * NW + warp) * NCH + c) * 2 + 1];
+                    mat2_apply_acc(st.Q, c1, c2, n1, n2);
+                    state_out[(k * NCH + c) * 2 + 0] = n1;
+                    state_out[(k * NCH + c) * 2 + 1] = n2;
+                }
+                // lane carry-in = exclusive prefix + P^lane * C_w
+                mat2_apply_acc(st.Ppow[lane], c1, c2, e1[c], e2[c]);
+            }
+            if (warp == NW - 1 && lane == 0) {
+                __threadfence();
+                st_release(my_flag, k + 1);
+            }
+            // add the homogeneous response to the carried-in state
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float h1 = e1[c], h2 = e2[c];
+#pragma unroll
+                for (int i = 0; i < L; ++i) {
+                    const float t = h1;
+                    v[c][i] += t;
+                    h1 = fmaf(na1, t, h2);
+                    h2 = na2 * t;
+                }
+            }
+            if (tid == NT - 1) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    tail2[((k + 1) * NCH + c) * 2 + 0] = v[c][L - 2];
+                    tail2[((k + 1) * NCH + c) * 2 + 1] = v[c][L - 1];
+                }
+            }
+        }
+    }
+
+    // ------------------------------ compressor ------------------------------
+    if (a.flags & kChainComp) {
+        // EQ output into the delay line; its last LA samples go to the successor tile.
+        float* etail_out = a.etail + ((long long)row * a.ntiles + tile) * NCH * LA;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int i = 0; i < L; ++i) ebuf[c * ebuf_stride + pidx(LA + tid * L + i)] = v[c][i];
+            const int off = tid * L - (TILE - LA);
+            if (off >= 0) store_chunk<L>(etail_out + c * LA + off, L, (LA & 3) == 0, v[c]);
+            else if (off + L > 0) {
+#pragma unroll
+                for (int i = 0; i < L; ++i)
+                    if (off + i >= 0) etail_out[c * LA + off + i] = v[c][i];
+            }
+        }
+        // side-chain level -> static gain curve -> zero-state one-pole smoothing
+        float g[L];
+        float gs = 0.0f;
+        {
+            const float alpha = tb.alpha, beta = tb.beta;
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+                float side = v[0][i];
+                if (NCH > 1) side += v[NCH - 1][i];
+                float tc, lin;
+                const float gc = gain_computer(side, tb, tc, lin);
+                gs = fmaf(alpha, gs, beta * gc);
+                g[i] = gs;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float t = __shfl_up_sync(0xffffffffu, gs, 1 << j);
+            if (lane >= (1 << j)) gs = fmaf(tb.a2pow[j], t, gs);
+        }
+        float ex = __shfl_up_sync(0xffffffffu, gs, 1);
+        if (lane == 0) ex = 0.0f;
+        if (lane == 31) s_W[(6 * NW + warp) * NCH * 2] = gs;
+        if (tid == 0) {
+            if (tile > 0) {
+                wait_flag_ge(pred_flag, kFlagSmooth);
+                s_in[6 * NCH * 2] = __ldcg(state_in + kStateSmooth);
+            } else {
+                s_in[6 * NCH * 2] = 0.0f;
+            }
+        }
+        __syncthreads();
+        float cw = s_in[6 * NCH * 2];
+        for (int u = 0; u < warp; ++u) cw = fmaf(tb.aQ, cw, s_W[(6 * NW + u) * NCH * 2]);
+        if (warp == NW - 1 && lane == 0) {
+            state_out[kStateSmooth] = fmaf(tb.aQ, cw, s_W[(6 * NW + warp) * NCH * 2]);
+            __threadfence();  // also orders every thread's etail stores (made before the barrier)
+            st_release(my_flag, kFlagSmooth);
+        }
+        const float carry = fmaf(tb.a_lane[lane], cw, ex);
+        // halo: predecessor's last LA EQ outputs (zeros before the start of the signal)
+        {
+            const float* etail_in = a.etail + ((long long)row * a.ntiles + tile - 1) * NCH * LA;
+            for (int idx = tid; idx < NCH * LA; idx += NT) {
+                const int c = idx / LA, j = idx - c * LA;
+                ebuf[c * ebuf_stride + pidx(j)] = (tile > 0) ? __ldcg(etail_in + idx) : 0.0f;
+            }
+        }
+        __syncthreads();
+        const float makeup = tb.makeup;
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            const float gtrue = fmaf(tb.a_i[i], carry, g[i]);
+            const float G = exp2f(kLog2Per20Db * (gtrue + makeup));
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) v[c][i] = ebuf[c * ebuf_stride + pidx(tid * L + i)] * G;
+        }
+    }
+
+    // ------------------------------ sinks ------------------------------
+    if constexpr (!MASTER) {
+        store_chunk<L>(a.y + (long long)row * a.Tp + t0, a.Tp - t0, true, v[0]);
+        if (a.want_mixed) {
+            const int b = row / a.N, n = row - b * a.N;
+            float o[L];
+#pragma unroll
+            for (int i = 0; i < L; ++i) o[i] = tb.gL * v[0][i];
+            store_chunk<L>(a.mixed + ((long long)(b * 2 + 0) * a.N + n) * a.T + t0, a.T - t0, a.user_vec_ok != 0, o);
+#pragma unroll
+            for (int i = 0; i < L; ++i) o[i] = tb.gR * v[0][i];
+            store_chunk<L>(a.mixed + ((long long)(b * 2 + 1) * a.N + n) * a.T + t0, a.T - t0, a.user_vec_ok != 0, o);
+        }
+    } else {
+        if (a.flags & kChainOutGain) {
+            const float go = tb.g_out;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int i = 0; i < L; ++i) v[c][i] *= go;
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+            store_chunk<L>(a.mix + (long long)(row * NCH + c) * a.T + t0, a.T - t0, a.user_vec_ok != 0, v[c]);
+    }
+}
+
+}  // namespace dmst

@@ -1,0 +1,287 @@
+// Host-side launch logic of the mix console behind the C ABI (include/diffmst_b200.h).
+#pragma once
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/diffmst_b200.h"
+#include "console_bwd.cuh"
+#include "console_fwd.cuh"
+#include "console_prepare.cuh"
+
+namespace dmst {
+
+// Tile geometry.  Forward and backward must agree on NT*L per row kind because backward
+// restarts each tile from the carry-in states the forward pass saved.
+constexpr int kTrackL = 16, kTrackNT = 256;     // 4096-sample tiles
+constexpr int kMasterL = 16, kMasterNT = 256;   // 4096-sample tiles, 2 channels per thread
+constexpr int kTrackTile = kTrackL * kTrackNT;
+constexpr int kMasterTile = kMasterL * kMasterNT;
+
+#ifdef DMST_EMULATE
+#define DMST_MEMSET_ASYNC(ptr, val, bytes, stream) (memset((ptr), (val), (bytes)), 0)
+#define DMST_LAST_ERROR() 0
+#define DMST_SET_SMEM(kernel, bytes) 0
+#else
+#define DMST_MEMSET_ASYNC(ptr, val, bytes, stream) (int)cudaMemsetAsync((ptr), (val), (bytes), (stream))
+#define DMST_LAST_ERROR() (int)cudaGetLastError()
+#define DMST_SET_SMEM(kernel, bytes) \
+    (int)cudaFuncSetAttribute((kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#endif
+
+struct Carver {
+    unsigned char* base;
+    size_t off;
+    template <class T>
+    T* take(size_t count) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct ConsoleWs {
+    int* header;          // [0..3] tickets (fwd track, fwd master, bwd master, bwd track)
+    RowTab *track_tab, *master_tab;
+    float *y, *bus_pre, *dbus;
+    // forward chain (kept for backward)
+    int *t_flag, *m_flag;
+    float *t_state, *m_state, *t_tail2, *m_tail2, *t_etail, *m_etail;
+    // backward chain
+    int *t_bflag, *m_bflag;
+    float *t_bstate, *m_bstate, *t_dhead, *m_dhead, *t_partial, *m_partial;
+    size_t flags_begin, flags_end;    // byte range of forward flags (zeroed per forward)
+    size_t bflags_begin, bflags_end;  // byte range of backward flags
+    int Tp, nt_track, nt_master;
+    size_t total;
+};
+
+inline ConsoleWs carve_console(void* base, int B, int N, int T, int la_t, int la_m) {
+    ConsoleWs w;
+    Carver c{reinterpret_cast<unsigned char*>(base), 0};
+    w.Tp = (T + 3) & ~3;
+    w.nt_track = (T + kTrackTile - 1) / kTrackTile;
+    w.nt_master = (T + kMasterTile - 1) / kMasterTile;
+    const size_t rows = (size_t)B * N, rt = rows * w.nt_track, rm = (size_t)B * w.nt_master;
+    w.header = c.take<int>(64);
+    w.track_tab = c.take<RowTab>(rows);
+    w.master_tab = c.take<RowTab>(B);
+    w.y = c.take<float>(rows * w.Tp);
+    w.bus_pre = c.take<float>((size_t)B * 2 * w.Tp);
+    w.dbus = c.take<float>((size_t)B * 2 * w.Tp);
+    w.flags_begin = (c.off + 255) & ~size_t(255);
+    w.t_flag = c.take<int>(rt);
+    w.m_flag = c.take<int>(rm);
+    w.flags_end = c.off;
+    w.bflags_begin = (c.off + 255) & ~size_t(255);
+    w.t_bflag = c.take<int>(rt);
+    w.m_bflag = c.take<int>(rm);
+    w.bflags_end = c.off;
+    w.t_state = c.take<float>(rt * kStateStride);
+    w.m_state = c.take<float>(rm * kStateStride);
+    w.t_tail2 = c.take<float>(rt * kTail2Stride);
+    w.m_tail2 = c.take<float>(rm * kTail2Stride);
+    w.t_etail = c.take<float>(rt * (size_t)la_t + 4);
+    w.m_etail = c.take<float>(rm * 2 * (size_t)la_m + 4);
+    w.t_bstate = c.take<float>(rt * kStateStride);
+    w.m_bstate = c.take<float>(rm * kStateStride);
+    w.t_dhead = c.take<float>(rt * (size_t)la_t + 4);
+    w.m_dhead = c.take<float>(rm * 2 * (size_t)la_m + 4);
+    w.t_partial = c.take<float>(rt * kGradCount);
+    w.m_partial = c.take<float>(rm * kGradCount);
+    w.total = (c.off + 255) & ~size_t(255);
+    return w;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+inline unsigned track_chain_flags(unsigned f) {
+    unsigned c = 0;
+    if (f & DMST_USE_TRACK_INPUT_FADER) c |= kChainGain;
+    if (!(f & DMST_BASIC_CONSOLE)) {
+        if (f & DMST_USE_TRACK_EQ) c |= kChainEq;
+        if (f & DMST_USE_TRACK_COMPRESSOR) c |= kChainComp;
+    }
+    return c;
+}
+inline unsigned master_chain_flags(unsigned f) {
+    unsigned c = 0;
+    if (f & DMST_BASIC_CONSOLE) return 0;
+    if (f & DMST_USE_MASTER_BUS) c |= kChainGain | kChainEq | kChainComp;
+    if (f & DMST_USE_OUTPUT_FADER) c |= kChainOutGain;
+    return c;
+}
+
+inline size_t fwd_smem_bytes(int nch, int tile, int la) { return (size_t)nch * (pidx(la + tile) + 1) * 4; }
+inline size_t bwd_smem_bytes(int nch, int tile, int la, int nt) {
+    return (size_t)(2 * nch * (pidx(la + tile) + 1) + 12 * nch * nt) * 4;
+}
+
+struct ConsoleCall {
+    const float* tracks; long long tbs, trs;
+    const float* track_params; const float* master_params;
+    const dmst_ranges* ranges; float sr;
+    int B, N, T; unsigned flags; int la_t, la_m;
+};
+
+inline int check_call(const ConsoleCall& k) {
+    if (!k.tracks || !k.track_params || !k.ranges) return DMST_EINVAL;
+    if (k.B <= 0 || k.N <= 0 || k.T <= 0) return DMST_EINVAL;
+    if (k.flags & DMST_USE_FX_BUS) return DMST_EINVAL;              // out of scope
+    if (!(k.flags & DMST_USE_TRACK_PANNER)) return DMST_EINVAL;     // broken upstream (modules.py:269)
+    if (!(k.flags & DMST_BASIC_CONSOLE) && !k.master_params) return DMST_EINVAL;
+    if (k.la_t < 0 || k.la_t > kTrackTile || k.la_m < 0 || k.la_m > kMasterTile) return DMST_EINVAL;
+    return 0;
+}
+
+inline void fill_prepare(PrepareArgs& p, const ConsoleCall& k, bool master, ConsoleWs& w, int* status) {
+    memset(&p, 0, sizeof(p));
+    const bool basic = (k.flags & DMST_BASIC_CONSOLE) != 0;
+    if (!master) {
+        p.params = k.track_params; p.rows = k.B * k.N;
+        p.np = basic ? 2 : DMST_NUM_TRACK_PARAMS; p.kind = basic ? 1 : 0;
+        if (basic) {
+            p.lo[0] = k.ranges->track_lo[0]; p.hi[0] = k.ranges->track_hi[0];
+            p.lo[1] = k.ranges->track_lo[25]; p.hi[1] = k.ranges->track_hi[25];
+        } else {
+            for (int i = 0; i < DMST_NUM_TRACK_PARAMS; ++i) { p.lo[i] = k.ranges->track_lo[i]; p.hi[i] = k.ranges->track_hi[i]; }
+        }
+        p.L = kTrackL; p.tab = w.track_tab; p.status_base = 0;
+    } else {
+        p.params = k.master_params; p.rows = k.B;
+        p.np = DMST_NUM_MASTER_PARAMS; p.kind = 2;
+        for (int i = 0; i < DMST_NUM_MASTER_PARAMS; ++i) { p.lo[i] = k.ranges->master_lo[i]; p.hi[i] = k.ranges->master_hi[i]; }
+        p.L = kMasterL; p.tab = w.master_tab; p.status_base = 1000;
+    }
+    p.sr = (double)k.sr; p.status = status;
+}
+
+inline void fill_chain(ChainArgs& a, const ConsoleCall& k, bool master, ConsoleWs& w) {
+    memset(&a, 0, sizeof(a));
+    a.N = k.N; a.T = k.T; a.Tp = w.Tp;
+    if (!master) {
+        a.nrows = k.B * k.N; a.ntiles = w.nt_track; a.flags = track_chain_flags(k.flags);
+        a.lookahead = k.la_t;
+        a.src = k.tracks; a.src_batch_stride = k.tbs; a.src_row_stride = k.trs;
+        a.src_vec_ok = aligned16(k.tracks) && (k.tbs % 4 == 0) && (k.trs % 4 == 0);
+        a.tab = w.track_tab; a.track_tab = w.track_tab; a.y = w.y;
+        a.ticket = w.header + 0; a.flag = w.t_flag; a.state = w.t_state; a.tail2 = w.t_tail2; a.etail = w.t_etail;
+        a.partial = w.t_partial; a.bflag = w.t_bflag; a.bstate = w.t_bstate; a.dhead = w.t_dhead;
+    } else {
+        a.nrows = k.B; a.ntiles = w.nt_master; a.flags = master_chain_flags(k.flags);
+        a.lookahead = k.la_m;
+        a.src = w.y; a.tab = w.master_tab; a.track_tab = w.track_tab; a.bus_pre = w.bus_pre;
+        a.ticket = w.header + 1; a.flag = w.m_flag; a.state = w.m_state; a.tail2 = w.m_tail2; a.etail = w.m_etail;
+        a.partial = w.m_partial; a.bflag = w.m_bflag; a.bstate = w.m_bstate; a.dhead = w.m_dhead;
+    }
+}
+
+#define DMST_CHECK(expr)            \
+    do {                            \
+        int _e = (expr);            \
+        if (_e != 0) return _e;     \
+    } while (0)
+
+inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* status, void* ws,
+                           size_t ws_bytes, cudaStream_t stream) {
+    DMST_CHECK(check_call(k));
+    if (!mix || !status || !ws) return DMST_EINVAL;
+    if ((k.flags & DMST_WANT_MIXED_TRACKS) && !mixed) return DMST_EINVAL;
+    ConsoleWs w = carve_console(ws, k.B, k.N, k.T, k.la_t, k.la_m);
+    if (ws_bytes < w.total || !aligned16(ws)) return DMST_EINVAL;
+    unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+    DMST_CHECK(DMST_MEMSET_ASYNC(w.header, 0, 64 * sizeof(int), stream));
+    DMST_CHECK(DMST_MEMSET_ASYNC(base + w.flags_begin, 0, w.flags_end - w.flags_begin, stream));
+    DMST_CHECK(DMST_MEMSET_ASYNC(status, 0x7f, 4, stream));  // 0x7f7f7f7f = "no offender yet"
+
+    PrepareArgs pt, pm;
+    fill_prepare(pt, k, false, w, status);
+    DMST_LAUNCH(prepare_kernel, dim3((pt.rows * 8 + 127) / 128), dim3(128), 0, stream, pt);
+    fill_prepare(pm, k, true, w, status);
+    if (!k.master_params) { pm.kind = 3; pm.np = 0; }
+    DMST_LAUNCH(prepare_kernel, dim3((pm.rows * 8 + 127) / 128), dim3(128), 0, stream, pm);
+
+    ChainArgs at, am;
+    fill_chain(at, k, false, w);
+    at.want_mixed = (k.flags & DMST_WANT_MIXED_TRACKS) ? 1 : 0;
+    at.mixed = mixed;
+    at.user_vec_ok = mixed && aligned16(mixed) && (k.T % 4 == 0);
+    {
+        auto kern = chain_fwd_kernel<1, kTrackL, kTrackNT, false>;
+        const size_t smem = fwd_smem_bytes(1, kTrackTile, k.la_t);
+        DMST_CHECK(DMST_SET_SMEM(kern, smem));
+        DMST_LAUNCH(kern, dim3(at.nrows * at.ntiles), dim3(kTrackNT), smem, stream, at);
+    }
+    fill_chain(am, k, true, w);
+    am.mix = mix;
+    am.user_vec_ok = aligned16(mix) && (k.T % 4 == 0);
+    {
+        auto kern = chain_fwd_kernel<2, kMasterL, kMasterNT, true>;
+        const size_t smem = fwd_smem_bytes(2, kMasterTile, k.la_m);
+        DMST_CHECK(DMST_SET_SMEM(kern, smem));
+        DMST_LAUNCH(kern, dim3(am.nrows * am.ntiles), dim3(kMasterNT), smem, stream, am);
+    }
+    return DMST_LAST_ERROR();
+}
+
+inline int console_backward(const ConsoleCall& k, const float* gmix, const float* gmixed, float* gtp,
+                            float* gmp, float* gtracks, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    DMST_CHECK(check_call(k));
+    if (!gmix || !gtp || !ws) return DMST_EINVAL;
+    if ((k.flags & DMST_WANT_GRAD_TRACKS) && !gtracks) return DMST_EINVAL;
+    ConsoleWs w = carve_console(ws, k.B, k.N, k.T, k.la_t, k.la_m);
+    if (ws_bytes < w.total || !aligned16(ws)) return DMST_EINVAL;
+    unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+    DMST_CHECK(DMST_MEMSET_ASYNC(w.header, 0, 64 * sizeof(int), stream));
+    DMST_CHECK(DMST_MEMSET_ASYNC(base + w.bflags_begin, 0, w.bflags_end - w.bflags_begin, stream));
+
+    ChainArgs am, at;
+    fill_chain(am, k, true, w);
+    am.src = w.bus_pre;
+    am.gout = gmix; am.gsrc = w.dbus;
+    am.user_vec_ok = aligned16(gmix) && (k.T % 4 == 0);
+    am.ticket = w.header + 2;
+    {
+        auto kern = chain_bwd_kernel<2, kMasterL, kMasterNT, true>;
+        const size_t smem = bwd_smem_bytes(2, kMasterTile, k.la_m, kMasterNT);
+        DMST_CHECK(DMST_SET_SMEM(kern, smem));
+        DMST_LAUNCH(kern, dim3(am.nrows * am.ntiles), dim3(kMasterNT), smem, stream, am);
+    }
+    if (gmp && k.master_params) {
+        EpilogueArgs e;
+        memset(&e, 0, sizeof(e));
+        e.params = k.master_params; e.rows = k.B; e.np = DMST_NUM_MASTER_PARAMS; e.kind = 2;
+        for (int i = 0; i < DMST_NUM_MASTER_PARAMS; ++i) { e.lo[i] = k.ranges->master_lo[i]; e.hi[i] = k.ranges->master_hi[i]; }
+        e.sr = (double)k.sr; e.partial = w.m_partial; e.ntiles = w.nt_master; e.flags = am.flags; e.grad = gmp;
+        DMST_LAUNCH(grad_epilogue_kernel, dim3((e.rows + 63) / 64), dim3(64), 0, stream, e);
+    }
+    fill_chain(at, k, false, w);
+    at.gout = w.dbus; at.gmixed = gmixed;
+    at.gsrc = (k.flags & DMST_WANT_GRAD_TRACKS) ? gtracks : nullptr;
+    at.user_vec_ok = (k.T % 4 == 0) && (!gmixed || aligned16(gmixed)) && (!at.gsrc || aligned16(at.gsrc));
+    at.ticket = w.header + 3;
+    {
+        auto kern = chain_bwd_kernel<1, kTrackL, kTrackNT, false>;
+        const size_t smem = bwd_smem_bytes(1, kTrackTile, k.la_t, kTrackNT);
+        DMST_CHECK(DMST_SET_SMEM(kern, smem));
+        DMST_LAUNCH(kern, dim3(at.nrows * at.ntiles), dim3(kTrackNT), smem, stream, at);
+    }
+    {
+        EpilogueArgs e;
+        memset(&e, 0, sizeof(e));
+        const bool basic = (k.flags & DMST_BASIC_CONSOLE) != 0;
+        e.params = k.track_params; e.rows = k.B * k.N;
+        e.np = basic ? 2 : DMST_NUM_TRACK_PARAMS; e.kind = basic ? 1 : 0;
+        if (basic) {
+            e.lo[0] = k.ranges->track_lo[0]; e.hi[0] = k.ranges->track_hi[0];
+            e.lo[1] = k.ranges->track_lo[25]; e.hi[1] = k.ranges->track_hi[25];
+        } else {
+            for (int i = 0; i < DMST_NUM_TRACK_PARAMS; ++i) { e.lo[i] = k.ranges->track_lo[i]; e.hi[i] = k.ranges->track_hi[i]; }
+        }
+        e.sr = (double)k.sr; e.partial = w.t_partial; e.ntiles = w.nt_track; e.flags = at.flags; e.grad = gtp;
+        DMST_LAUNCH(grad_epilogue_kernel, dim3((e.rows + 63) / 64), dim3(64), 0, stream, e);
+    }
+    return DMST_LAST_ERROR();
+}
+
+}  // namespace dmst

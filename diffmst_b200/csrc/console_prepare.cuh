@@ -1,0 +1,252 @@
+// Parameter handling for the mix console, in float64 on the device:
+//   * prepare: normalised (0..1) controller outputs -> denormalised values
+//     (mst/modules.py:71-97) -> RBJ biquad coefficients, compressor constants, pan gains
+//      -> the scan tables of common.cuh (RowTab);
+//     out-of-range parameters are reported through `status` (ValueError of modules.py:86-89).
+//   * grad epilogue: sums the per-tile gradient partials of the backward kernels and
+//     chains them through the Jacobian of the parameter design, using forward-mode
+//     dual numbers so the derivative code cannot drift from the design code.
+#pragma once
+#include "common.cuh"
+
+namespace dmst {
+
+constexpr double kPi = 3.14159265358979323846;
+
+// ---- tiny forward-mode dual number: value + 3 partials (gain_db, cutoff, q) ----
+struct Dual {
+    double v, d[3];
+};
+__device__ __forceinline__ Dual dconst(double c) { return {c, {0, 0, 0}}; }
+__device__ __forceinline__ Dual dvar(double c, int i) { Dual r = {c, {0, 0, 0}}; r.d[i] = 1; return r; }
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return {a.v + b.v, {a.d[0] + b.d[0], a.d[1] + b.d[1], a.d[2] + b.d[2]}}; }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return {a.v - b.v, {a.d[0] - b.d[0], a.d[1] - b.d[1], a.d[2] - b.d[2]}}; }
+__device__ __forceinline__ Dual operator-(Dual a) { return {-a.v, {-a.d[0], -a.d[1], -a.d[2]}}; }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) {
+    return {a.v * b.v, {a.d[0] * b.v + a.v * b.d[0], a.d[1] * b.v + a.v * b.d[1], a.d[2] * b.v + a.v * b.d[2]}};
+}
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
+    double inv = 1.0 / b.v, q = a.v * inv;
+    return {q, {(a.d[0] - q * b.d[0]) * inv, (a.d[1] - q * b.d[1]) * inv, (a.d[2] - q * b.d[2]) * inv}};
+}
+__device__ __forceinline__ Dual operator*(double s, Dual a) { return {s * a.v, {s * a.d[0], s * a.d[1], s * a.d[2]}}; }
+__device__ __forceinline__ Dual operator+(double s, Dual a) { return {s + a.v, {a.d[0], a.d[1], a.d[2]}}; }
+__device__ __forceinline__ Dual dsin(Dual a) { double c = cos(a.v); return {sin(a.v), {c * a.d[0], c * a.d[1], c * a.d[2]}}; }
+__device__ __forceinline__ Dual dcos(Dual a) { double s = -sin(a.v); return {cos(a.v), {s * a.d[0], s * a.d[1], s * a.d[2]}}; }
+__device__ __forceinline__ Dual dsqrt(Dual a) { double r = sqrt(a.v), k = 0.5 / r; return {r, {k * a.d[0], k * a.d[1], k * a.d[2]}}; }
+__device__ __forceinline__ Dual dpow10(Dual a) { double r = pow(10.0, a.v), k = r * 2.302585092994046; return {r, {k * a.d[0], k * a.d[1], k * a.d[2]}}; }
+
+// RBJ cookbook section, normalised by a0 (dasp_pytorch.signal.biquad, Appendix A).
+// kind: 0 low_shelf, 1 peaking, 2 high_shelf.  out = {b0, b1, b2, a1, a2}.
+__device__ inline void rbj_design(double gain_db, double freq, double q, double sr, int kind, Dual out[5]) {
+    Dual G = dvar(gain_db, 0), F = dvar(freq, 1), Q = dvar(q, 2);
+    Dual A = dpow10((1.0 / 40.0) * G);
+    Dual w0 = (2.0 * kPi / sr) * F;
+    Dual al = dsin(w0) / (2.0 * Q);
+    Dual c = dcos(w0);
+    Dual b0, b1, b2, a0, a1, a2;
+    if (kind == 1) {
+        b0 = 1.0 + al * A; b1 = -2.0 * c; b2 = 1.0 + (-(al * A));
+        a0 = 1.0 + al / A; a1 = -2.0 * c; a2 = 1.0 + (-(al / A));
+    } else {
+        Dual sA2al = 2.0 * (dsqrt(A) * al);
+        Dual Ap1 = 1.0 + A, Am1 = -1.0 + A;
+        if (kind == 0) {
+            b0 = A * (Ap1 - Am1 * c + sA2al);
+            b1 = 2.0 * (A * (Am1 - Ap1 * c));
+            b2 = A * (Ap1 - Am1 * c - sA2al);
+            a0 = Ap1 + Am1 * c + sA2al;
+            a1 = -2.0 * (Am1 + Ap1 * c);
+            a2 = Ap1 + Am1 * c - sA2al;
+        } else {
+            b0 = A * (Ap1 + Am1 * c + sA2al);
+            b1 = -2.0 * (A * (Am1 + Ap1 * c));
+            b2 = A * (Ap1 + Am1 * c - sA2al);
+            a0 = Ap1 - Am1 * c + sA2al;
+            a1 = 2.0 * (Am1 - Ap1 * c);
+            a2 = Ap1 - Am1 * c - sA2al;
+        }
+    }
+    out[0] = b0 / a0; out[1] = b1 / a0; out[2] = b2 / a0; out[3] = a1 / a0; out[4] = a2 / a0;
+}
+
+__device__ __forceinline__ int section_kind(int k) { return k == 0 ? 0 : (k == 5 ? 2 : 1); }
+
+struct M2 { double a, b, c, d; };
+__device__ __forceinline__ M2 mmul(M2 x, M2 y) {
+    return {x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d};
+}
+__device__ __forceinline__ void mstore(float* o, M2 m) { o[0] = (float)m.a; o[1] = (float)m.b; o[2] = (float)m.c; o[3] = (float)m.d; }
+
+struct PrepareArgs {
+    const float* params;   // tracks: (rows, np) ; master: (rows, 26)
+    int rows;
+    int np;                // parameters per row (27, 2 or 26)
+    int kind;              // 0 advanced track, 1 basic track, 2 master, 3 neutral (no params)
+    float lo[32], hi[32];
+    double sr;
+    int L;                 // thread chunk length the tables are built for
+    RowTab* tab;           // [rows]
+    int* status;
+    int status_base;       // added to the flat index reported in status[0]
+};
+
+// index maps into the normalised parameter vector (mst/modules.py:353-460)
+struct ParamMap { int gain_in, eq0, comp0, pan, gain_out; };
+__device__ __forceinline__ ParamMap param_map(int kind) {
+    if (kind == 0) return {0, 1, 19, 25, -1};
+    if (kind == 1) return {0, -1, -1, 1, -1};
+    if (kind == 3) return {-1, -1, -1, -1, -1};  // no parameters: neutral row
+    return {25, 0, 18, -1, 24};
+}
+
+template <class Args>
+__device__ __forceinline__ double denorm(const Args& a, const float* p, int i) {
+    return (double)p[i] * ((double)a.hi[i] - (double)a.lo[i]) + (double)a.lo[i];
+}
+
+// one thread per (row, job): jobs 0..5 = EQ sections, 6 = everything else, 7 = range check
+__global__ void prepare_kernel(PrepareArgs a) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = gid >> 3, job = gid & 7;
+    if (row >= a.rows) return;
+    const float* p = a.params + (long long)row * a.np;
+    RowTab& tb = a.tab[row];
+    const ParamMap pm = param_map(a.kind);
+    const int L = a.L;
+
+    if (job == 7) {
+        int bad = 0x7fffffff;
+        for (int i = 0; i < a.np; ++i)
+            if (p[i] < 0.0f || p[i] > 1.0f) { bad = a.status_base + 1 + i; break; }
+        if (bad != 0x7fffffff) atomicMin(a.status, bad);
+        return;
+    }
+    if (job < 6) {
+        SectionTab& st = tb.sec[job];
+        double cf[5] = {1, 0, 0, 0, 0};
+        if (pm.eq0 >= 0) {
+            Dual o[5];
+            rbj_design(denorm(a, p, pm.eq0 + 3 * job), denorm(a, p, pm.eq0 + 3 * job + 1),
+                       denorm(a, p, pm.eq0 + 3 * job + 2), a.sr, section_kind(job), o);
+            for (int j = 0; j < 5; ++j) cf[j] = o[j].v;
+        }
+        st.b0 = (float)cf[0]; st.b1 = (float)cf[1]; st.b2 = (float)cf[2];
+        st.a1 = (float)cf[3]; st.a2 = (float)cf[4];
+        st.inv_b0 = (float)(1.0 / (double)st.b0);
+        st.pad0 = st.pad1 = 0.0f;
+        // powers of the state matrix of the recursion the kernels actually run
+        // (float32-rounded a1, a2), evaluated in float64
+        M2 A = {-(double)st.a1, 1.0, -(double)st.a2, 0.0};
+        M2 P = A;
+        for (int s = 1; s < L; s <<= 1) P = mmul(P, P);  // A^L, L a power of two
+        M2 Pj = P;
+        for (int j = 0; j < 5; ++j) { mstore(st.P2[j], Pj); Pj = mmul(Pj, Pj); }
+        mstore(st.Q, Pj);  // P^32
+        M2 R = {1, 0, 0, 1};
+        for (int l = 0; l < 32; ++l) { mstore(st.Ppow[l], R); R = mmul(R, P); }
+        return;
+    }
+    // job 6: gains, compressor, pan
+    tb.g_in = (pm.gain_in >= 0) ? (float)pow(10.0, denorm(a, p, pm.gain_in) / 20.0) : 1.0f;
+    tb.g_out = (pm.gain_out >= 0) ? (float)pow(10.0, denorm(a, p, pm.gain_out) / 20.0) : 1.0f;
+    if (pm.pan >= 0) {
+        double th = denorm(a, p, pm.pan) * (kPi / 2);
+        tb.gL = (float)sqrt(((kPi / 2) - th) * (2 / kPi) * cos(th));
+        tb.gR = (float)sqrt(th * (2 / kPi) * sin(th));
+    } else {
+        tb.gL = tb.gR = 1.0f;
+    }
+    double thr = 0, ratio = 1, attack = 1, knee = 1, makeup = 0;
+    if (pm.comp0 >= 0) {
+        thr = denorm(a, p, pm.comp0 + 0); ratio = denorm(a, p, pm.comp0 + 1);
+        attack = denorm(a, p, pm.comp0 + 2); knee = denorm(a, p, pm.comp0 + 4);
+        makeup = denorm(a, p, pm.comp0 + 5);  // comp0 + 3 = release_ms: unused upstream
+    }
+    const float alpha = (float)exp(-log(9.0) / (a.sr * (attack / 1e3)));
+    tb.alpha = alpha;
+    tb.beta = (float)(1.0 - (double)alpha);
+    tb.thr_lo = (float)(thr - knee / 2);
+    tb.knee = (float)knee; tb.inv_knee = (float)(1.0 / knee); tb.inv_2knee = (float)(0.5 / knee);
+    tb.slope = (float)(1.0 / ratio - 1.0);
+    tb.makeup = (float)makeup;
+    tb.inv_ratio2 = (float)(1.0 / (ratio * ratio));
+    tb.pad[0] = tb.pad[1] = tb.pad[2] = 0.0f; tb.pad2[0] = tb.pad2[1] = 0.0f;
+    double aL = pow((double)alpha, (double)L);
+    double aj = aL;
+    for (int j = 0; j < 5; ++j) { tb.a2pow[j] = (float)aj; aj *= aj; }
+    tb.aQ = (float)aj;
+    double r = 1.0;
+    for (int l = 0; l < 32; ++l) { tb.a_lane[l] = (float)r; r *= aL; }
+    r = (double)alpha;
+    for (int i = 0; i < kMaxL; ++i) { tb.a_i[i] = (float)r; r *= (double)alpha; }
+}
+
+struct EpilogueArgs {
+    const float* params;
+    int rows, np, kind;
+    float lo[32], hi[32];
+    double sr;
+    const float* partial;  // [rows][ntiles][kGradCount]
+    int ntiles;
+    unsigned flags;        // kChain* actually enabled (disabled stages contribute zero)
+    float* grad;           // [rows][np], gradient w.r.t. the NORMALISED parameters
+};
+
+// one thread per row
+__global__ void grad_epilogue_kernel(EpilogueArgs a) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= a.rows) return;
+    const float* p = a.params + (long long)row * a.np;
+    float* g = a.grad + (long long)row * a.np;
+    const ParamMap pm = param_map(a.kind);
+    double acc[kGradCount];
+    for (int j = 0; j < kGradCount; ++j) acc[j] = 0.0;
+    for (int t = 0; t < a.ntiles; ++t) {
+        const float* q = a.partial + ((long long)row * a.ntiles + t) * kGradCount;
+        for (int j = 0; j < kGradCount; ++j) acc[j] += (double)q[j];
+    }
+    for (int i = 0; i < a.np; ++i) g[i] = 0.0f;
+    auto scale = [&](int i) { return (double)a.hi[i] - (double)a.lo[i]; };
+    const double ln10_20 = 0.11512925464970229;
+    if (pm.gain_in >= 0 && (a.flags & kChainGain))
+        g[pm.gain_in] = (float)(acc[kGradGin] * ln10_20 * scale(pm.gain_in));
+    if (pm.gain_out >= 0 && (a.flags & kChainOutGain))
+        g[pm.gain_out] = (float)(acc[kGradGout] * ln10_20 * scale(pm.gain_out));
+    if (pm.eq0 >= 0 && (a.flags & kChainEq)) {
+        for (int k = 0; k < kNumSections; ++k) {
+            Dual o[5];
+            const int i0 = pm.eq0 + 3 * k;
+            rbj_design(denorm(a, p, i0), denorm(a, p, i0 + 1), denorm(a, p, i0 + 2), a.sr,
+                       section_kind(k), o);
+            // the backward kernel accumulates in the basis {b0+b1+b2, b1+2 b2, b2, a1+a2, a2}
+            Dual basis[5] = {o[0] + o[1] + o[2], o[1] + 2.0 * o[2], o[2], o[3] + o[4], o[4]};
+            for (int d = 0; d < 3; ++d) {
+                double s = 0.0;
+                for (int j = 0; j < 5; ++j) s += acc[kGradEq + 5 * k + j] * basis[j].d[d];
+                g[i0 + d] = (float)(s * scale(i0 + d));
+            }
+        }
+    }
+    if (pm.comp0 >= 0 && (a.flags & kChainComp)) {
+        const double attack = denorm(a, p, pm.comp0 + 2);
+        const double alpha = exp(-log(9.0) / (a.sr * (attack / 1e3)));
+        const double dalpha_dattack = alpha * log(9.0) * 1e3 / (a.sr * attack * attack);
+        g[pm.comp0 + 0] = (float)(acc[kGradThr] * scale(pm.comp0 + 0));
+        g[pm.comp0 + 1] = (float)(acc[kGradRatio] * scale(pm.comp0 + 1));
+        g[pm.comp0 + 2] = (float)(acc[kGradAlpha] * dalpha_dattack * scale(pm.comp0 + 2));
+        g[pm.comp0 + 3] = 0.0f;  // release_ms has no effect upstream
+        g[pm.comp0 + 4] = (float)(acc[kGradKnee] * scale(pm.comp0 + 4));
+        g[pm.comp0 + 5] = (float)(acc[kGradMakeup] * scale(pm.comp0 + 5));
+    }
+    if (pm.pan >= 0) {
+        const double th = denorm(a, p, pm.pan) * (kPi / 2);
+        const double uL = ((kPi / 2) - th) * (2 / kPi) * cos(th), uR = th * (2 / kPi) * sin(th);
+        const double duL = (2 / kPi) * (-cos(th) - ((kPi / 2) - th) * sin(th));
+        const double duR = (2 / kPi) * (sin(th) + th * cos(th));
+        const double dgL = uL > 0 ? 0.5 * duL / sqrt(uL) : 0.0, dgR = uR > 0 ? 0.5 * duR / sqrt(uR) : 0.0;
+        g[pm.pan] = (float)((acc[kGradGL] * dgL + acc[kGradGR] * dgR) * (kPi / 2) * scale(pm.pan));
+    }
+}
+
+}  // namespace dmst

@@ -1,0 +1,289 @@
+"""GPU parity tests of the mix console: CUDA path (through the C ABI) vs the float64 oracle,
+the golden fixtures, and size-independent properties at BASELINE's full size.
+
+Tolerances (north_star): <= 1e-4 relative for IIR/compressor floats, judged against the
+float64 oracle; where the reference's own float32 evaluation of the same case is further
+than that from float64 the bound is that distance instead."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.console import OracleAdvancedMixConsole
+
+pytestmark = pytest.mark.gpu
+
+SR = 44100
+FLAG_NAMES = ["use_track_input_fader", "use_track_eq", "use_track_compressor",
+              "use_track_panner", "use_master_bus", "use_fx_bus", "use_output_fader"]
+CASES = ["console_adv_all", "console_adv_b2", "console_adv_train_flags", "console_adv_eq_only",
+         "console_adv_comp_only", "console_adv_gainpan_only"]
+TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+def relmax(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def rell2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def run_ours(tracks, tp, fp, mp, probe, flags, grad_tracks=False):
+    from diffmst_b200 import AdvancedMixConsole
+    con = AdvancedMixConsole(SR).cuda()
+    x = torch.as_tensor(tracks).cuda().requires_grad_(grad_tracks)
+    tpc = torch.as_tensor(tp).cuda().requires_grad_(True)
+    mpc = torch.as_tensor(mp).cuda().requires_grad_(True)
+    mixed, mix, tpd, fpd, mpd = con(x, tpc, torch.as_tensor(fp).cuda(), mpc, **flags)
+    (mix * torch.as_tensor(probe).cuda()).sum().backward()
+    gm = mpc.grad if mpc.grad is not None else torch.zeros_like(mpc)
+    return dict(mix=mix.detach().cpu().numpy(), mixed=mixed.detach().cpu().numpy(),
+                gtp=tpc.grad.cpu().numpy(), gmp=gm.cpu().numpy(),
+                gx=x.grad.cpu().numpy() if grad_tracks else None, tpd=tpd, mpd=mpd)
+
+
+def run_oracle(tracks, tp, fp, mp, probe, flags, dtype):
+    con = OracleAdvancedMixConsole(SR)
+    x = torch.as_tensor(tracks).to(dtype).requires_grad_(True)
+    tpc = torch.as_tensor(tp).to(dtype).requires_grad_(True)
+    mpc = torch.as_tensor(mp).to(dtype).requires_grad_(True)
+    mixed, mix, _, _, _ = con(x, tpc, torch.as_tensor(fp).to(dtype), mpc, **flags)
+    (mix * torch.as_tensor(probe).to(dtype)).sum().backward()
+    gm = mpc.grad if mpc.grad is not None else torch.zeros_like(mpc)
+    return dict(mix=mix.detach().numpy(), mixed=mixed.detach().numpy(), gtp=tpc.grad.numpy(),
+                gmp=gm.numpy(), gx=x.grad.numpy())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_cases(golden, name):
+    d = golden(name)
+    flags = {k: bool(v) for k, v in zip(FLAG_NAMES, d["flags"])}
+    ours = run_ours(d["tracks"], d["track_params"], d["fx_bus_params"], d["master_bus_params"],
+                    d["probe"], flags, grad_tracks=True)
+    ref32 = run_oracle(d["tracks"], d["track_params"], d["fx_bus_params"], d["master_bus_params"],
+                       d["probe"], flags, torch.float32)
+    # forward: vs the float64 golden mix
+    bound = max(TOL, relmax(ref32["mix"], d["mix"]))
+    assert relmax(ours["mix"], d["mix"]) <= bound, (name, relmax(ours["mix"], d["mix"]), bound)
+    assert np.allclose((ours["mixed"].astype(np.float64) ** 2).sum(-1), d["mixed_energy"], rtol=max(4 * bound, 1e-3))
+    assert relmax(ours["mixed"][..., :1024], d["mixed_head"]) <= max(bound, 2e-4)
+    # backward: vs the float64 golden gradients
+    gb = max(GRAD_TOL, rell2(ref32["gtp"], d["grad_track_params"]))
+    assert rell2(ours["gtp"], d["grad_track_params"]) <= gb, (name, rell2(ours["gtp"], d["grad_track_params"]), gb)
+    if np.abs(d["grad_master_bus_params"]).max() > 0:
+        gbm = max(GRAD_TOL, rell2(ref32["gmp"], d["grad_master_bus_params"]))
+        assert rell2(ours["gmp"], d["grad_master_bus_params"]) <= gbm
+    else:
+        assert np.abs(ours["gmp"]).max() == 0
+    gbx = max(10 * GRAD_TOL, 2 * relmax(ref32["gx"][..., :2048], d["grad_tracks_head"]))
+    assert relmax(ours["gx"][..., :2048], d["grad_tracks_head"]) <= gbx
+    # release_ms and fx send have no effect upstream: exactly zero gradient
+    assert np.all(ours["gtp"][..., 22] == 0) and np.all(ours["gtp"][..., 26] == 0)
+    # denormalised dictionaries are bit-identical to the reference's torch expressions
+    assert np.array_equal(ours["tpd"]["compressor"]["threshold_db"].detach().cpu().numpy(), d["denorm_threshold_db"])
+    assert np.array_equal(ours["tpd"]["parametric_eq"]["band3_cutoff_freq"].detach().cpu().numpy(), d["denorm_band3_cutoff"])
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 65536), (1, 5, 44100), (3, 1, 20000)])
+def test_seeded_vs_float64_oracle(shape):
+    B, N, T = shape
+    g = torch.Generator().manual_seed(100 + T)
+    tracks = torch.randn(B, N, T, generator=g) * 0.1
+    tp, fp, mp = torch.rand(B, N, 27, generator=g), torch.rand(B, 25, generator=g), torch.rand(B, 26, generator=g)
+    probe = torch.randn(B, 2, T, generator=g)
+    flags = dict(use_fx_bus=False)
+    ours = run_ours(tracks, tp, fp, mp, probe, flags)
+    o64 = run_oracle(tracks, tp, fp, mp, probe, flags, torch.float64)
+    o32 = run_oracle(tracks, tp, fp, mp, probe, flags, torch.float32)
+    # FSM time-aliasing of the oracle itself is not negligible below ~32768 samples
+    alias = 0.0 if T >= 32768 else 2e-3
+    bound = max(TOL, relmax(o32["mix"], o64["mix"])) + alias
+    assert relmax(ours["mix"], o64["mix"]) <= bound, (relmax(ours["mix"], o64["mix"]), bound)
+    for b in range(B):
+        for n in range(N):
+            bt = max(TOL, relmax(o32["mixed"][b, :, n], o64["mixed"][b, :, n])) + alias
+            assert relmax(ours["mixed"][b, :, n], o64["mixed"][b, :, n]) <= bt, (b, n)
+    if T >= 32768:
+        gb = max(GRAD_TOL, rell2(o32["gtp"], o64["gtp"]))
+        assert rell2(ours["gtp"], o64["gtp"]) <= gb, (rell2(ours["gtp"], o64["gtp"]), gb)
+        gbm = max(GRAD_TOL, rell2(o32["gmp"], o64["gmp"]))
+        assert rell2(ours["gmp"], o64["gmp"]) <= gbm
+
+
+def test_time_domain_oracle_short_length():
+    """At short lengths the kernel must match the exact recursion (what FSM approximates)."""
+    from oracle import timedomain as td
+    from oracle.console import EQ_KEYS, COMP_KEYS
+    g = torch.Generator().manual_seed(5)
+    N, T = 3, 6000
+    tracks = torch.randn(1, N, T, generator=g) * 0.1
+    tp, fp, mp = torch.rand(1, N, 27, generator=g), torch.rand(1, 25, generator=g), torch.rand(1, 26, generator=g)
+    ours = run_ours(tracks, tp, fp, mp, torch.zeros(1, 2, T), dict(use_fx_bus=False))
+    tpd, mpd = ours["tpd"], ours["mpd"]
+    tpn = np.zeros((N, 27)); mpn = np.zeros(26)
+    tpn[:, 0] = tpd["input_fader"]["gain_db"][0].detach().cpu().numpy()
+    for i, k in enumerate(EQ_KEYS):
+        tpn[:, 1 + i] = tpd["parametric_eq"][k][0].detach().cpu().numpy(); mpn[i] = float(mpd["parametric_eq"][k][0])
+    for i, k in enumerate(COMP_KEYS):
+        tpn[:, 19 + i] = tpd["compressor"][k][0].detach().cpu().numpy(); mpn[18 + i] = float(mpd["compressor"][k][0])
+    tpn[:, 25] = tpd["stereo_panner"]["pan"][0].detach().cpu().numpy()
+    mpn[24] = float(mpd["output_fader"]["gain_db"][0]); mpn[25] = float(mpd["input_fader"]["gain_db"][0])
+    mixed, mix = td.console(tracks[0].numpy().astype(np.float64), tpn, mpn, SR)
+    assert relmax(ours["mix"][0], mix) <= 2e-4
+    assert relmax(ours["mixed"][0], mixed) <= 2e-4
+
+
+def test_indexing_is_exact_with_neutral_processing():
+    """Impulses through gain/pan/bus with EQ+compressor off land on the exact sample, with the
+    exact float32 product of the per-track scalars."""
+    from diffmst_b200 import AdvancedMixConsole
+    B, N, T = 2, 3, 9000
+    x = torch.zeros(B, N, T)
+    pos = [[17, 4095, 4096], [0, 8191, 8999]]
+    for b in range(B):
+        for n in range(N):
+            x[b, n, pos[b][n]] = 1.0 + n
+    tp = torch.rand(B, N, 27, generator=torch.Generator().manual_seed(1))
+    mp = torch.rand(B, 26, generator=torch.Generator().manual_seed(2))
+    con = AdvancedMixConsole(SR).cuda()
+    mixed, mix, tpd, _, _ = con(x.cuda(), tp.cuda(), torch.rand(B, 25).cuda(), mp.cuda(), use_track_eq=False,
+                                use_track_compressor=False, use_master_bus=False, use_fx_bus=False,
+                                use_output_fader=False)
+    mixed, mix = mixed.cpu(), mix.cpu()
+    assert mixed.shape == (B, 2, N, T) and mix.shape == (B, 2, T)
+    nz = torch.nonzero(mixed)
+    for b in range(B):
+        for n in range(N):
+            rows = nz[(nz[:, 0] == b) & (nz[:, 2] == n)]
+            assert set(rows[:, 3].tolist()) == {pos[b][n]}
+    g_in = 10 ** (tpd["input_fader"]["gain_db"].double().cpu() / 20)
+    th = tpd["stereo_panner"]["pan"].double().cpu() * np.pi / 2
+    gl = torch.sqrt((np.pi / 2 - th) * (2 / np.pi) * torch.cos(th))
+    for b in range(B):
+        for n in range(N):
+            want = (1.0 + n) * g_in[b, n] * gl[b, n]
+            assert abs(float(mixed[b, 0, n, pos[b][n]]) - float(want)) <= 4e-7 * abs(float(want))
+    assert torch.allclose(mix, mixed.sum(2), rtol=0, atol=1e-6 * float(mix.abs().max()))
+
+
+def test_lookahead_delay_and_zero_head():
+    """With ratio 1 (no gain reduction), 0 dB makeup and flat EQ the chain is a pure delay of
+    2048 + 1024 samples with a zeroed head (roll + zero of the dasp compressor)."""
+    from diffmst_b200 import AdvancedMixConsole
+    B, N, T = 1, 2, 16384
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, N, T, generator=g) * 0.1
+    tp = torch.full((B, N, 27), 0.5)
+    tp[..., 20] = 0.0   # ratio 1
+    tp[..., 24] = 0.0   # makeup 0 dB
+    tp[..., 25] = 0.0   # pan hard left: gL = 1
+    mp = torch.full((B, 26), 0.5)
+    mp[..., 19] = 0.0
+    mp[..., 23] = 0.0
+    con = AdvancedMixConsole(SR).cuda()
+    mixed, mix, _, _, _ = con(x.cuda(), tp.cuda(), torch.rand(B, 25).cuda(), mp.cuda(), use_fx_bus=False)
+    mix = mix.cpu()
+    assert float(mix[..., :3072].abs().max()) == 0.0
+    want = x.sum(1)[:, : T - 3072]
+    assert torch.allclose(mix[:, 0, 3072:], want, rtol=0, atol=2e-6)
+    assert float(mix[:, 1].abs().max()) == 0.0
+
+
+def test_api_contract_and_errors():
+    from diffmst_b200 import AdvancedMixConsole
+    con = AdvancedMixConsole(SR).cuda()
+    assert len(con.state_dict()) == 0
+    con.load_state_dict({}, strict=True)  # mst/utils.py:245-249
+    B, N, T = 1, 2, 8192
+    x = torch.randn(B, N, T).cuda() * 0.1
+    tp, fp, mp = torch.rand(B, N, 27).cuda(), torch.rand(B, 25).cuda(), torch.rand(B, 26).cuda()
+    out = con(x, tp, fp, mp, use_fx_bus=False)
+    assert len(out) == 5
+    assert list(out[2].keys()) == ["input_fader", "parametric_eq", "compressor", "stereo_panner", "fx_bus"]
+    assert list(out[4].keys()) == ["parametric_eq", "compressor", "output_fader", "input_fader"]
+    assert list(out[3]["reverberation"].keys())[-1] == "mix"
+    bad = tp.clone(); bad[0, 1, 20] = 1.5
+    with pytest.raises(ValueError, match="Parameter ratio of effect compressor is out of range."):
+        con(x, bad, fp, mp, use_fx_bus=False)
+    badm = mp.clone(); badm[0, 24] = -0.1
+    with pytest.raises(ValueError, match="Parameter gain_db of effect output_fader is out of range."):
+        con(x, tp, fp, badm, use_fx_bus=False)
+    with pytest.raises(RuntimeError):
+        con(x, tp, fp, mp, use_track_panner=False, use_fx_bus=False)
+    with pytest.raises(NotImplementedError):
+        con(x, tp, fp, mp)  # use_fx_bus defaults to True upstream
+    # under no_grad (mst/mixing.py:72) and with the positional forward_mix_console call
+    with torch.no_grad():
+        m1 = con(x, tp, fp, mp, use_fx_bus=False)[1]
+        m2 = con.forward_mix_console(x, out[2], out[3], out[4], True, True, True, True, False, True, True)[1]
+    assert torch.equal(m1, out[1])
+    assert relmax(m2.cpu().numpy(), m1.cpu().numpy()) < 1e-4
+
+
+def test_strided_tracks_and_determinism():
+    """system.py:258 passes tracks[..., middle:] (a strided view); results must equal the
+    contiguous call bit for bit, and repeated calls are bit-identical."""
+    from diffmst_b200 import AdvancedMixConsole
+    con = AdvancedMixConsole(SR).cuda()
+    g = torch.Generator().manual_seed(11)
+    full = (torch.randn(2, 3, 40000, generator=g) * 0.1).cuda()
+    tp, fp, mp = torch.rand(2, 3, 27, generator=g).cuda(), torch.rand(2, 25).cuda(), torch.rand(2, 26, generator=g).cuda()
+    view = full[..., 20000:]
+    assert not view.is_contiguous()
+    a = con(view, tp, fp, mp, use_fx_bus=False)[1]
+    b = con(view.contiguous(), tp, fp, mp, use_fx_bus=False)[1]
+    c = con(view, tp, fp, mp, use_fx_bus=False)[1]
+    assert torch.equal(a, b) and torch.equal(a, c)
+    odd = full[..., 20001:]  # 4-byte aligned only: scalar load path
+    d = con(odd, tp, fp, mp, use_fx_bus=False)[1]
+    e = con(odd.contiguous(), tp, fp, mp, use_fx_bus=False)[1]
+    assert torch.equal(d, e)
+
+
+def test_basic_console_golden(golden):
+    from diffmst_b200 import BasicMixConsole
+    d = golden("console_basic")
+    con = BasicMixConsole(SR).cuda()
+    tp = torch.from_numpy(d["track_params"]).cuda().requires_grad_(True)
+    mixed, mix, tpd, fxd, md = con(torch.from_numpy(d["tracks"]).cuda(), tp)
+    assert con.num_track_control_params == 2 and fxd == {} and md == {}
+    assert list(tpd.keys()) == ["input_gain", "stereo_panner"]
+    assert np.array_equal(tpd["input_gain"]["gain_db"].detach().cpu().numpy(), d["gain_db"])
+    assert relmax(mix.detach().cpu().numpy(), d["mix_f64"]) < 2e-6
+    assert relmax(mixed.detach().cpu().numpy()[..., :2048], d["mixed_f32_head"]) < 2e-6
+    mix.sum().backward()
+    assert torch.isfinite(tp.grad).all() and float(tp.grad.abs().max()) > 0
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (8 x 16 x 262144): finite output, exact homogeneity of the
+    linear part, zero in -> zero out, gradient finite and deterministic."""
+    from diffmst_b200 import AdvancedMixConsole
+    B, N, T = 8, 16, 262144
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(B, N, T, generator=g) * 0.1).cuda()
+    tp = torch.rand(B, N, 27, generator=g).cuda().requires_grad_(True)
+    fp = torch.rand(B, 25, generator=g).cuda()
+    mp = torch.rand(B, 26, generator=g).cuda().requires_grad_(True)
+    con = AdvancedMixConsole(SR).cuda()
+    con.materialize_tracks = False
+    mixed, mix, _, _, _ = con(x, tp, fp, mp, use_fx_bus=False)
+    assert mixed.numel() == 0 and mix.shape == (B, 2, T)
+    assert torch.isfinite(mix).all()
+    mix.square().mean().backward()
+    g1 = tp.grad.clone(); tp.grad = None; mp.grad = None
+    mix2 = con(x, tp, fp, mp, use_fx_bus=False)[1]
+    assert torch.equal(mix, mix2)
+    mix2.square().mean().backward()
+    assert torch.equal(g1, tp.grad) and torch.isfinite(g1).all() and torch.isfinite(mp.grad).all()
+    # linear part (no compressor): scaling the input by 2 scales the mix by exactly 2
+    kw = dict(use_track_compressor=False, use_master_bus=False, use_fx_bus=False)
+    with torch.no_grad():
+        m1 = con(x, tp, fp, mp, **kw)[1]
+        m2 = con(2 * x, tp, fp, mp, **kw)[1]
+        assert torch.equal(m2, 2 * m1)
+        z = con(torch.zeros_like(x), tp, fp, mp, use_fx_bus=False)[1]
+        assert float(z.abs().max()) == 0.0
