@@ -56,6 +56,19 @@ def lib():
     l.dmst_console_backward.restype = i
     l.dmst_console_backward.argtypes = [vp, ll, ll, vp, vp, ctypes.POINTER(Ranges), f, i, i, i, u, i, i,
                                         vp, vp, vp, vp, vp, vp, sz, vp]
+    l.dmst_mrstft_workspace_bytes.restype = sz
+    l.dmst_mrstft_workspace_bytes.argtypes = [ctypes.POINTER(MrstftCfg), i, i]
+    l.dmst_mrstft_forward.restype = i
+    l.dmst_mrstft_forward.argtypes = [vp, ll, vp, ll, vp, ctypes.POINTER(MrstftCfg), i, i, vp, vp, vp, sz, vp]
+    l.dmst_afl_workspace_bytes.restype = sz
+    l.dmst_afl_workspace_bytes.argtypes = [i, i, i, i]
+    fp5 = ctypes.POINTER(ctypes.c_float)
+    l.dmst_afl_forward.restype = i
+    l.dmst_afl_forward.argtypes = [vp, vp, ll, ll, vp, vp, fp5, i, i, i, i, vp, vp, sz, vp]
+    l.dmst_afl_backward.restype = i
+    l.dmst_afl_backward.argtypes = [vp, ll, ll, vp, vp, fp5, vp, i, i, i, i, vp, vp, sz, vp]
+    l.dmst_peak_normalize.restype = i
+    l.dmst_peak_normalize.argtypes = [vp, ll, ll, vp, i, i, vp]
     _lib = l
     return l
 

@@ -1,5 +1,8 @@
 // extern "C" entry points of libdiffmst_b200.so (include/diffmst_b200.h).
 #include "console_host.cuh"
+#include "afl.cuh"
+#include "mrstft.cuh"
+#include "peaknorm.cuh"
 
 extern "C" {
 
@@ -37,6 +40,68 @@ int dmst_console_backward(const float* tracks, long long tracks_batch_stride, lo
     return dmst::console_backward(k, grad_mix, grad_mixed_tracks, grad_track_params, grad_master_params,
                                   grad_tracks, workspace, workspace_bytes,
                                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t dmst_mrstft_workspace_bytes(const dmst_mrstft_cfg* cfg, int rows, int T) {
+#ifndef DMST_EMULATE
+    if (!cfg || cfg->n_res <= 0 || cfg->n_res > DMST_MRSTFT_MAX_RES || rows <= 0 || T <= 0) return 0;
+    dmst::MrWs w;
+    if (dmst::mr_carve(nullptr, cfg, rows, T, &w) != 0) return 0;
+    return w.total;
+#else
+    return 0;
+#endif
+}
+
+int dmst_mrstft_forward(const float* x, long long x_row_stride, const float* y, long long y_row_stride,
+                        const float* windows, const dmst_mrstft_cfg* cfg, int rows, int T, float* loss,
+                        float* grad_x, void* workspace, size_t workspace_bytes, void* stream) {
+#ifndef DMST_EMULATE
+    return dmst::mrstft_run(x, x_row_stride, y, y_row_stride, windows, cfg, rows, T, loss, grad_x, workspace,
+                            workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+#else
+    return DMST_EINVAL;
+#endif
+}
+
+size_t dmst_afl_workspace_bytes(int B, int T, int fft_size, int n_bands) {
+#ifndef DMST_EMULATE
+    dmst::AflWs w;
+    if (dmst::afl_carve(nullptr, B, T, fft_size, n_bands, &w) != 0) return 0;
+    return w.total;
+#else
+    return 0;
+#endif
+}
+
+int dmst_afl_forward(const float* input, const float* target, long long batch_stride, long long ch_stride,
+                     const float* bark_fb, const float* window, const float* weights_host, int B, int T,
+                     int fft_size, int n_bands, float* losses, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+#ifndef DMST_EMULATE
+    return dmst::afl_forward(input, target, batch_stride, ch_stride, bark_fb, window, weights_host, B, T, fft_size,
+                             n_bands, losses, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+#else
+    return DMST_EINVAL;
+#endif
+}
+
+int dmst_afl_backward(const float* input, long long batch_stride, long long ch_stride, const float* bark_fb,
+                      const float* window, const float* weights_host, const float* grad_w, int B, int T,
+                      int fft_size, int n_bands, float* grad_input, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+#ifndef DMST_EMULATE
+    return dmst::afl_backward(input, batch_stride, ch_stride, bark_fb, window, weights_host, grad_w, B, T, fft_size,
+                              n_bands, grad_input, workspace, workspace_bytes,
+                              reinterpret_cast<cudaStream_t>(stream));
+#else
+    return DMST_EINVAL;
+#endif
+}
+
+int dmst_peak_normalize(const float* x, long long batch_stride, long long ch_stride, float* y, int B, int T,
+                        void* stream) {
+    return dmst::peak_normalize(x, batch_stride, ch_stride, y, B, T, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

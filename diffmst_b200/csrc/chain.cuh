@@ -94,6 +94,97 @@ __device__ __forceinline__ void store_chunk(float* p, int valid, bool vec_ok, co
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Second-level scans over the NW warp aggregates of a CTA, done redundantly by every warp
+// with shuffles (no divergent loops, one barrier per recurrence).
+//
+// Forward: sW[u] = end state of warp u with zero warp carry-in; (sin1, sin2) = tile carry-in.
+// Returns the carry-in (c1, c2) of the calling warp and the end state of the tile.
+// ---------------------------------------------------------------------------------
+template <int NW>
+__device__ __forceinline__ void cross_warp_fwd(const float* sW, int stride, const float (*P2)[4], float sin1,
+                                               float sin2, int lane, int warp, float& c1, float& c2,
+                                               float& end1, float& end2) {
+    float w1 = 0.0f, w2 = 0.0f;
+    if (lane < NW) { w1 = sW[lane * stride]; w2 = sW[lane * stride + 1]; }
+    if (lane == 0) mat2_apply_acc(P2[5], sin1, sin2, w1, w2);  // fold the tile carry-in into warp 0
+#pragma unroll
+    for (int j = 0; (1 << j) < NW; ++j) {
+        const float t1 = __shfl_up_sync(0xffffffffu, w1, 1 << j);
+        const float t2 = __shfl_up_sync(0xffffffffu, w2, 1 << j);
+        if (lane >= (1 << j)) mat2_apply_acc(P2[5 + j], t1, t2, w1, w2);
+    }
+    end1 = __shfl_sync(0xffffffffu, w1, NW - 1);
+    end2 = __shfl_sync(0xffffffffu, w2, NW - 1);
+    const int src = warp > 0 ? warp - 1 : 0;
+    c1 = __shfl_sync(0xffffffffu, w1, src);
+    c2 = __shfl_sync(0xffffffffu, w2, src);
+    if (warp == 0) { c1 = sin1; c2 = sin2; }
+}
+// Reverse: sW[u] = state at the START of warp u with zero right carry; (sin1, sin2) = state at
+// the start of the successor tile.  Transposed matrices (reverse all-pole recursion).
+template <int NW>
+__device__ __forceinline__ void cross_warp_rev(const float* sW, int stride, const float (*P2)[4], float sin1,
+                                               float sin2, int lane, int warp, float& c1, float& c2,
+                                               float& start1, float& start2) {
+    float w1 = 0.0f, w2 = 0.0f;
+    if (lane < NW) { w1 = sW[lane * stride]; w2 = sW[lane * stride + 1]; }
+    if (lane == NW - 1) mat2T_apply_acc(P2[5], sin1, sin2, w1, w2);
+#pragma unroll
+    for (int j = 0; (1 << j) < NW; ++j) {
+        const float t1 = __shfl_down_sync(0xffffffffu, w1, 1 << j);
+        const float t2 = __shfl_down_sync(0xffffffffu, w2, 1 << j);
+        if (lane + (1 << j) < NW) mat2T_apply_acc(P2[5 + j], t1, t2, w1, w2);
+    }
+    start1 = __shfl_sync(0xffffffffu, w1, 0);
+    start2 = __shfl_sync(0xffffffffu, w2, 0);
+    const int src = warp < NW - 1 ? warp + 1 : NW - 1;
+    c1 = __shfl_sync(0xffffffffu, w1, src);
+    c2 = __shfl_sync(0xffffffffu, w2, src);
+    if (warp == NW - 1) { c1 = sin1; c2 = sin2; }
+}
+// scalar (one-pole) versions; a2pow[j] = alpha^(L 2^j)
+template <int NW>
+__device__ __forceinline__ void cross_warp_fwd1(const float* sW, int stride, const float* a2pow, float sin,
+                                                int lane, int warp, float& c, float& end) {
+    float w = (lane < NW) ? sW[lane * stride] : 0.0f;
+    if (lane == 0) w = fmaf(a2pow[5], sin, w);
+#pragma unroll
+    for (int j = 0; (1 << j) < NW; ++j) {
+        const float t = __shfl_up_sync(0xffffffffu, w, 1 << j);
+        if (lane >= (1 << j)) w = fmaf(a2pow[5 + j], t, w);
+    }
+    end = __shfl_sync(0xffffffffu, w, NW - 1);
+    c = __shfl_sync(0xffffffffu, w, warp > 0 ? warp - 1 : 0);
+    if (warp == 0) c = sin;
+}
+template <int NW>
+__device__ __forceinline__ void cross_warp_rev1(const float* sW, int stride, const float* a2pow, float sin,
+                                                int lane, int warp, float& c, float& start) {
+    float w = (lane < NW) ? sW[lane * stride] : 0.0f;
+    if (lane == NW - 1) w = fmaf(a2pow[5], sin, w);
+#pragma unroll
+    for (int j = 0; (1 << j) < NW; ++j) {
+        const float t = __shfl_down_sync(0xffffffffu, w, 1 << j);
+        if (lane + (1 << j) < NW) w = fmaf(a2pow[5 + j], t, w);
+    }
+    start = __shfl_sync(0xffffffffu, w, 0);
+    c = __shfl_sync(0xffffffffu, w, warp < NW - 1 ? warp + 1 : NW - 1);
+    if (warp == NW - 1) c = sin;
+}
+
+// 4 consecutive floats from global memory with bounds (zero beyond `valid`)
+__device__ __forceinline__ float4 load4(const float* p, int valid, bool vec_ok) {
+    if (vec_ok && valid >= 4) return __ldg(reinterpret_cast<const float4*>(p));
+    float4 r;
+    r.x = valid > 0 ? __ldg(p) : 0.0f;
+    r.y = valid > 1 ? __ldg(p + 1) : 0.0f;
+    r.z = valid > 2 ? __ldg(p + 2) : 0.0f;
+    r.w = valid > 3 ? __ldg(p + 3) : 0.0f;
+    return r;
+}
+
 // Static-curve gain computer of the dasp compressor, branch-free:
 // t = x_db - (thr - knee/2); g_c = slope * (clamp(t,0,W)^2/(2W) + max(t-W,0)).
 __device__ __forceinline__ float gain_computer(float side, const RowTab& tb, float& tc, float& lin) {

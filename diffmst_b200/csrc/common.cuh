@@ -15,7 +15,7 @@
 #define DMST_LAUNCH(kernel, grid, block, smem, stream, ...) \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define DMST_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
-#define DMST_SHARED_ARRAY(type, name, count) __shared__ type name[count]
+#define DMST_SHARED_ARRAY(type, name, count) __shared__ __align__(16) type name[count]
 #define DMST_DEVICE_BUILD 1
 #endif
 
@@ -38,14 +38,15 @@ constexpr float kCompEps = 1e-8f;                      // dasp compressor eps (A
 // A biquad section in transposed direct form II has the 2-vector state s and the
 // transition s' = A s + B x with A = [[-a1, 1], [-a2, 0]].  With each thread owning L
 // consecutive samples, P = A^L advances the state across one thread chunk:
-//   P2[j] = P^(2^j)  (warp Kogge-Stone steps),  Q = P^32 (across a warp),
+//   P2[j] = P^(2^j), j = 0..8: j < 5 are the warp Kogge-Stone steps, P2[5] = P^32 advances
+//   across a whole warp and P2[5..8] are the steps of the second-level scan over warps,
 //   Ppow[l] = P^l    (warp carry-in -> lane carry-in).
 // Matrices are row-major {m00, m01, m10, m11}.
 // ---------------------------------------------------------------------------------
 struct SectionTab {
     float b0, b1, b2, a1, a2, inv_b0, pad0, pad1;
-    float P2[5][4];
-    float Q[4];
+    float P2[9][4];
+    float pad2[4];
     float Ppow[32][4];
 };
 
@@ -61,9 +62,8 @@ struct RowTab {
     float makeup;
     float inv_ratio2;       // 1/ratio^2 (backward)
     float pad[3];
-    float a2pow[5];         // alpha^(L*2^j)
-    float aQ;               // alpha^(32 L)
-    float pad2[2];
+    float a2pow[9];         // alpha^(L*2^j), j = 0..8
+    float pad2[3];
     float a_lane[32];       // alpha^(L*l)
     float a_i[kMaxL];       // alpha^(i+1)
 };
@@ -108,6 +108,17 @@ __device__ __forceinline__ void wait_flag_ge(const int* p, int v) {
 
 // padded shared-memory index: conflict-free when lane l touches element l*L + i
 __host__ __device__ __forceinline__ int pidx(int i) { return i + (i >> 5); }
+
+// 2^x by the MUFU unit (ex2.approx: relative error below 2^-22, flushes subnormal results)
+__device__ __forceinline__ float fast_exp2(float x) {
+#ifdef DMST_EMULATE
+    return exp2f(x);
+#else
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#endif
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -7,11 +7,10 @@
 //      successor tile),
 //   3. runs the adjoint of each biquad section in reverse order: reverse-time all-pole
 //      recursion g = (1/A)^T u solved with the same matrix-power scan (transposed
-//      matrices), coefficient gradients db_j = sum g[n] x[n-j], da_j = -sum g[n] y[n-j] (accumulated in a
-//      differenced basis, see below),
-//      input gradient B^T g.  The section input x is recovered from its output with the
-//      inverse recursion that shares the section's state trajectory, so only two signals
-//      live in registers at a time,
+//      matrices), coefficient gradients db_j = sum g[n] x[n-j], da_j = -sum g[n] y[n-j]
+//      (accumulated in a differenced basis, see below), input gradient B^T g.  The section
+//      input x is recovered from its output with the inverse recursion that shares the
+//      section's state trajectory, so only two signals live in registers at a time,
 //   4. writes per-tile partial sums; console_prepare.cuh's epilogue chains them through the
 //      parameter Jacobian.
 // Gradient definitions follow the float64 autograd of the oracle (tests/golden).
@@ -23,8 +22,8 @@ namespace dmst {
 constexpr int kBFlagComp = 1;  // reverse smoother state + dhead published
 // section k (5..0) published <=> bflag >= 2 + (5 - k)
 
-template <int NCH, int L, int NT, bool MASTER>
-__global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
+template <int NCH, int L, int NT, bool MASTER, int MINB>
+__global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
     constexpr int NW = NT / 32;
     constexpr int TILE = NT * L;
     static_assert(L % 4 == 0 && L <= kMaxL, "chunk length");
@@ -64,11 +63,13 @@ __global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
     const float* bstate_in = a.bstate + (rt + 1) * kStateStride;
     int* my_flag = a.bflag + rt;
     const int* succ_flag = my_flag + 1;
+    const int bb = MASTER ? row : row / a.N;
+    const int nn = MASTER ? 0 : row - bb * a.N;
+    const bool uvec = a.user_vec_ok != 0;
 
     float v[NCH][L];
     if constexpr (!MASTER) {
-        const int b = row / a.N, n = row - b * a.N;
-        load_chunk<L>(a.src + (long long)b * a.src_batch_stride + (long long)n * a.src_row_stride + t0,
+        load_chunk<L>(a.src + (long long)bb * a.src_batch_stride + (long long)nn * a.src_row_stride + t0,
                       a.T - t0, a.src_vec_ok != 0, v[0]);
     } else {
 #pragma unroll
@@ -127,13 +128,10 @@ __global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
             __syncthreads();
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                float c1 = has_pred ? __ldg(state_in + (k * NCH + c) * 2 + 0) : 0.0f;
-                float c2 = has_pred ? __ldg(state_in + (k * NCH + c) * 2 + 1) : 0.0f;
-                for (int u = 0; u < warp; ++u) {
-                    float n1 = s_W[((k * NW + u) * NCH + c) * 2 + 0], n2 = s_W[((k * NW + u) * NCH + c) * 2 + 1];
-                    mat2_apply_acc(st.Q, c1, c2, n1, n2);
-                    c1 = n1; c2 = n2;
-                }
+                const float i1 = has_pred ? __ldg(state_in + (k * NCH + c) * 2 + 0) : 0.0f;
+                const float i2 = has_pred ? __ldg(state_in + (k * NCH + c) * 2 + 1) : 0.0f;
+                float c1, c2, n1, n2;
+                cross_warp_fwd<NW>(s_W + (k * NW * NCH + c) * 2, NCH * 2, st.P2, i1, i2, lane, warp, c1, c2, n1, n2);
                 mat2_apply_acc(st.Ppow[lane], c1, c2, e1[c], e2[c]);
                 sE[((k * NCH + c) * 2 + 0) * NT + tid] = e1[c];
                 sE[((k * NCH + c) * 2 + 1) * NT + tid] = e2[c];
@@ -149,35 +147,64 @@ __global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
         }
     }
 
-    // ---------------- upstream gradient w.r.t. the chain output ----------------
     float u[NCH][L];
     float acc_gout = 0.0f, acc_gl = 0.0f, acc_gr = 0.0f;
-    float dbl[L], dbr[L];
-    if constexpr (!MASTER) {
-        const int b = row / a.N, n = row - b * a.N;
-        load_chunk<L>(a.gout + (long long)(b * 2 + 0) * a.Tp + t0, a.Tp - t0, true, dbl);
-        load_chunk<L>(a.gout + (long long)(b * 2 + 1) * a.Tp + t0, a.Tp - t0, true, dbr);
-        if (a.gmixed) {
-            float t[L];
-            load_chunk<L>(a.gmixed + ((long long)(b * 2 + 0) * a.N + n) * a.T + t0, a.T - t0, a.user_vec_ok != 0, t);
-#pragma unroll
-            for (int i = 0; i < L; ++i) dbl[i] += t[i];
-            load_chunk<L>(a.gmixed + ((long long)(b * 2 + 1) * a.N + n) * a.T + t0, a.T - t0, a.user_vec_ok != 0, t);
-#pragma unroll
-            for (int i = 0; i < L; ++i) dbr[i] += t[i];
-        }
-#pragma unroll
-        for (int i = 0; i < L; ++i) {
-            if (t0 + i >= a.T) { dbl[i] = 0.0f; dbr[i] = 0.0f; }
-            u[0][i] = fmaf(tb.gL, dbl[i], tb.gR * dbr[i]);
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-            load_chunk<L>(a.gout + (long long)(row * NCH + c) * a.T + t0, a.T - t0, a.user_vec_ok != 0, u[c]);
-    }
-
     float acc_comp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // alpha, thr, ratio, knee, makeup
+
+    // Pass over the chunk that forms, per sample, the gradient w.r.t. the compressor output
+    // (tracks: gL*dbusL + gR*dbusR [+ grad of mixed_tracks]; master: g_out * dmix) and hands it
+    // with the compressor output `o` (or the EQ output when the compressor is off) to `fn`.
+    auto for_each_upstream = [&](auto&& out_of, auto&& fn) {
+#pragma unroll
+        for (int i0 = 0; i0 < L; i0 += 4) {
+            float d[NCH][4];
+            float bl[4] = {0.f, 0.f, 0.f, 0.f}, br[4] = {0.f, 0.f, 0.f, 0.f};
+            if constexpr (MASTER) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const float4 g4 = load4(a.gout + (long long)(row * NCH + c) * a.T + t0 + i0, a.T - t0 - i0, uvec);
+                    d[c][0] = g4.x; d[c][1] = g4.y; d[c][2] = g4.z; d[c][3] = g4.w;
+                }
+            } else {
+                const float4 l4 = load4(a.gout + (long long)(bb * 2 + 0) * a.Tp + t0 + i0, a.Tp - t0 - i0, true);
+                const float4 r4 = load4(a.gout + (long long)(bb * 2 + 1) * a.Tp + t0 + i0, a.Tp - t0 - i0, true);
+                bl[0] = l4.x; bl[1] = l4.y; bl[2] = l4.z; bl[3] = l4.w;
+                br[0] = r4.x; br[1] = r4.y; br[2] = r4.z; br[3] = r4.w;
+                if (a.gmixed) {
+                    const float4 ml = load4(a.gmixed + ((long long)(bb * 2 + 0) * a.N + nn) * a.T + t0 + i0, a.T - t0 - i0, uvec);
+                    const float4 mr = load4(a.gmixed + ((long long)(bb * 2 + 1) * a.N + nn) * a.T + t0 + i0, a.T - t0 - i0, uvec);
+                    bl[0] += ml.x; bl[1] += ml.y; bl[2] += ml.z; bl[3] += ml.w;
+                    br[0] += mr.x; br[1] += mr.y; br[2] += mr.z; br[3] += mr.w;
+                }
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d[c][j] = 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j;
+                const bool live = (t0 + i) < a.T;
+                float dc[NCH], o[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    o[c] = out_of(c, i);
+                    if constexpr (MASTER) {
+                        float g = live ? d[c][j] : 0.0f;
+                        if (a.flags & kChainOutGain) { acc_gout = fmaf(g, o[c] * tb.g_out, acc_gout); g *= tb.g_out; }
+                        dc[c] = g;
+                    } else {
+                        const float l = live ? bl[j] : 0.0f, r = live ? br[j] : 0.0f;
+                        acc_gl = fmaf(l, o[c], acc_gl);
+                        acc_gr = fmaf(r, o[c], acc_gr);
+                        dc[c] = fmaf(tb.gL, l, tb.gR * r);
+                    }
+                }
+                fn(i, dc, o);
+            }
+        }
+    };
+
     if (a.flags & kChainComp) {
         // ---- forward recompute: delay line, smoothed gain ----
 #pragma unroll
@@ -186,10 +213,10 @@ __global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
             for (int i = 0; i < L; ++i) ebuf[c * buf_stride + pidx(LA + tid * L + i)] = v[c][i];
         {
             const float* etail_in = a.etail + (rt - 1) * NCH * LA;
-            for (int idx = tid; idx < NCH * LA; idx += NT) {
-                const int c = idx / LA, j = idx - c * LA;
-                ebuf[c * buf_stride + pidx(j)] = has_pred ? __ldg(etail_in + idx) : 0.0f;
-            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+                for (int j = tid; j < LA; j += NT)
+                    ebuf[c * buf_stride + pidx(j)] = has_pred ? __ldg(etail_in + c * LA + j) : 0.0f;
         }
         float gs[L];
         float gz = 0.0f;
@@ -212,8 +239,9 @@ __global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
         if (lane == 0) ex = 0.0f;
         if (lane == 31) s_W[(6 * NW + warp) * NCH * 2] = gz;
         __syncthreads();  // ebuf + smoother aggregates visible
-        float cw = has_pred ? __ldg(state_in + kStateSmooth) : 0.0f;
-        for (int w = 0; w < warp; ++w) cw = fmaf(tb.aQ, cw, s_W[(6 * NW + w) * NCH * 2]);
+        float cw, gend;
+        cross_warp_fwd1<NW>(s_W + 6 * NW * NCH * 2, NCH * 2, tb.a2pow,
+                            has_pred ? __ldg(state_in + kStateSmooth) : 0.0f, lane, warp, cw, gend);
         const float gcarry = fmaf(tb.a_lane[lane], cw, ex);  // g_s just before this chunk
 #pragma unroll
         for (int i = 0; i < L; ++i) gs[i] = fmaf(tb.a_i[i], gcarry, gs[i]);
@@ -221,28 +249,24 @@ __global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
         // ---- adjoint: output -> (delayed signal path, gain path) ----
         float q[L];
         float* dhead_out = a.dhead + rt * NCH * LA;
+        float Gi = 0.0f;
+        for_each_upstream(
+            [&](int c, int i) {
+                if (c == 0) Gi = fast_exp2(kLog2Per20Db * (gs[i] + tb.makeup));
+                return ebuf[c * buf_stride + pidx(tid * L + i)] * Gi;
+            },
+            [&](int i, const float* dc, const float* o) {
+                float r = 0.0f;
 #pragma unroll
-        for (int i = 0; i < L; ++i) {
-            const float G = exp2f(kLog2Per20Db * (gs[i] + tb.makeup));
-            float r = 0.0f;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const float o = ebuf[c * buf_stride + pidx(tid * L + i)] * G;  // chain output (pre out-gain)
-                float dcomp = u[c][i];
-                if constexpr (MASTER) {
-                    if (a.flags & kChainOutGain) { acc_gout = fmaf(dcomp, o * tb.g_out, acc_gout); dcomp *= tb.g_out; }
-                } else {
-                    acc_gl = fmaf(dbl[i], o, acc_gl);
-                    acc_gr = fmaf(dbr[i], o, acc_gr);
+                for (int c = 0; c < NCH; ++c) {
+                    r = fmaf(dc[c], o[c], r);
+                    const float dyG = dc[c] * Gi;
+                    dbuf[c * buf_stride + pidx(tid * L + i)] = dyG;
+                    if (tid * L + i < LA) dhead_out[c * LA + tid * L + i] = dyG;
                 }
-                r = fmaf(dcomp, o, r);
-                const float dyG = dcomp * G;
-                dbuf[c * buf_stride + pidx(tid * L + i)] = dyG;
-                if (tid * L + i < LA) dhead_out[c * LA + tid * L + i] = dyG;
-            }
-            q[i] = r * kLn10Over20;
-            acc_comp[4] += q[i];
-        }
+                q[i] = r * kLn10Over20;
+                acc_comp[4] += q[i];
+            });
         // ---- reverse one-pole: p[n] = q[n] + alpha p[n+1] ----
         float pz = 0.0f;
 #pragma unroll
@@ -264,10 +288,10 @@ __global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
             }
         }
         __syncthreads();  // dbuf (own tile), reverse aggregates, successor state visible
-        float pc = s_in[7 * NCH * 2];
-        for (int w = NW - 1; w > warp; --w) pc = fmaf(tb.aQ, pc, s_W[(7 * NW + w) * NCH * 2]);
+        float pc, pstart;
+        cross_warp_rev1<NW>(s_W + 7 * NW * NCH * 2, NCH * 2, tb.a2pow, s_in[7 * NCH * 2], lane, warp, pc, pstart);
         if (tid == 0) {
-            bstate_out[kStateSmooth] = fmaf(tb.aQ, pc, s_W[(7 * NW + 0) * NCH * 2]);
+            bstate_out[kStateSmooth] = pstart;
             __threadfence();  // also orders every thread's dhead stores (made before the barrier)
             st_release(my_flag, kBFlagComp);
         }
@@ -275,10 +299,10 @@ __global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
         // halo of dy*G from the successor tile
         {
             const float* dhead_in = a.dhead + (rt + 1) * NCH * LA;
-            for (int idx = tid; idx < NCH * LA; idx += NT) {
-                const int c = idx / LA, j = idx - c * LA;
-                dbuf[c * buf_stride + pidx(TILE + j)] = has_succ ? __ldcg(dhead_in + idx) : 0.0f;
-            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+                for (int j = tid; j < LA; j += NT)
+                    dbuf[c * buf_stride + pidx(TILE + j)] = has_succ ? __ldcg(dhead_in + c * LA + j) : 0.0f;
         }
         __syncthreads();
         float gprev = gcarry;
@@ -302,18 +326,11 @@ __global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
         }
     } else {
         // no compressor: chain output = EQ output
+        for_each_upstream([&](int c, int i) { return v[c][i]; },
+                          [&](int i, const float* dc, const float*) {
 #pragma unroll
-        for (int i = 0; i < L; ++i) {
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                if constexpr (MASTER) {
-                    if (a.flags & kChainOutGain) { acc_gout = fmaf(u[c][i], v[c][i] * tb.g_out, acc_gout); u[c][i] *= tb.g_out; }
-                } else {
-                    acc_gl = fmaf(dbl[i], v[c][i], acc_gl);
-                    acc_gr = fmaf(dbr[i], v[c][i], acc_gr);
-                }
-            }
-        }
+                              for (int c = 0; c < NCH; ++c) u[c][i] = dc[c];
+                          });
     }
     {
         float t;
@@ -413,16 +430,10 @@ __global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
             __syncthreads();
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                // warp right-carry: C_{NW-1} = successor tile state, C_w = W_{w+1} + Q^T C_{w+1}
-                float c1 = s_in[(k * NCH + c) * 2 + 0], c2 = s_in[(k * NCH + c) * 2 + 1];
-                for (int w = NW - 1; w > warp; --w) {
-                    float n1 = s_W[((k * NW + w) * NCH + c) * 2 + 0], n2 = s_W[((k * NW + w) * NCH + c) * 2 + 1];
-                    mat2T_apply_acc(st.Q, c1, c2, n1, n2);
-                    c1 = n1; c2 = n2;
-                }
+                float c1, c2, n1, n2;
+                cross_warp_rev<NW>(s_W + (k * NW * NCH + c) * 2, NCH * 2, st.P2, s_in[(k * NCH + c) * 2 + 0],
+                                   s_in[(k * NCH + c) * 2 + 1], lane, warp, c1, c2, n1, n2);
                 if (tid == 0) {
-                    float n1 = s_W[((k * NW + 0) * NCH + c) * 2 + 0], n2 = s_W[((k * NW + 0) * NCH + c) * 2 + 1];
-                    mat2T_apply_acc(st.Q, c1, c2, n1, n2);
                     bstate_out[(k * NCH + c) * 2 + 0] = n1;
                     bstate_out[(k * NCH + c) * 2 + 1] = n2;
                 }
@@ -502,7 +513,7 @@ __global__ void __launch_bounds__(NT) chain_bwd_kernel(ChainArgs a) {
         } else if (a.gsrc) {
 #pragma unroll
             for (int i = 0; i < L; ++i) u[0][i] *= g;
-            store_chunk<L>(a.gsrc + (long long)row * a.T + t0, a.T - t0, a.user_vec_ok != 0, u[0]);
+            store_chunk<L>(a.gsrc + (long long)row * a.T + t0, a.T - t0, uvec, u[0]);
         }
     }
     __syncthreads();

@@ -143,25 +143,20 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
                 }
             }
             __syncthreads();
-            // warp carry-in: C_0 = tile carry-in, C_{w+1} = Q C_w + W_w
+            // second-level scan over warps -> warp carry-in; publish the tile end state
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                float c1 = s_in[(k * NCH + c) * 2 + 0], c2 = s_in[(k * NCH + c) * 2 + 1];
-                for (int u = 0; u < warp; ++u) {
-                    float n1 = s_W[((k * NW + u) * NCH + c) * 2 + 0], n2 = s_W[((k * NW + u) * NCH + c) * 2 + 1];
-                    mat2_apply_acc(st.Q, c1, c2, n1, n2);
-                    c1 = n1; c2 = n2;
-                }
-                if (warp == NW - 1 && lane == 0) {
-                    float n1 = s_W[((k * NW + warp) * NCH + c) * 2 + 0], n2 = s_W[((k * NW + warp) * NCH + c) * 2 + 1];
-                    mat2_apply_acc(st.Q, c1, c2, n1, n2);
+                float c1, c2, n1, n2;
+                cross_warp_fwd<NW>(s_W + (k * NW * NCH + c) * 2, NCH * 2, st.P2, s_in[(k * NCH + c) * 2 + 0],
+                                   s_in[(k * NCH + c) * 2 + 1], lane, warp, c1, c2, n1, n2);
+                if (tid == 0) {
                     state_out[(k * NCH + c) * 2 + 0] = n1;
                     state_out[(k * NCH + c) * 2 + 1] = n2;
                 }
                 // lane carry-in = exclusive prefix + P^lane * C_w
                 mat2_apply_acc(st.Ppow[lane], c1, c2, e1[c], e2[c]);
             }
-            if (warp == NW - 1 && lane == 0) {
+            if (tid == 0) {
                 __threadfence();
                 st_release(my_flag, k + 1);
             }
@@ -235,10 +230,10 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
             }
         }
         __syncthreads();
-        float cw = s_in[6 * NCH * 2];
-        for (int u = 0; u < warp; ++u) cw = fmaf(tb.aQ, cw, s_W[(6 * NW + u) * NCH * 2]);
-        if (warp == NW - 1 && lane == 0) {
-            state_out[kStateSmooth] = fmaf(tb.aQ, cw, s_W[(6 * NW + warp) * NCH * 2]);
+        float cw, gend;
+        cross_warp_fwd1<NW>(s_W + 6 * NW * NCH * 2, NCH * 2, tb.a2pow, s_in[6 * NCH * 2], lane, warp, cw, gend);
+        if (tid == 0) {
+            state_out[kStateSmooth] = gend;
             __threadfence();  // also orders every thread's etail stores (made before the barrier)
             st_release(my_flag, kFlagSmooth);
         }
@@ -246,17 +241,17 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
         // halo: predecessor's last LA EQ outputs (zeros before the start of the signal)
         {
             const float* etail_in = a.etail + ((long long)row * a.ntiles + tile - 1) * NCH * LA;
-            for (int idx = tid; idx < NCH * LA; idx += NT) {
-                const int c = idx / LA, j = idx - c * LA;
-                ebuf[c * ebuf_stride + pidx(j)] = (tile > 0) ? __ldcg(etail_in + idx) : 0.0f;
-            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+                for (int j = tid; j < LA; j += NT)
+                    ebuf[c * ebuf_stride + pidx(j)] = (tile > 0) ? __ldcg(etail_in + c * LA + j) : 0.0f;
         }
         __syncthreads();
         const float makeup = tb.makeup;
 #pragma unroll
         for (int i = 0; i < L; ++i) {
             const float gtrue = fmaf(tb.a_i[i], carry, g[i]);
-            const float G = exp2f(kLog2Per20Db * (gtrue + makeup));
+            const float G = fast_exp2(kLog2Per20Db * (gtrue + makeup));
 #pragma unroll
             for (int c = 0; c < NCH; ++c) v[c][i] = ebuf[c * ebuf_stride + pidx(tid * L + i)] * G;
         }

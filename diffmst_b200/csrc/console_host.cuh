@@ -12,10 +12,12 @@ namespace dmst {
 
 // Tile geometry.  Forward and backward must agree on NT*L per row kind because backward
 // restarts each tile from the carry-in states the forward pass saved.
-constexpr int kTrackL = 16, kTrackNT = 256;     // 4096-sample tiles
-constexpr int kMasterL = 16, kMasterNT = 256;   // 4096-sample tiles, 2 channels per thread
-constexpr int kTrackTile = kTrackL * kTrackNT;
+constexpr int kTrackFwdL = 32, kTrackFwdNT = 256;   // 8192-sample tiles
+constexpr int kTrackBwdL = 16, kTrackBwdNT = 512;
+constexpr int kMasterL = 16, kMasterNT = 256;       // 4096-sample tiles, 2 channels per thread
+constexpr int kTrackTile = kTrackFwdL * kTrackFwdNT;
 constexpr int kMasterTile = kMasterL * kMasterNT;
+static_assert(kTrackFwdL * kTrackFwdNT == kTrackBwdL * kTrackBwdNT, "forward/backward tiles must agree");
 
 #ifdef DMST_EMULATE
 #define DMST_MEMSET_ASYNC(ptr, val, bytes, stream) (memset((ptr), (val), (bytes)), 0)
@@ -42,7 +44,7 @@ struct Carver {
 
 struct ConsoleWs {
     int* header;          // [0..3] tickets (fwd track, fwd master, bwd master, bwd track)
-    RowTab *track_tab, *master_tab;
+    RowTab *track_tab, *track_tab_b, *master_tab;  // track_tab: forward L, track_tab_b: backward L
     float *y, *bus_pre, *dbus;
     // forward chain (kept for backward)
     int *t_flag, *m_flag;
@@ -65,6 +67,7 @@ inline ConsoleWs carve_console(void* base, int B, int N, int T, int la_t, int la
     const size_t rows = (size_t)B * N, rt = rows * w.nt_track, rm = (size_t)B * w.nt_master;
     w.header = c.take<int>(64);
     w.track_tab = c.take<RowTab>(rows);
+    w.track_tab_b = (kTrackBwdL == kTrackFwdL) ? w.track_tab : c.take<RowTab>(rows);
     w.master_tab = c.take<RowTab>(B);
     w.y = c.take<float>(rows * w.Tp);
     w.bus_pre = c.take<float>((size_t)B * 2 * w.Tp);
@@ -146,12 +149,14 @@ inline void fill_prepare(PrepareArgs& p, const ConsoleCall& k, bool master, Cons
         } else {
             for (int i = 0; i < DMST_NUM_TRACK_PARAMS; ++i) { p.lo[i] = k.ranges->track_lo[i]; p.hi[i] = k.ranges->track_hi[i]; }
         }
-        p.L = kTrackL; p.tab = w.track_tab; p.status_base = 0;
+        p.L[0] = kTrackFwdL; p.tab[0] = w.track_tab;
+        if (w.track_tab_b != w.track_tab) { p.L[1] = kTrackBwdL; p.tab[1] = w.track_tab_b; }
+        p.status_base = 0;
     } else {
         p.params = k.master_params; p.rows = k.B;
         p.np = DMST_NUM_MASTER_PARAMS; p.kind = 2;
         for (int i = 0; i < DMST_NUM_MASTER_PARAMS; ++i) { p.lo[i] = k.ranges->master_lo[i]; p.hi[i] = k.ranges->master_hi[i]; }
-        p.L = kMasterL; p.tab = w.master_tab; p.status_base = 1000;
+        p.L[0] = kMasterL; p.tab[0] = w.master_tab; p.status_base = 1000;
     }
     p.sr = (double)k.sr; p.status = status;
 }
@@ -196,10 +201,10 @@ inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* 
 
     PrepareArgs pt, pm;
     fill_prepare(pt, k, false, w, status);
-    DMST_LAUNCH(prepare_kernel, dim3((pt.rows * 8 + 127) / 128), dim3(128), 0, stream, pt);
+    DMST_LAUNCH(prepare_kernel, dim3(pt.rows), dim3(256), 0, stream, pt);
     fill_prepare(pm, k, true, w, status);
     if (!k.master_params) { pm.kind = 3; pm.np = 0; }
-    DMST_LAUNCH(prepare_kernel, dim3((pm.rows * 8 + 127) / 128), dim3(128), 0, stream, pm);
+    DMST_LAUNCH(prepare_kernel, dim3(pm.rows), dim3(256), 0, stream, pm);
 
     ChainArgs at, am;
     fill_chain(at, k, false, w);
@@ -207,10 +212,10 @@ inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* 
     at.mixed = mixed;
     at.user_vec_ok = mixed && aligned16(mixed) && (k.T % 4 == 0);
     {
-        auto kern = chain_fwd_kernel<1, kTrackL, kTrackNT, false>;
+        auto kern = chain_fwd_kernel<1, kTrackFwdL, kTrackFwdNT, false>;
         const size_t smem = fwd_smem_bytes(1, kTrackTile, k.la_t);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
-        DMST_LAUNCH(kern, dim3(at.nrows * at.ntiles), dim3(kTrackNT), smem, stream, at);
+        DMST_LAUNCH(kern, dim3(at.nrows * at.ntiles), dim3(kTrackFwdNT), smem, stream, at);
     }
     fill_chain(am, k, true, w);
     am.mix = mix;
@@ -242,7 +247,7 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
     am.user_vec_ok = aligned16(gmix) && (k.T % 4 == 0);
     am.ticket = w.header + 2;
     {
-        auto kern = chain_bwd_kernel<2, kMasterL, kMasterNT, true>;
+        auto kern = chain_bwd_kernel<2, kMasterL, kMasterNT, true, 1>;
         const size_t smem = bwd_smem_bytes(2, kMasterTile, k.la_m, kMasterNT);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
         DMST_LAUNCH(kern, dim3(am.nrows * am.ntiles), dim3(kMasterNT), smem, stream, am);
@@ -253,7 +258,7 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
         e.params = k.master_params; e.rows = k.B; e.np = DMST_NUM_MASTER_PARAMS; e.kind = 2;
         for (int i = 0; i < DMST_NUM_MASTER_PARAMS; ++i) { e.lo[i] = k.ranges->master_lo[i]; e.hi[i] = k.ranges->master_hi[i]; }
         e.sr = (double)k.sr; e.partial = w.m_partial; e.ntiles = w.nt_master; e.flags = am.flags; e.grad = gmp;
-        DMST_LAUNCH(grad_epilogue_kernel, dim3((e.rows + 63) / 64), dim3(64), 0, stream, e);
+        DMST_LAUNCH(grad_epilogue_kernel, dim3(e.rows), dim3(64), 0, stream, e);
     }
     fill_chain(at, k, false, w);
     at.gout = w.dbus; at.gmixed = gmixed;
@@ -261,10 +266,11 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
     at.user_vec_ok = (k.T % 4 == 0) && (!gmixed || aligned16(gmixed)) && (!at.gsrc || aligned16(at.gsrc));
     at.ticket = w.header + 3;
     {
-        auto kern = chain_bwd_kernel<1, kTrackL, kTrackNT, false>;
-        const size_t smem = bwd_smem_bytes(1, kTrackTile, k.la_t, kTrackNT);
+        auto kern = chain_bwd_kernel<1, kTrackBwdL, kTrackBwdNT, false, 1>;
+        const size_t smem = bwd_smem_bytes(1, kTrackTile, k.la_t, kTrackBwdNT);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
-        DMST_LAUNCH(kern, dim3(at.nrows * at.ntiles), dim3(kTrackNT), smem, stream, at);
+        at.tab = w.track_tab_b;
+        DMST_LAUNCH(kern, dim3(at.nrows * at.ntiles), dim3(kTrackBwdNT), smem, stream, at);
     }
     {
         EpilogueArgs e;
@@ -279,7 +285,7 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
             for (int i = 0; i < DMST_NUM_TRACK_PARAMS; ++i) { e.lo[i] = k.ranges->track_lo[i]; e.hi[i] = k.ranges->track_hi[i]; }
         }
         e.sr = (double)k.sr; e.partial = w.t_partial; e.ntiles = w.nt_track; e.flags = at.flags; e.grad = gtp;
-        DMST_LAUNCH(grad_epilogue_kernel, dim3((e.rows + 63) / 64), dim3(64), 0, stream, e);
+        DMST_LAUNCH(grad_epilogue_kernel, dim3(e.rows), dim3(64), 0, stream, e);
     }
     return DMST_LAST_ERROR();
 }

@@ -85,8 +85,8 @@ struct PrepareArgs {
     int kind;              // 0 advanced track, 1 basic track, 2 master, 3 neutral (no params)
     float lo[32], hi[32];
     double sr;
-    int L;                 // thread chunk length the tables are built for
-    RowTab* tab;           // [rows]
+    int L[2];              // thread chunk lengths the tables are built for (powers of two)
+    RowTab* tab[2];        // [rows] each; tab[1] may be null
     int* status;
     int status_base;       // added to the flat index reported in status[0]
 };
@@ -105,25 +105,31 @@ __device__ __forceinline__ double denorm(const Args& a, const float* p, int i) {
     return (double)p[i] * ((double)a.hi[i] - (double)a.lo[i]) + (double)a.lo[i];
 }
 
-// one thread per (row, job): jobs 0..5 = EQ sections, 6 = everything else, 7 = range check
+__device__ __forceinline__ M2 mpow_from_squares(const M2* sq, int e) {
+    // product of sq[j] (= base^(2^j)) over the set bits of e
+    M2 r = {1, 0, 0, 1};
+    for (int j = 0; j < 9; ++j)
+        if ((e >> j) & 1) r = mmul(r, sq[j]);
+    return r;
+}
+
+// One warp per (row, job): jobs 0..5 = EQ sections, job 6 = gains / compressor / pan, job 7 =
+// range check.  Lanes split the table entries (lane l builds P^l), everything in float64.
+// grid: rows blocks of 256 threads.
 __global__ void prepare_kernel(PrepareArgs a) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = gid >> 3, job = gid & 7;
-    if (row >= a.rows) return;
+    const int row = blockIdx.x;
+    const int job = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* p = a.params + (long long)row * a.np;
-    RowTab& tb = a.tab[row];
     const ParamMap pm = param_map(a.kind);
-    const int L = a.L;
 
     if (job == 7) {
         int bad = 0x7fffffff;
-        for (int i = 0; i < a.np; ++i)
-            if (p[i] < 0.0f || p[i] > 1.0f) { bad = a.status_base + 1 + i; break; }
+        for (int i = lane; i < a.np; i += 32)
+            if (p[i] < 0.0f || p[i] > 1.0f) bad = min(bad, a.status_base + 1 + i);
         if (bad != 0x7fffffff) atomicMin(a.status, bad);
         return;
     }
     if (job < 6) {
-        SectionTab& st = tb.sec[job];
         double cf[5] = {1, 0, 0, 0, 0};
         if (pm.eq0 >= 0) {
             Dual o[5];
@@ -131,32 +137,30 @@ __global__ void prepare_kernel(PrepareArgs a) {
                        denorm(a, p, pm.eq0 + 3 * job + 2), a.sr, section_kind(job), o);
             for (int j = 0; j < 5; ++j) cf[j] = o[j].v;
         }
-        st.b0 = (float)cf[0]; st.b1 = (float)cf[1]; st.b2 = (float)cf[2];
-        st.a1 = (float)cf[3]; st.a2 = (float)cf[4];
-        st.inv_b0 = (float)(1.0 / (double)st.b0);
-        st.pad0 = st.pad1 = 0.0f;
+        const float fb0 = (float)cf[0], fb1 = (float)cf[1], fb2 = (float)cf[2], fa1 = (float)cf[3], fa2 = (float)cf[4];
         // powers of the state matrix of the recursion the kernels actually run
         // (float32-rounded a1, a2), evaluated in float64
-        M2 A = {-(double)st.a1, 1.0, -(double)st.a2, 0.0};
-        M2 P = A;
-        for (int s = 1; s < L; s <<= 1) P = mmul(P, P);  // A^L, L a power of two
-        M2 Pj = P;
-        for (int j = 0; j < 5; ++j) { mstore(st.P2[j], Pj); Pj = mmul(Pj, Pj); }
-        mstore(st.Q, Pj);  // P^32
-        M2 R = {1, 0, 0, 1};
-        for (int l = 0; l < 32; ++l) { mstore(st.Ppow[l], R); R = mmul(R, P); }
+        const M2 A = {-(double)fa1, 1.0, -(double)fa2, 0.0};
+        for (int v = 0; v < 2; ++v) {
+            if (!a.tab[v]) continue;
+            SectionTab& st = a.tab[v][row].sec[job];
+            M2 P = A;
+            for (int s = 1; s < a.L[v]; s <<= 1) P = mmul(P, P);  // A^L
+            M2 sq[9];
+            sq[0] = P;
+            for (int j = 1; j < 9; ++j) sq[j] = mmul(sq[j - 1], sq[j - 1]);
+            mstore(st.Ppow[lane], mpow_from_squares(sq, lane));
+            if (lane < 9) mstore(st.P2[lane], sq[lane]);
+            if (lane == 9) {
+                st.b0 = fb0; st.b1 = fb1; st.b2 = fb2; st.a1 = fa1; st.a2 = fa2;
+                st.inv_b0 = (float)(1.0 / (double)fb0);
+                st.pad0 = st.pad1 = 0.0f;
+                st.pad2[0] = st.pad2[1] = st.pad2[2] = st.pad2[3] = 0.0f;
+            }
+        }
         return;
     }
     // job 6: gains, compressor, pan
-    tb.g_in = (pm.gain_in >= 0) ? (float)pow(10.0, denorm(a, p, pm.gain_in) / 20.0) : 1.0f;
-    tb.g_out = (pm.gain_out >= 0) ? (float)pow(10.0, denorm(a, p, pm.gain_out) / 20.0) : 1.0f;
-    if (pm.pan >= 0) {
-        double th = denorm(a, p, pm.pan) * (kPi / 2);
-        tb.gL = (float)sqrt(((kPi / 2) - th) * (2 / kPi) * cos(th));
-        tb.gR = (float)sqrt(th * (2 / kPi) * sin(th));
-    } else {
-        tb.gL = tb.gR = 1.0f;
-    }
     double thr = 0, ratio = 1, attack = 1, knee = 1, makeup = 0;
     if (pm.comp0 >= 0) {
         thr = denorm(a, p, pm.comp0 + 0); ratio = denorm(a, p, pm.comp0 + 1);
@@ -164,22 +168,33 @@ __global__ void prepare_kernel(PrepareArgs a) {
         makeup = denorm(a, p, pm.comp0 + 5);  // comp0 + 3 = release_ms: unused upstream
     }
     const float alpha = (float)exp(-log(9.0) / (a.sr * (attack / 1e3)));
-    tb.alpha = alpha;
-    tb.beta = (float)(1.0 - (double)alpha);
-    tb.thr_lo = (float)(thr - knee / 2);
-    tb.knee = (float)knee; tb.inv_knee = (float)(1.0 / knee); tb.inv_2knee = (float)(0.5 / knee);
-    tb.slope = (float)(1.0 / ratio - 1.0);
-    tb.makeup = (float)makeup;
-    tb.inv_ratio2 = (float)(1.0 / (ratio * ratio));
-    tb.pad[0] = tb.pad[1] = tb.pad[2] = 0.0f; tb.pad2[0] = tb.pad2[1] = 0.0f;
-    double aL = pow((double)alpha, (double)L);
-    double aj = aL;
-    for (int j = 0; j < 5; ++j) { tb.a2pow[j] = (float)aj; aj *= aj; }
-    tb.aQ = (float)aj;
-    double r = 1.0;
-    for (int l = 0; l < 32; ++l) { tb.a_lane[l] = (float)r; r *= aL; }
-    r = (double)alpha;
-    for (int i = 0; i < kMaxL; ++i) { tb.a_i[i] = (float)r; r *= (double)alpha; }
+    for (int v = 0; v < 2; ++v) {
+        if (!a.tab[v]) continue;
+        RowTab& tb = a.tab[v][row];
+        const double aL = pow((double)alpha, (double)a.L[v]);
+        tb.a_lane[lane] = (float)pow(aL, (double)lane);
+        tb.a_i[lane] = (float)pow((double)alpha, (double)(lane + 1));
+        if (lane < 9) tb.a2pow[lane] = (float)pow(aL, (double)(1 << lane));
+        if (lane == 9) {
+            tb.g_in = (pm.gain_in >= 0) ? (float)pow(10.0, denorm(a, p, pm.gain_in) / 20.0) : 1.0f;
+            tb.g_out = (pm.gain_out >= 0) ? (float)pow(10.0, denorm(a, p, pm.gain_out) / 20.0) : 1.0f;
+            if (pm.pan >= 0) {
+                const double th = denorm(a, p, pm.pan) * (kPi / 2);
+                tb.gL = (float)sqrt(((kPi / 2) - th) * (2 / kPi) * cos(th));
+                tb.gR = (float)sqrt(th * (2 / kPi) * sin(th));
+            } else {
+                tb.gL = tb.gR = 1.0f;
+            }
+            tb.alpha = alpha;
+            tb.beta = (float)(1.0 - (double)alpha);
+            tb.thr_lo = (float)(thr - knee / 2);
+            tb.knee = (float)knee; tb.inv_knee = (float)(1.0 / knee); tb.inv_2knee = (float)(0.5 / knee);
+            tb.slope = (float)(1.0 / ratio - 1.0);
+            tb.makeup = (float)makeup;
+            tb.inv_ratio2 = (float)(1.0 / (ratio * ratio));
+            tb.pad[0] = tb.pad[1] = tb.pad[2] = 0.0f; tb.pad2[0] = tb.pad2[1] = tb.pad2[2] = 0.0f;
+        }
+    }
 }
 
 struct EpilogueArgs {
@@ -193,59 +208,72 @@ struct EpilogueArgs {
     float* grad;           // [rows][np], gradient w.r.t. the NORMALISED parameters
 };
 
-// one thread per row
+// one 64-thread block per row: threads 0..kGradCount-1 reduce the tile partials (coalesced,
+// fixed order => deterministic), then threads 0..5 chain one EQ section each and thread 6
+// the gains / compressor / pan through the design Jacobian.
 __global__ void grad_epilogue_kernel(EpilogueArgs a) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= a.rows) return;
+    const int row = blockIdx.x;
+    const int tid = threadIdx.x;
+    DMST_SHARED_ARRAY(double, acc, kGradCount);
+    if (tid < kGradCount) {
+        double s = 0.0;
+        const float* q = a.partial + (long long)row * a.ntiles * kGradCount + tid;
+        for (int t = 0; t < a.ntiles; ++t) s += (double)q[(long long)t * kGradCount];
+        acc[tid] = s;
+    }
+    __syncthreads();
     const float* p = a.params + (long long)row * a.np;
     float* g = a.grad + (long long)row * a.np;
     const ParamMap pm = param_map(a.kind);
-    double acc[kGradCount];
-    for (int j = 0; j < kGradCount; ++j) acc[j] = 0.0;
-    for (int t = 0; t < a.ntiles; ++t) {
-        const float* q = a.partial + ((long long)row * a.ntiles + t) * kGradCount;
-        for (int j = 0; j < kGradCount; ++j) acc[j] += (double)q[j];
-    }
-    for (int i = 0; i < a.np; ++i) g[i] = 0.0f;
     auto scale = [&](int i) { return (double)a.hi[i] - (double)a.lo[i]; };
     const double ln10_20 = 0.11512925464970229;
-    if (pm.gain_in >= 0 && (a.flags & kChainGain))
-        g[pm.gain_in] = (float)(acc[kGradGin] * ln10_20 * scale(pm.gain_in));
-    if (pm.gain_out >= 0 && (a.flags & kChainOutGain))
-        g[pm.gain_out] = (float)(acc[kGradGout] * ln10_20 * scale(pm.gain_out));
-    if (pm.eq0 >= 0 && (a.flags & kChainEq)) {
-        for (int k = 0; k < kNumSections; ++k) {
-            Dual o[5];
+    if (tid < kNumSections) {
+        const int k = tid;
+        if (pm.eq0 >= 0) {
             const int i0 = pm.eq0 + 3 * k;
-            rbj_design(denorm(a, p, i0), denorm(a, p, i0 + 1), denorm(a, p, i0 + 2), a.sr,
-                       section_kind(k), o);
-            // the backward kernel accumulates in the basis {b0+b1+b2, b1+2 b2, b2, a1+a2, a2}
-            Dual basis[5] = {o[0] + o[1] + o[2], o[1] + 2.0 * o[2], o[2], o[3] + o[4], o[4]};
-            for (int d = 0; d < 3; ++d) {
-                double s = 0.0;
-                for (int j = 0; j < 5; ++j) s += acc[kGradEq + 5 * k + j] * basis[j].d[d];
-                g[i0 + d] = (float)(s * scale(i0 + d));
+            if (a.flags & kChainEq) {
+                Dual o[5];
+                rbj_design(denorm(a, p, i0), denorm(a, p, i0 + 1), denorm(a, p, i0 + 2), a.sr, section_kind(k), o);
+                // the backward kernel accumulates in the basis {b0+b1+b2, b1+2 b2, b2, a1+a2, a2}
+                Dual basis[5] = {o[0] + o[1] + o[2], o[1] + 2.0 * o[2], o[2], o[3] + o[4], o[4]};
+                for (int d = 0; d < 3; ++d) {
+                    double s = 0.0;
+                    for (int j = 0; j < 5; ++j) s += acc[kGradEq + 5 * k + j] * basis[j].d[d];
+                    g[i0 + d] = (float)(s * scale(i0 + d));
+                }
+            } else {
+                g[i0] = g[i0 + 1] = g[i0 + 2] = 0.0f;
             }
         }
-    }
-    if (pm.comp0 >= 0 && (a.flags & kChainComp)) {
-        const double attack = denorm(a, p, pm.comp0 + 2);
-        const double alpha = exp(-log(9.0) / (a.sr * (attack / 1e3)));
-        const double dalpha_dattack = alpha * log(9.0) * 1e3 / (a.sr * attack * attack);
-        g[pm.comp0 + 0] = (float)(acc[kGradThr] * scale(pm.comp0 + 0));
-        g[pm.comp0 + 1] = (float)(acc[kGradRatio] * scale(pm.comp0 + 1));
-        g[pm.comp0 + 2] = (float)(acc[kGradAlpha] * dalpha_dattack * scale(pm.comp0 + 2));
-        g[pm.comp0 + 3] = 0.0f;  // release_ms has no effect upstream
-        g[pm.comp0 + 4] = (float)(acc[kGradKnee] * scale(pm.comp0 + 4));
-        g[pm.comp0 + 5] = (float)(acc[kGradMakeup] * scale(pm.comp0 + 5));
-    }
-    if (pm.pan >= 0) {
-        const double th = denorm(a, p, pm.pan) * (kPi / 2);
-        const double uL = ((kPi / 2) - th) * (2 / kPi) * cos(th), uR = th * (2 / kPi) * sin(th);
-        const double duL = (2 / kPi) * (-cos(th) - ((kPi / 2) - th) * sin(th));
-        const double duR = (2 / kPi) * (sin(th) + th * cos(th));
-        const double dgL = uL > 0 ? 0.5 * duL / sqrt(uL) : 0.0, dgR = uR > 0 ? 0.5 * duR / sqrt(uR) : 0.0;
-        g[pm.pan] = (float)((acc[kGradGL] * dgL + acc[kGradGR] * dgR) * (kPi / 2) * scale(pm.pan));
+    } else if (tid == 6) {
+        if (pm.gain_in >= 0)
+            g[pm.gain_in] = (a.flags & kChainGain) ? (float)(acc[kGradGin] * ln10_20 * scale(pm.gain_in)) : 0.0f;
+        if (pm.gain_out >= 0)
+            g[pm.gain_out] = (a.flags & kChainOutGain) ? (float)(acc[kGradGout] * ln10_20 * scale(pm.gain_out)) : 0.0f;
+        if (pm.comp0 >= 0) {
+            if (a.flags & kChainComp) {
+                const double attack = denorm(a, p, pm.comp0 + 2);
+                const double alpha = exp(-log(9.0) / (a.sr * (attack / 1e3)));
+                const double dalpha_dattack = alpha * log(9.0) * 1e3 / (a.sr * attack * attack);
+                g[pm.comp0 + 0] = (float)(acc[kGradThr] * scale(pm.comp0 + 0));
+                g[pm.comp0 + 1] = (float)(acc[kGradRatio] * scale(pm.comp0 + 1));
+                g[pm.comp0 + 2] = (float)(acc[kGradAlpha] * dalpha_dattack * scale(pm.comp0 + 2));
+                g[pm.comp0 + 3] = 0.0f;  // release_ms has no effect upstream
+                g[pm.comp0 + 4] = (float)(acc[kGradKnee] * scale(pm.comp0 + 4));
+                g[pm.comp0 + 5] = (float)(acc[kGradMakeup] * scale(pm.comp0 + 5));
+            } else {
+                for (int j = 0; j < 6; ++j) g[pm.comp0 + j] = 0.0f;
+            }
+        }
+        if (pm.pan >= 0) {
+            const double th = denorm(a, p, pm.pan) * (kPi / 2);
+            const double uL = ((kPi / 2) - th) * (2 / kPi) * cos(th), uR = th * (2 / kPi) * sin(th);
+            const double duL = (2 / kPi) * (-cos(th) - ((kPi / 2) - th) * sin(th));
+            const double duR = (2 / kPi) * (sin(th) + th * cos(th));
+            const double dgL = uL > 0 ? 0.5 * duL / sqrt(uL) : 0.0, dgR = uR > 0 ? 0.5 * duR / sqrt(uR) : 0.0;
+            g[pm.pan] = (float)((acc[kGradGL] * dgL + acc[kGradGR] * dgR) * (kPi / 2) * scale(pm.pan));
+        }
+        if (a.kind == 0) g[26] = 0.0f;  // fx send: the fx bus is off, no path to the mix
     }
 }
 

@@ -98,6 +98,59 @@ int dmst_console_backward(const float* tracks, long long tracks_batch_stride,
                           float* grad_master_params, float* grad_tracks, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* ---- multi-resolution STFT loss: replaces auraloss.freq.MultiResolutionSTFTLoss.forward
+ *      (instantiated at configs/models/naive.yaml:54-68 and mst/system.py:61-69, called at
+ *      mst/system.py:332; algorithm in SURVEY.md Appendix B) ---- */
+
+#define DMST_MRSTFT_MAX_RES 8
+typedef struct dmst_mrstft_cfg {
+    int n_res;
+    int fft_size[DMST_MRSTFT_MAX_RES], hop_size[DMST_MRSTFT_MAX_RES],
+        win_length[DMST_MRSTFT_MAX_RES];
+    float w_sc, w_log_mag, w_lin_mag;
+    float eps; /* clamp inside the sqrt, auraloss default 1e-8 */
+} dmst_mrstft_cfg;
+
+/* Workspace bytes (0 on invalid configuration).  Creates and caches the cuFFT plans. */
+size_t dmst_mrstft_workspace_bytes(const dmst_mrstft_cfg* cfg_host, int rows, int T);
+/*
+ * x, y: (rows, T) float32 with row strides (rows = batch * channels, as auraloss views its
+ * (B, C, T) arguments).  windows: the per-resolution windows concatenated (win_length[r]
+ * floats each, device).  loss: float32[1 + 3*n_res] (device): [0] the loss, then
+ * (L_sc, L_log, L_lin) per resolution.  When grad_x != NULL it receives d loss / d x,
+ * (rows, T) contiguous; the target y gets no gradient.
+ */
+int dmst_mrstft_forward(const float* x, long long x_row_stride, const float* y,
+                        long long y_row_stride, const float* windows,
+                        const dmst_mrstft_cfg* cfg_host, int rows, int T, float* loss,
+                        float* grad_x, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- audio feature loss: replaces mst.loss.AudioFeatureLoss.forward (mst/loss.py:238-260)
+ *      and the compute_* transforms (mst/loss.py:62-195) ---- */
+
+size_t dmst_afl_workspace_bytes(int B, int T, int fft_size, int n_bands);
+/*
+ * input/target: (B,2,T) float32 with batch/channel strides.  bark_fb: (n_bands,
+ * fft_size/2+1) row-major (the transpose of mst/filter.py's (n_freqs, n_barks)); window:
+ * float32[fft_size]; weights_host: 5 floats.  losses: float32[5] (device) = weight_i * mse_i
+ * in the reference's key order (rms, crest_factor, stereo_width, stereo_imbalance,
+ * barkspectrum).  The workspace keeps what dmst_afl_backward needs.
+ */
+int dmst_afl_forward(const float* input, const float* target, long long batch_stride,
+                     long long ch_stride, const float* bark_fb, const float* window,
+                     const float* weights_host, int B, int T, int fft_size, int n_bands,
+                     float* losses, void* workspace, size_t workspace_bytes, void* stream);
+/* grad_input (B,2,T contiguous) = d(sum_i grad_w[i] * losses[i]) / d input; grad_w: float32[5]
+ * (device) upstream gradients, NULL means ones. */
+int dmst_afl_backward(const float* input, long long batch_stride, long long ch_stride,
+                      const float* bark_fb, const float* window, const float* weights_host,
+                      const float* grad_w, int B, int T, int fft_size, int n_bands,
+                      float* grad_input, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- batch_stereo_peak_normalize (mst/utils.py:14-29): y = x / max(peak over (2,T), 1e-8) ---- */
+int dmst_peak_normalize(const float* x, long long batch_stride, long long ch_stride, float* y,
+                        int B, int T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

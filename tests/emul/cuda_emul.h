@@ -42,6 +42,8 @@ struct double2 { double x, y; };
 static inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
 static inline float2 make_float2(float a, float b) { return {a, b}; }
 
+using std::min;
+using std::max;
 typedef int cudaError_t;
 typedef void* cudaStream_t;
 #define cudaSuccess 0
@@ -148,6 +150,7 @@ static inline float atomicAdd(float* p, float v) {
 static inline float emul_log2f(float x) { return std::log2(x); }
 #define __log2f emul_log2f
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __ldg(const float* p) { return *p; }
 static inline float4 __ldg(const float4* p) { return *p; }
