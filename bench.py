@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the Diff-MST hot path on B200 (driver contract: see DESIGN.md section 6).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): AdvancedMixConsole forward + backward with the
+multi-resolution STFT loss, batch 8 x 16 tracks x 262144 samples per GPU, float32, synthetic
+white-noise tracks (0.1 * randn), uniform random parameters, fx bus off (as every shipped
+config).  One "step" = console forward -> MRSTFT(mix, target mix) -> backward to the console
+parameters.  Metric: track-seconds per second = B*N*T / 44100 / step time, summed over GPUs
+(weak scaling, batch-sharded, no collective on the path).
+
+`--impl reference` times the reference algorithm's CPU path instead: the float32 oracle port
+(oracle/, the reference classes cannot travel to the GPU box because their third-party DSP
+dependencies are not installable) on all host cores, on a bounded sample (batch 1).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 44100
+B, N, T = 8, 16, 262144
+RES = dict(fft_sizes=[512, 2048, 8192], hop_sizes=[256, 1024, 4096], win_lengths=[512, 2048, 8192])
+METRIC = "track-seconds/sec AdvancedMixConsole fwd+bwd (16trk,262144) @1/2/4/8 B200"
+UNIT = "track-seconds/s"
+FLAGS = dict(use_track_input_fader=True, use_track_eq=True, use_track_compressor=True,
+             use_track_panner=True, use_master_bus=True, use_fx_bus=False, use_output_fader=True)
+# algorithmic bytes per track-sample (SURVEY.md section 8d / BASELINE.md section 3, bus-only mode)
+BYTES_FWD = 4.0 + 8.0 / N
+BYTES_BWD = 4.0 + 8.0 / N
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(torch, seed, batch, device):
+    g = torch.Generator().manual_seed(seed)
+    tracks = torch.randn(batch, N, T, generator=g) * 0.1
+    tp = torch.rand(batch, N, 27, generator=g)
+    fp = torch.rand(batch, 25, generator=g)
+    mp = torch.rand(batch, 26, generator=g)
+    # target mix: a second random mix of the same tracks (mst/system.py:232-249)
+    tp2, mp2 = torch.rand(batch, N, 27, generator=g), torch.rand(batch, 26, generator=g)
+    return tracks, tp, fp, mp, tp2, mp2
+
+
+def run_reference(args):
+    """CPU path of the reference algorithm (oracle port, float32), bounded sample: batch 1."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.auraloss.freq import MultiResolutionSTFTLoss
+    from oracle.console import OracleAdvancedMixConsole
+    from oracle.loss import batch_stereo_peak_normalize
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = 1
+    tracks, tp, fp, mp, tp2, mp2 = make_inputs(torch, 0, batch, "cpu")
+    con = OracleAdvancedMixConsole(SR)
+    loss_fn = MultiResolutionSTFTLoss(**RES)
+    with torch.no_grad():
+        target = batch_stereo_peak_normalize(con(tracks, tp2, fp, mp2, **FLAGS)[1])
+    tp.requires_grad_(True); mp.requires_grad_(True)
+
+    def step():
+        tp.grad = None; mp.grad = None
+        mix = con(tracks, tp, fp, mp, **FLAGS)[1]
+        loss = loss_fn(mix, target)
+        loss.backward()
+        return float(loss.detach())
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = batch * N * T / SR / dt
+    sample = f"batch 1 of the workload ({N} tracks x {T} samples), fwd+bwd+MRSTFT, float32, {steps} steps"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "AdvancedMixConsole fwd+bwd + MRSTFT, 16 tracks x 262144 samples (CPU sample: batch 1)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(torch):
+    from oracle.auraloss.freq import MultiResolutionSTFTLoss
+    from oracle.console import OracleAdvancedMixConsole
+    from oracle.loss import batch_stereo_peak_normalize
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tracks, tp, fp, mp, tp2, mp2 = make_inputs(torch, 0, 1, "cpu")
+    con = OracleAdvancedMixConsole(SR)
+    loss_fn = MultiResolutionSTFTLoss(**RES)
+    with torch.no_grad():
+        target = batch_stereo_peak_normalize(con(tracks, tp2, fp, mp2, **FLAGS)[1])
+    tp.requires_grad_(True); mp.requires_grad_(True)
+    times = []
+    for i in range(4):
+        tp.grad = None; mp.grad = None
+        t0 = time.perf_counter()
+        loss_fn(con(tracks, tp, fp, mp, **FLAGS)[1], target).backward()
+        times.append(time.perf_counter() - t0)
+    dt = statistics.median(times[1:])
+    return {"value": N * T / SR / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"batch 1 ({N} tracks x {T} samples) fwd+bwd+MRSTFT, float32 oracle port on {cores} host "
+                      f"threads, median of 3 after 1 warm-up ({dt:.2f} s/step)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from diffmst_b200 import AdvancedMixConsole, MRSTFTLoss, batch_stereo_peak_normalize, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    con = AdvancedMixConsole(SR).to(dev)
+    con.materialize_tracks = False   # bus-only mode
+    con.check_ranges = False         # inputs are generated in range; skips one host sync per call
+    loss_fn = MRSTFTLoss(**RES)
+    tracks_h, tp_h, fp_h, mp_h, tp2, mp2 = make_inputs(torch, rank, B, "cpu")
+    tracks = tracks_h.to(dev); fp = fp_h.to(dev)
+    tp = tp_h.to(dev).requires_grad_(True); mp = mp_h.to(dev).requires_grad_(True)
+    with torch.no_grad():
+        target = batch_stereo_peak_normalize(con(tracks, tp2.to(dev), fp, mp2.to(dev), **FLAGS)[1])
+
+    def step(x):
+        tp.grad = None; mp.grad = None
+        mix = con(x, tp, fp, mp, **FLAGS)[1]
+        loss = loss_fn(mix, target)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    lib = _lib.lib()
+    # ---------------- device-resident timing ----------------
+    for _ in range(max(args.warmup, 3)):
+        step(tracks)
+    sampler = ClockSampler(local)
+    barrier()
+    lib.dmst_profile_enable(args.steps)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step(tracks)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    kern_ms = {}
+    buf = (ctypes.c_float * args.steps)()
+    for kind, name in enumerate(["track_fwd", "master_fwd", "master_bwd", "track_bwd"]):
+        n = lib.dmst_profile_read(kind, buf, args.steps)
+        kern_ms[name] = sum(buf[i] for i in range(n)) / n if n > 0 else None
+    lib.dmst_profile_enable(0)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---------------- end to end: host buffers, H2D of the step's inputs, D2H of its results ----
+    pinned = [tracks_h.pin_memory(), tracks_h.clone().pin_memory()]
+    tp_pin, mp_pin = tp_h.pin_memory(), mp_h.pin_memory()
+    dev_bufs = [torch.empty_like(tracks), torch.empty_like(tracks)]
+    copy_stream = torch.cuda.Stream(dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    host_out = {"loss": torch.empty(1).pin_memory(), "gtp": torch.empty(B, N, 27).pin_memory(),
+                "gmp": torch.empty(B, 26).pin_memory()}
+    h2d = tracks_h.numel() * 4 + tp_h.numel() * 4 + mp_h.numel() * 4
+    d2h = 4 + (B * N * 27 + B * 26) * 4
+
+    def e2e_loop(steps):
+        # two-deep pipeline: the copy of step i+1's tracks overlaps the compute of step i
+        main = torch.cuda.current_stream(dev)
+        for b in range(2):
+            freed[b].record(main)
+        def upload(i):
+            b = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[b])
+                dev_bufs[b].copy_(pinned[b], non_blocking=True)
+                ready[b].record(copy_stream)
+        upload(0)
+        for i in range(steps):
+            b = i & 1
+            if i + 1 < steps:
+                upload(i + 1)
+            main.wait_event(ready[b])
+            with torch.no_grad():
+                tp.copy_(tp_pin, non_blocking=True); mp.copy_(mp_pin, non_blocking=True)
+            loss = step(dev_bufs[b])
+            freed[b].record(main)
+            host_out["loss"].copy_(loss.detach().reshape(1), non_blocking=True)
+            host_out["gtp"].copy_(tp.grad, non_blocking=True)
+            host_out["gmp"].copy_(mp.grad, non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    e2e_loop(max(args.warmup, 3))
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    e2e_loop(args.steps)
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_max = float(t.item())
+
+    if rank == 0:
+        units = world * B * N * T / SR  # track-seconds per step over all ranks
+        value = units / (ms_max / 1e3 / args.steps)
+        e2e_value = units / (e2e_ms_max / 1e3 / args.steps)
+        peak, peak_src = measured_peaks()
+        samples = B * N * T
+        roof = None
+        if kern_ms.get("track_bwd"):
+            achieved = BYTES_BWD * samples / (kern_ms["track_bwd"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "chain_bwd_kernel<tracks>", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": BYTES_BWD * samples,
+                    "avg_launch_ms": kern_ms["track_bwd"],
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch,
+                    # from profiles/ (ncu --set full); None until a capture of this build exists
+                    "traffic": TRAFFIC_TRACK_BWD_BYTES,
+                    "kernel_ms": kern_ms,
+                    "step_frac_of_hbm_roofline": (BYTES_FWD + BYTES_BWD) * samples / (ms_max / args.steps * 1e-3) / 1e9 / peak}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "AdvancedMixConsole fwd+bwd + MRSTFT loss, batch 8 x 16 tracks x 262144 "
+                                       "samples per GPU (BASELINE configs[1])",
+                           "global_batch": world * B, "tracks": N, "samples": T, "parallelism": f"dp{world}",
+                           "mode": "bus-only (mixed_tracks not materialised)",
+                           "l2": "inputs larger than L2 (134 MB of tracks per step, re-read every step)"},
+                "clocks": clocks, "gpu_launches": 26 * args.steps,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms_max / args.steps,
+                        "note": "pinned host tracks + parameters copied in every step (copy of step i+1 overlaps "
+                                "compute of step i), loss and parameter gradients copied out every step"},
+                "roofline": roof}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(torch)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram traffic of the track-backward kernel per launch (bytes) from profiles/ncu_r1_summary.md
+TRAFFIC_TRACK_BWD_BYTES = None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

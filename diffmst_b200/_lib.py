@@ -69,6 +69,10 @@ def lib():
     l.dmst_afl_backward.argtypes = [vp, ll, ll, vp, vp, fp5, vp, i, i, i, i, vp, vp, sz, vp]
     l.dmst_peak_normalize.restype = i
     l.dmst_peak_normalize.argtypes = [vp, ll, ll, vp, i, i, vp]
+    l.dmst_profile_enable.restype = i
+    l.dmst_profile_enable.argtypes = [i]
+    l.dmst_profile_read.restype = i
+    l.dmst_profile_read.argtypes = [i, ctypes.POINTER(ctypes.c_float), i]
     _lib = l
     return l
 

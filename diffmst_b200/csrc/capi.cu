@@ -42,6 +42,47 @@ int dmst_console_backward(const float* tracks, long long tracks_batch_stride, lo
                                   reinterpret_cast<cudaStream_t>(stream));
 }
 
+int dmst_profile_enable(int max_records) {
+#ifndef DMST_EMULATE
+    dmst::Profiler& p = dmst::profiler();
+    if (max_records <= 0) { p.enabled = false; return 0; }
+    if (p.cap < max_records) {
+        for (int k = 0; k < dmst::Profiler::kKinds; ++k) {
+            cudaEvent_t* n = new cudaEvent_t[2 * max_records];
+            for (int i = 0; i < 2 * max_records; ++i) {
+                if (p.ev[k] && i < 2 * p.cap) n[i] = p.ev[k][i];
+                else if (cudaEventCreate(&n[i]) != cudaSuccess) return (int)cudaGetLastError();
+            }
+            delete[] p.ev[k];
+            p.ev[k] = n;
+        }
+        p.cap = max_records;
+    }
+    for (int k = 0; k < dmst::Profiler::kKinds; ++k) p.count[k] = 0;
+    p.enabled = true;
+    return 0;
+#else
+    (void)max_records;
+    return DMST_EINVAL;
+#endif
+}
+
+int dmst_profile_read(int kind, float* ms_host, int capacity) {
+#ifndef DMST_EMULATE
+    dmst::Profiler& p = dmst::profiler();
+    if (kind < 0 || kind >= dmst::Profiler::kKinds || !ms_host) return DMST_EINVAL;
+    const int n = p.count[kind] < capacity ? p.count[kind] : capacity;
+    for (int i = 0; i < n; ++i) {
+        if (cudaEventSynchronize(p.ev[kind][2 * i + 1]) != cudaSuccess) return -1;
+        if (cudaEventElapsedTime(&ms_host[i], p.ev[kind][2 * i], p.ev[kind][2 * i + 1]) != cudaSuccess) return -1;
+    }
+    return n;
+#else
+    (void)kind; (void)ms_host; (void)capacity;
+    return DMST_EINVAL;
+#endif
+}
+
 size_t dmst_mrstft_workspace_bytes(const dmst_mrstft_cfg* cfg, int rows, int T) {
 #ifndef DMST_EMULATE
     if (!cfg || cfg->n_res <= 0 || cfg->n_res > DMST_MRSTFT_MAX_RES || rows <= 0 || T <= 0) return 0;

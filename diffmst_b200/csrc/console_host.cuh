@@ -30,6 +30,38 @@ static_assert(kTrackFwdL * kTrackFwdNT == kTrackBwdL * kTrackBwdNT, "forward/bac
     (int)cudaFuncSetAttribute((kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 #endif
 
+// Optional per-kernel timing (bench.py's roofline figure): when enabled, every launch of a chain
+// kernel is bracketed by a pair of CUDA events recorded on the launching stream; nothing
+// synchronises until dmst_profile_read.
+struct Profiler {
+    static constexpr int kKinds = 4;  // 0 track fwd, 1 master fwd, 2 master bwd, 3 track bwd
+#ifndef DMST_EMULATE
+    cudaEvent_t* ev[kKinds] = {nullptr, nullptr, nullptr, nullptr};
+    int count[kKinds] = {0, 0, 0, 0};
+    int cap = 0;
+#endif
+    bool enabled = false;
+};
+inline Profiler& profiler() { static Profiler p; return p; }
+#ifndef DMST_EMULATE
+struct ScopedTimer {
+    int kind; cudaStream_t s; bool on;
+    ScopedTimer(int k, cudaStream_t st) : kind(k), s(st) {
+        Profiler& p = profiler();
+        on = p.enabled && p.count[k] < p.cap;
+        if (on) cudaEventRecord(p.ev[k][2 * p.count[k]], s);
+    }
+    ~ScopedTimer() {
+        if (!on) return;
+        Profiler& p = profiler();
+        cudaEventRecord(p.ev[kind][2 * p.count[kind] + 1], s);
+        p.count[kind]++;
+    }
+};
+#else
+struct ScopedTimer { ScopedTimer(int, cudaStream_t) {} };
+#endif
+
 struct Carver {
     unsigned char* base;
     size_t off;
@@ -215,6 +247,7 @@ inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* 
         auto kern = chain_fwd_kernel<1, kTrackFwdL, kTrackFwdNT, false>;
         const size_t smem = fwd_smem_bytes(1, kTrackTile, k.la_t);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
+        ScopedTimer tm(0, stream);
         DMST_LAUNCH(kern, dim3(at.nrows * at.ntiles), dim3(kTrackFwdNT), smem, stream, at);
     }
     fill_chain(am, k, true, w);
@@ -224,6 +257,7 @@ inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* 
         auto kern = chain_fwd_kernel<2, kMasterL, kMasterNT, true>;
         const size_t smem = fwd_smem_bytes(2, kMasterTile, k.la_m);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
+        ScopedTimer tm(1, stream);
         DMST_LAUNCH(kern, dim3(am.nrows * am.ntiles), dim3(kMasterNT), smem, stream, am);
     }
     return DMST_LAST_ERROR();
@@ -250,6 +284,7 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
         auto kern = chain_bwd_kernel<2, kMasterL, kMasterNT, true, 1>;
         const size_t smem = bwd_smem_bytes(2, kMasterTile, k.la_m, kMasterNT);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
+        ScopedTimer tm(2, stream);
         DMST_LAUNCH(kern, dim3(am.nrows * am.ntiles), dim3(kMasterNT), smem, stream, am);
     }
     if (gmp && k.master_params) {
@@ -270,6 +305,7 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
         const size_t smem = bwd_smem_bytes(1, kTrackTile, k.la_t, kTrackBwdNT);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
         at.tab = w.track_tab_b;
+        ScopedTimer tm(3, stream);
         DMST_LAUNCH(kern, dim3(at.nrows * at.ntiles), dim3(kTrackBwdNT), smem, stream, at);
     }
     {

@@ -98,6 +98,15 @@ int dmst_console_backward(const float* tracks, long long tracks_batch_stride,
                           float* grad_master_params, float* grad_tracks, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* ---- measurement hooks (used by bench.py only) ----
+ * dmst_profile_enable(n > 0): from now on every console chain-kernel launch is bracketed by a
+ * pair of CUDA events on its stream (at most n per kernel kind); n <= 0 disables.
+ * dmst_profile_read(kind, ms_host, capacity): synchronises on the recorded events of `kind`
+ * (0 track forward, 1 master forward, 2 master backward, 3 track backward) and writes their
+ * durations in milliseconds; returns the number written, or a negative value on error. */
+int dmst_profile_enable(int max_records);
+int dmst_profile_read(int kind, float* ms_host, int capacity);
+
 /* ---- multi-resolution STFT loss: replaces auraloss.freq.MultiResolutionSTFTLoss.forward
  *      (instantiated at configs/models/naive.yaml:54-68 and mst/system.py:61-69, called at
  *      mst/system.py:332; algorithm in SURVEY.md Appendix B) ---- */
