@@ -52,15 +52,16 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []      # (host time, fields)
         self.proc = None
+        self.window = None  # (t0, t1) host times of the timed region
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -70,7 +71,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -82,7 +83,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        if self.window is not None:
+            inside = [r for r in rows if self.window[0] <= r[0] <= self.window[1] + 0.05]
+            rows = inside if inside else rows[-3:]   # region shorter than the sampling period
+        for _, r in rows:
             if len(r) < 6:
                 continue
             try:
@@ -218,17 +223,23 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step(tracks)
     sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs a moment to come up: start it before the last warm-up
+    for _ in range(3):
+        step(tracks)
     barrier()
     lib.dmst_profile_enable(args.steps)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         step(tracks)
     ev1.record()
     barrier()
+    sampler.window = (t_host0, time.perf_counter())
+    if rank == 0:
+        time.sleep(0.06)         # let the sampler deliver the sample taken during the region
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     kern_ms = {}
@@ -339,7 +350,7 @@ TRAFFIC_TRACK_BWD_BYTES = None
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

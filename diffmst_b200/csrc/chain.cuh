@@ -15,7 +15,8 @@ namespace dmst {
 constexpr int kStateStride = 32;   // floats per (row, tile): [sec][ch][2] (24) + smoother (1)
 constexpr int kStateSmooth = 24;
 constexpr int kTail2Stride = 32;   // floats per (row, tile): [stage 0..6][ch][2]
-constexpr int kFlagSmooth = 7;     // flag value meaning "EQ sections 1..6 and smoother published"
+constexpr int kFlagSmooth = 7;
+constexpr int kBwdChunk = 16;      // thread chunk of the backward kernel (state checkpoint spacing)     // flag value meaning "EQ sections 1..6 and smoother published"
 
 struct ChainArgs {
     // ---- geometry ----
@@ -43,16 +44,19 @@ struct ChainArgs {
     // ---- chain workspace (kept for backward) ----
     int* ticket;
     int* flag;                   // [nrows*ntiles]
-    float* state;                // [nrows*ntiles*kStateStride] end-of-tile states
+    Mail* state;                 // [nrows*ntiles*kStateStride] end-of-tile states (mailboxes, see common.cuh)
     float* tail2;                // [nrows*ntiles*kTail2Stride] last two samples of each stage
     float* etail;                // [nrows*ntiles*NCH*lookahead] last `lookahead` EQ outputs
+    // optional checkpoints that let backward skip the forward EQ recompute (tracks):
+    float* esave;                // (nrows, Tp) EQ output, or null
+    float* ssave;                // [nrows*ntiles][6*NCH*2][TILE/kBwdChunk] section states every kBwdChunk samples
     // ---- backward only ----
     const float* gout;           // tracks: dbus (B*2, Tp); master: caller's grad_mix (B,2,T)
     const float* gmixed;         // tracks: caller's grad of mixed_tracks (B,2,N,T) or null
     float* gsrc;                 // tracks: caller's grad_tracks (B,N,T) or null; master: dbus (B*2,Tp)
     float* partial;              // [nrows*ntiles*kGradCount]
     int* bflag;                  // [nrows*ntiles] reverse-chain flags
-    float* bstate;               // [nrows*ntiles*kStateStride] reverse states at tile start
+    Mail* bstate;                // [nrows*ntiles*kStateStride] reverse states at tile start (mailboxes)
     float* dhead;                // [nrows*ntiles*NCH*lookahead] first `lookahead` of dy*G
 };
 

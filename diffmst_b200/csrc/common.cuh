@@ -70,6 +70,7 @@ struct RowTab {
 
 // Flags understood by the chain kernels
 constexpr unsigned kChainGain = 1u, kChainEq = 2u, kChainComp = 4u, kChainOutGain = 8u;
+constexpr unsigned kChainDebugNoWait = 64u;  // measurement only (DMST_DEBUG_NOWAIT=1): skip inter-tile waits, results invalid
 
 // Gradient partial layout (per row, per tile), see console_bwd.cu
 constexpr int kGradEq = 0;        // 30 values: section*5 + {b0,b1,b2,a1,a2}
@@ -96,7 +97,8 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
     return v;
 #endif
 }
-__device__ __forceinline__ void wait_flag_ge(const int* p, int v) {
+__device__ __forceinline__ void wait_flag_ge(const int* p, int v, bool skip = false) {
+    if (skip) return;
     while (ld_acquire(p) < v) {
 #ifndef DMST_EMULATE
         __nanosleep(64);
@@ -104,6 +106,47 @@ __device__ __forceinline__ void wait_flag_ge(const int* p, int v) {
         __nanosleep(0);
 #endif
     }
+}
+
+// ---------------------------------------------------------------------------------
+// "Flag in data" mailboxes for the chained section states: a value and its validity tag travel
+// in one aligned 8-byte word, so a consumer needs a single L2 round trip and the producer needs
+// no fence.  Mailboxes are zeroed (cudaMemsetAsync) before each launch; tag == kMailValid marks
+// a published value.
+// ---------------------------------------------------------------------------------
+struct __align__(8) Mail { float v; int tag; };
+constexpr int kMailValid = 1;
+__device__ __forceinline__ void mail_put(Mail* p, float v) {
+#ifdef DMST_EMULATE
+    uint64_t w; Mail m{v, kMailValid}; memcpy(&w, &m, 8);
+    reinterpret_cast<std::atomic<uint64_t>*>(p)->store(w, std::memory_order_release);
+#else
+    asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_int(v)), "r"(kMailValid) : "memory");
+#endif
+}
+__device__ __forceinline__ bool mail_try(const Mail* p, float& v) {
+#ifdef DMST_EMULATE
+    uint64_t w = reinterpret_cast<const std::atomic<uint64_t>*>(p)->load(std::memory_order_acquire);
+    Mail m; memcpy(&m, &w, 8);
+    v = m.v; return m.tag == kMailValid;
+#else
+    int a, b;
+    asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+    v = __int_as_float(a);
+    return b == kMailValid;
+#endif
+}
+__device__ __forceinline__ float mail_wait(const Mail* p, bool skip = false) {
+    float v;
+    while (!mail_try(p, v)) {
+        if (skip) break;
+#ifndef DMST_EMULATE
+        __nanosleep(32);
+#else
+        __nanosleep(0);
+#endif
+    }
+    return v;
 }
 
 // padded shared-memory index: conflict-free when lane l touches element l*L + i

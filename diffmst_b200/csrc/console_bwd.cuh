@@ -19,8 +19,7 @@
 
 namespace dmst {
 
-constexpr int kBFlagComp = 1;  // reverse smoother state + dhead published
-// section k (5..0) published <=> bflag >= 2 + (5 - k)
+constexpr int kBFlagComp = 1;  // reverse smoother state + dhead halo published (section states use mailboxes)
 
 template <int NCH, int L, int NT, bool MASTER, int MINB>
 __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
@@ -30,8 +29,10 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
 
     DMST_DYN_SMEM(smem_raw);
     DMST_SHARED_ARRAY(float, s_W, 8 * NW * NCH * 2);       // warp aggregates, slot 7 = reverse smoother
-    DMST_SHARED_ARRAY(float, s_nb, NW * NCH * 2);           // last two section-input samples of each warp
-    DMST_SHARED_ARRAY(float, s_in, 8 * NCH * 2);
+    DMST_SHARED_ARRAY(float, s_nb, 3 * NW * NCH * 2);       // last two samples of each warp: [section parity 0/1, chain output]
+    DMST_SHARED_ARRAY(float, s_pre, kStateStride);   // successor's reverse states (prefetched)
+    DMST_SHARED_ARRAY(float, s_fst, kStateStride);   // predecessor's forward end states (saved by forward)
+    DMST_SHARED_ARRAY(unsigned, s_premask, 2);       // [0] published mailboxes at tile start, [1] successor flag
     DMST_SHARED_ARRAY(float, s_part, NW * kGradCount);
     DMST_SHARED_ARRAY(int, s_ticket, 1);
     DMST_SHARED_ARRAY(float, s_tabf, sizeof(RowTab) / 4);
@@ -45,6 +46,8 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
     const int row = ticket % a.nrows;
     const int LA = a.lookahead;
     const int buf_stride = pidx(LA + TILE) + 1;
+    // LA % 32 == 0 and L | 32 (checked on the host): pidx(LA + tid*L + i) = pLA + pb + i
+    const int pLA = pidx(LA), pb = pidx(tid * L);
     float* ebuf = reinterpret_cast<float*>(smem_raw);          // [NCH][buf_stride]  e delay line
     float* dbuf = ebuf + NCH * buf_stride;                      // [NCH][buf_stride]  dy*G, future halo
     float* sE = dbuf + NCH * buf_stride;                        // [6*NCH*2][NT] forward lane carry-ins
@@ -57,18 +60,37 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
     const int t0 = tile * TILE + tid * L;
     const bool has_pred = tile > 0, has_succ = tile < a.ntiles - 1;
     const long long rt = (long long)row * a.ntiles + tile;
-    const float* state_in = a.state + (rt - 1) * kStateStride;  // forward carry-in
+    const Mail* state_in = a.state + (rt - 1) * kStateStride;  // forward carry-in
     const float* tail_in = a.tail2 + (rt - 1) * kTail2Stride;
-    float* bstate_out = a.bstate + rt * kStateStride;
-    const float* bstate_in = a.bstate + (rt + 1) * kStateStride;
+    Mail* bstate_out = a.bstate + rt * kStateStride;
+    const Mail* bstate_in = a.bstate + (rt + 1) * kStateStride;
     int* my_flag = a.bflag + rt;
     const int* succ_flag = my_flag + 1;
+    const bool nowait = (a.flags & kChainDebugNoWait) != 0;
+    if (warp == 0) {
+        float pv = 0.0f;
+        const bool ok = has_succ ? mail_try(bstate_in + lane, pv) : true;
+        s_pre[lane] = pv;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) { s_premask[0] = m; s_premask[1] = has_succ ? (unsigned)ld_acquire(succ_flag) : 99u; }
+    } else if (warp == 1) {
+        s_fst[lane] = has_pred ? state_in[lane].v : 0.0f;
+    }
     const int bb = MASTER ? row : row / a.N;
     const int nn = MASTER ? 0 : row - bb * a.N;
     const bool uvec = a.user_vec_ok != 0;
 
+    // With checkpoints from forward (EQ output + section states every kBwdChunk samples) the
+    // forward EQ recompute below is skipped.
+    const bool saved = (a.esave != nullptr) && (a.flags & kChainEq);
+    static_assert(L == kBwdChunk, "state checkpoints are spaced by the backward chunk length");
+    const float* ssave = a.ssave ? a.ssave + rt * (kNumSections * NCH * 2) * NT : nullptr;
     float v[NCH][L];
-    if constexpr (!MASTER) {
+    if (saved) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+            load_chunk<L>(a.esave + (long long)(row * NCH + c) * a.Tp + t0, a.Tp - t0, true, v[c]);
+    } else if constexpr (!MASTER) {
         load_chunk<L>(a.src + (long long)bb * a.src_batch_stride + (long long)nn * a.src_row_stride + t0,
                       a.T - t0, a.src_vec_ok != 0, v[0]);
     } else {
@@ -77,7 +99,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
             load_chunk<L>(a.src + (long long)(row * NCH + c) * a.Tp + t0, a.Tp - t0, true, v[c]);
     }
     __syncthreads();
-    if (a.flags & kChainGain) {
+    if (!saved && (a.flags & kChainGain)) {
         const float g = tb.g_in;
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
@@ -86,7 +108,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
     }
 
     // ---------------- forward recompute of the EQ cascade ----------------
-    if (a.flags & kChainEq) {
+    if ((a.flags & kChainEq) && !saved) {
 #pragma unroll 1
         for (int k = 0; k < kNumSections; ++k) {
             const SectionTab& st = tb.sec[k];
@@ -128,8 +150,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
             __syncthreads();
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                const float i1 = has_pred ? __ldg(state_in + (k * NCH + c) * 2 + 0) : 0.0f;
-                const float i2 = has_pred ? __ldg(state_in + (k * NCH + c) * 2 + 1) : 0.0f;
+                const float i1 = s_fst[(k * NCH + c) * 2 + 0], i2 = s_fst[(k * NCH + c) * 2 + 1];
                 float c1, c2, n1, n2;
                 cross_warp_fwd<NW>(s_W + (k * NW * NCH + c) * 2, NCH * 2, st.P2, i1, i2, lane, warp, c1, c2, n1, n2);
                 mat2_apply_acc(st.Ppow[lane], c1, c2, e1[c], e2[c]);
@@ -210,7 +231,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
 #pragma unroll
-            for (int i = 0; i < L; ++i) ebuf[c * buf_stride + pidx(LA + tid * L + i)] = v[c][i];
+            for (int i = 0; i < L; ++i) ebuf[c * buf_stride + pLA + pb + i] = v[c][i];
         {
             const float* etail_in = a.etail + (rt - 1) * NCH * LA;
 #pragma unroll
@@ -240,8 +261,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
         if (lane == 31) s_W[(6 * NW + warp) * NCH * 2] = gz;
         __syncthreads();  // ebuf + smoother aggregates visible
         float cw, gend;
-        cross_warp_fwd1<NW>(s_W + 6 * NW * NCH * 2, NCH * 2, tb.a2pow,
-                            has_pred ? __ldg(state_in + kStateSmooth) : 0.0f, lane, warp, cw, gend);
+        cross_warp_fwd1<NW>(s_W + 6 * NW * NCH * 2, NCH * 2, tb.a2pow, s_fst[kStateSmooth], lane, warp, cw, gend);
         const float gcarry = fmaf(tb.a_lane[lane], cw, ex);  // g_s just before this chunk
 #pragma unroll
         for (int i = 0; i < L; ++i) gs[i] = fmaf(tb.a_i[i], gcarry, gs[i]);
@@ -253,7 +273,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
         for_each_upstream(
             [&](int c, int i) {
                 if (c == 0) Gi = fast_exp2(kLog2Per20Db * (gs[i] + tb.makeup));
-                return ebuf[c * buf_stride + pidx(tid * L + i)] * Gi;
+                return ebuf[c * buf_stride + pb + i] * Gi;
             },
             [&](int i, const float* dc, const float* o) {
                 float r = 0.0f;
@@ -261,8 +281,8 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
                 for (int c = 0; c < NCH; ++c) {
                     r = fmaf(dc[c], o[c], r);
                     const float dyG = dc[c] * Gi;
-                    dbuf[c * buf_stride + pidx(tid * L + i)] = dyG;
-                    if (tid * L + i < LA) dhead_out[c * LA + tid * L + i] = dyG;
+                    dbuf[c * buf_stride + pb + i] = dyG;
+                    if (tid * L < LA) dhead_out[c * LA + tid * L + i] = dyG;  // whole chunk: L | LA
                 }
                 q[i] = r * kLn10Over20;
                 acc_comp[4] += q[i];
@@ -279,32 +299,38 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
         float px = __shfl_down_sync(0xffffffffu, pz, 1);
         if (lane == 31) px = 0.0f;
         if (lane == 0) s_W[(7 * NW + warp) * NCH * 2] = pz;
-        if (tid == 0) {
-            if (has_succ) {
-                wait_flag_ge(succ_flag, kBFlagComp);
-                s_in[7 * NCH * 2] = __ldcg(bstate_in + kStateSmooth);
-            } else {
-                s_in[7 * NCH * 2] = 0.0f;
-            }
-        }
-        __syncthreads();  // dbuf (own tile), reverse aggregates, successor state visible
-        float pc, pstart;
-        cross_warp_rev1<NW>(s_W + 7 * NW * NCH * 2, NCH * 2, tb.a2pow, s_in[7 * NCH * 2], lane, warp, pc, pstart);
-        if (tid == 0) {
-            bstate_out[kStateSmooth] = pstart;
-            __threadfence();  // also orders every thread's dhead stores (made before the barrier)
-            st_release(my_flag, kBFlagComp);
-        }
-        const float pcarry = fmaf(tb.a_lane[31 - lane], pc, px);  // p at the first sample after this chunk
-        // halo of dy*G from the successor tile
-        {
+        // successor already published its smoother state and halo (the common case): fetch the
+        // halo now and save a barrier; otherwise wait for it and fetch after the barrier
+        const bool halo_early = s_premask[1] >= (unsigned)kBFlagComp;
+        if (halo_early) {
             const float* dhead_in = a.dhead + (rt + 1) * NCH * LA;
 #pragma unroll
             for (int c = 0; c < NCH; ++c)
                 for (int j = tid; j < LA; j += NT)
                     dbuf[c * buf_stride + pidx(TILE + j)] = has_succ ? __ldcg(dhead_in + c * LA + j) : 0.0f;
+        } else if (tid == 0) {
+            wait_flag_ge(succ_flag, kBFlagComp, nowait);
         }
-        __syncthreads();
+        if (tid == 0 && has_succ && !((s_premask[0] >> kStateSmooth) & 1u))
+            s_pre[kStateSmooth] = mail_wait(bstate_in + kStateSmooth, nowait);
+        __syncthreads();  // dbuf (own tile), reverse aggregates, successor state visible
+        float pc, pstart;
+        cross_warp_rev1<NW>(s_W + 7 * NW * NCH * 2, NCH * 2, tb.a2pow, s_pre[kStateSmooth], lane, warp, pc, pstart);
+        if (tid == 0) {
+            mail_put(bstate_out + kStateSmooth, pstart);
+            // release is cumulative over the barrier: every thread's dhead stores made before the
+            // __syncthreads above are visible to whoever acquires this flag
+            st_release(my_flag, kBFlagComp);
+        }
+        const float pcarry = fmaf(tb.a_lane[31 - lane], pc, px);  // p at the first sample after this chunk
+        if (!halo_early) {  // halo of dy*G from the successor tile
+            const float* dhead_in = a.dhead + (rt + 1) * NCH * LA;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+                for (int j = tid; j < LA; j += NT)
+                    dbuf[c * buf_stride + pidx(TILE + j)] = has_succ ? __ldcg(dhead_in + c * LA + j) : 0.0f;
+            __syncthreads();
+        }
         float gprev = gcarry;
 #pragma unroll
         for (int i = 0; i < L; ++i) {
@@ -320,9 +346,9 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
             acc_comp[1] = fmaf(dgc, -dcurve, acc_comp[1]);                    // threshold
             acc_comp[2] = fmaf(dgc, -fmaf(tc * tc, tb.inv_2knee, lin) * tb.inv_ratio2, acc_comp[2]);  // ratio
             acc_comp[3] = fmaf(dgc, tb.slope * tc * tb.inv_2knee * (1.0f - tc * tb.inv_knee), acc_comp[3]);  // knee
-            const float dside = (fabsf(side) > kCompEps) ? dgc * dcurve * k20OverLn10 / side : 0.0f;
+            const float dside = (fabsf(side) > kCompEps) ? __fdividef(dgc * dcurve * k20OverLn10, side) : 0.0f;
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) u[c][i] = dbuf[c * buf_stride + pidx(tid * L + i + LA)] + dside;
+            for (int c = 0; c < NCH; ++c) u[c][i] = dbuf[c * buf_stride + pLA + pb + i] + dside;
         }
     } else {
         // no compressor: chain output = EQ output
@@ -348,33 +374,55 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
     if (a.flags & kChainEq) {
         // y[n-1], y[n-2] at the chunk start for the last section's output
         float ym1[NCH], ym2[NCH];
+        {
+            float* nb0 = s_nb + 2 * NW * NCH * 2;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            ym1[c] = __shfl_up_sync(0xffffffffu, v[c][L - 1], 1);
-            ym2[c] = __shfl_up_sync(0xffffffffu, v[c][L - 2], 1);
-            if (lane == 31) { s_nb[(warp * NCH + c) * 2 + 0] = v[c][L - 1]; s_nb[(warp * NCH + c) * 2 + 1] = v[c][L - 2]; }
-        }
-        __syncthreads();
+            for (int c = 0; c < NCH; ++c) {
+                ym1[c] = __shfl_up_sync(0xffffffffu, v[c][L - 1], 1);
+                ym2[c] = __shfl_up_sync(0xffffffffu, v[c][L - 2], 1);
+                if (lane == 31) { nb0[(warp * NCH + c) * 2 + 0] = v[c][L - 1]; nb0[(warp * NCH + c) * 2 + 1] = v[c][L - 2]; }
+            }
+            __syncthreads();
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            if (lane == 0) {
-                if (warp > 0) { ym1[c] = s_nb[((warp - 1) * NCH + c) * 2 + 0]; ym2[c] = s_nb[((warp - 1) * NCH + c) * 2 + 1]; }
-                else if (has_pred) { ym1[c] = __ldg(tail_in + (6 * NCH + c) * 2 + 1); ym2[c] = __ldg(tail_in + (6 * NCH + c) * 2 + 0); }
-                else { ym1[c] = 0.0f; ym2[c] = 0.0f; }
+            for (int c = 0; c < NCH; ++c) {
+                if (lane == 0) {
+                    if (warp > 0) { ym1[c] = nb0[((warp - 1) * NCH + c) * 2 + 0]; ym2[c] = nb0[((warp - 1) * NCH + c) * 2 + 1]; }
+                    else if (has_pred) { ym1[c] = __ldg(tail_in + (6 * NCH + c) * 2 + 1); ym2[c] = __ldg(tail_in + (6 * NCH + c) * 2 + 0); }
+                    else { ym1[c] = 0.0f; ym2[c] = 0.0f; }
+                }
             }
         }
-        __syncthreads();  // s_nb is rewritten per section below
 
+        // section states from forward's checkpoints, fetched one section ahead of their use
+        float sv1[NCH], sv2[NCH];
+        if (saved) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                sv1[c] = __ldg(ssave + (((kNumSections - 1) * NCH + c) * 2 + 0) * NT + tid);
+                sv2[c] = __ldg(ssave + (((kNumSections - 1) * NCH + c) * 2 + 1) * NT + tid);
+            }
+        }
 #pragma unroll 1
         for (int k = kNumSections - 1; k >= 0; --k) {
             const SectionTab& st = tb.sec[k];
+            float* nb = s_nb + (k & 1) * NW * NCH * 2;  // double-buffered: one barrier per section
             const float b0 = st.b0, b1 = st.b1, b2 = st.b2, na1 = -st.a1, na2 = -st.a2, inv_b0 = st.inv_b0;
             float xin[NCH][L];
             float r1[NCH], r2[NCH];
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 // (a) recover the section input from its output along the shared state trajectory
-                float s1 = sE[((k * NCH + c) * 2 + 0) * NT + tid], s2 = sE[((k * NCH + c) * 2 + 1) * NT + tid];
+                float s1, s2;
+                if (saved) {
+                    s1 = sv1[c]; s2 = sv2[c];
+                    if (k > 0) {
+                        sv1[c] = __ldg(ssave + (((k - 1) * NCH + c) * 2 + 0) * NT + tid);
+                        sv2[c] = __ldg(ssave + (((k - 1) * NCH + c) * 2 + 1) * NT + tid);
+                    }
+                } else {
+                    s1 = sE[((k * NCH + c) * 2 + 0) * NT + tid];
+                    s2 = sE[((k * NCH + c) * 2 + 1) * NT + tid];
+                }
 #pragma unroll
                 for (int i = 0; i < L; ++i) {
                     const float yv = v[c][i];
@@ -383,7 +431,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
                     s2 = fmaf(b2, x, na2 * yv);
                     xin[c][i] = x;
                 }
-                if (lane == 31) { s_nb[(warp * NCH + c) * 2 + 0] = xin[c][L - 1]; s_nb[(warp * NCH + c) * 2 + 1] = xin[c][L - 2]; }
+                if (lane == 31) { nb[(warp * NCH + c) * 2 + 0] = xin[c][L - 1]; nb[(warp * NCH + c) * 2 + 1] = xin[c][L - 2]; }
                 // (b) reverse-time all-pole recursion, zero right-hand state
                 float g1 = 0.0f, g2 = 0.0f;
 #pragma unroll
@@ -416,37 +464,24 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
                 xm1[c] = __shfl_up_sync(0xffffffffu, xin[c][L - 1], 1);
                 xm2[c] = __shfl_up_sync(0xffffffffu, xin[c][L - 2], 1);
             }
-            const int need = 2 + (kNumSections - 1 - k);
-            if (tid == 0) {
-                if (has_succ) {
-                    wait_flag_ge(succ_flag, need);
-#pragma unroll
-                    for (int qq = 0; qq < NCH * 2; ++qq) s_in[k * NCH * 2 + qq] = __ldcg(bstate_in + k * NCH * 2 + qq);
-                } else {
-#pragma unroll
-                    for (int qq = 0; qq < NCH * 2; ++qq) s_in[k * NCH * 2 + qq] = 0.0f;
-                }
-            }
+            if (warp == 0 && lane < NCH * 2 && has_succ && !((s_premask[0] >> (k * NCH * 2 + lane)) & 1u))
+                s_pre[k * NCH * 2 + lane] = mail_wait(bstate_in + k * NCH * 2 + lane, nowait);  // not prefetched
             __syncthreads();
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 float c1, c2, n1, n2;
-                cross_warp_rev<NW>(s_W + (k * NW * NCH + c) * 2, NCH * 2, st.P2, s_in[(k * NCH + c) * 2 + 0],
-                                   s_in[(k * NCH + c) * 2 + 1], lane, warp, c1, c2, n1, n2);
-                if (tid == 0) {
-                    bstate_out[(k * NCH + c) * 2 + 0] = n1;
-                    bstate_out[(k * NCH + c) * 2 + 1] = n2;
+                cross_warp_rev<NW>(s_W + (k * NW * NCH + c) * 2, NCH * 2, st.P2, s_pre[(k * NCH + c) * 2 + 0],
+                                   s_pre[(k * NCH + c) * 2 + 1], lane, warp, c1, c2, n1, n2);
+                if (tid == 0) {  // publish right away (value + tag in one store) so the predecessor can go on
+                    mail_put(bstate_out + (k * NCH + c) * 2 + 0, n1);
+                    mail_put(bstate_out + (k * NCH + c) * 2 + 1, n2);
                 }
                 mat2T_apply_acc(st.Ppow[31 - lane], c1, c2, x1[c], x2[c]);  // (g[L], g[L+1]) of this chunk
                 if (lane == 0) {
-                    if (warp > 0) { xm1[c] = s_nb[((warp - 1) * NCH + c) * 2 + 0]; xm2[c] = s_nb[((warp - 1) * NCH + c) * 2 + 1]; }
+                    if (warp > 0) { xm1[c] = nb[((warp - 1) * NCH + c) * 2 + 0]; xm2[c] = nb[((warp - 1) * NCH + c) * 2 + 1]; }
                     else if (has_pred) { xm1[c] = __ldg(tail_in + (k * NCH + c) * 2 + 1); xm2[c] = __ldg(tail_in + (k * NCH + c) * 2 + 0); }
                     else { xm1[c] = 0.0f; xm2[c] = 0.0f; }
                 }
-            }
-            if (tid == 0) {  // publish before the heavy part so the predecessor tile can proceed
-                __threadfence();
-                st_release(my_flag, need);
             }
             float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -489,7 +524,6 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
                 const float t = warp_sum(acc[j]);
                 if (lane == 0) s_part[warp * kGradCount + kGradEq + 5 * k + j] = t;
             }
-            __syncthreads();  // s_nb / s_in reuse by the next section
         }
     }
 

@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
     DMST_DYN_SMEM(smem_raw);
     float* ebuf = reinterpret_cast<float*>(smem_raw);  // [NCH][pidx(LA + TILE) + 1]
     DMST_SHARED_ARRAY(float, s_W, 7 * NW * NCH * 2);
-    DMST_SHARED_ARRAY(float, s_in, 7 * NCH * 2);
+    DMST_SHARED_ARRAY(float, s_pre, kStateStride);  // predecessor's end states ([sec][ch][2], smoother at 24)
+    DMST_SHARED_ARRAY(unsigned, s_premask, 1);      // which of them were already published at tile start
     DMST_SHARED_ARRAY(int, s_ticket, 1);
     DMST_SHARED_ARRAY(float, s_tabf, sizeof(RowTab) / 4);
     const RowTab& tb = *reinterpret_cast<const RowTab*>(s_tabf);
@@ -32,7 +33,24 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
     const int row = ticket - tile * a.nrows;
     const int LA = a.lookahead;
     const int ebuf_stride = pidx(LA + TILE) + 1;
+    // LA % 32 == 0 and L | 32 (checked on the host): pidx(LA + tid*L + i) = pLA + pb + i
+    const int pLA = pidx(LA), pb = pidx(tid * L);
 
+    float* tail2 = a.tail2 + ((long long)row * a.ntiles + tile) * kTail2Stride;
+    Mail* state_out = a.state + ((long long)row * a.ntiles + tile) * kStateStride;
+    const Mail* state_in = a.state + ((long long)row * a.ntiles + tile - 1) * kStateStride;
+    int* my_flag = a.flag + (long long)row * a.ntiles + tile;
+    const int* pred_flag = my_flag - 1;
+    // Prefetch whatever the predecessor tile has already published (usually everything: it was
+    // claimed nrows tickets earlier), so the per-section waits below rarely touch global memory.
+    const bool nowait = (a.flags & kChainDebugNoWait) != 0;
+    if (warp == 0) {
+        float pv = 0.0f;
+        const bool ok = (tile > 0) ? mail_try(state_in + lane, pv) : true;
+        s_pre[lane] = pv;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_premask[0] = m;
+    }
     {
         const float* src = reinterpret_cast<const float*>(a.tab + row);
         for (int i = tid; i < int(sizeof(RowTab) / 4); i += NT) s_tabf[i] = __ldg(src + i);
@@ -68,11 +86,6 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
     }
     __syncthreads();  // table in shared memory
 
-    float* tail2 = a.tail2 + ((long long)row * a.ntiles + tile) * kTail2Stride;
-    float* state_out = a.state + ((long long)row * a.ntiles + tile) * kStateStride;
-    const float* state_in = a.state + ((long long)row * a.ntiles + tile - 1) * kStateStride;
-    int* my_flag = a.flag + (long long)row * a.ntiles + tile;
-    const int* pred_flag = my_flag - 1;
 
     if (a.flags & kChainGain) {
         const float g = tb.g_in;
@@ -96,12 +109,15 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
             const SectionTab& st = tb.sec[k];
             const float b0 = st.b0, b1 = st.b1, b2 = st.b2, na1 = -st.a1, na2 = -st.a2;
             float s1[NCH], s2[NCH];
+            constexpr int NSUB = L / kBwdChunk;           // state checkpoints per thread chunk
+            float zm1[NCH][NSUB], zm2[NCH][NSUB];         // zero-state states at the checkpoints
             // zero-state pass over the thread chunk (transposed direct form II)
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 float z1 = 0.0f, z2 = 0.0f;
 #pragma unroll
                 for (int i = 0; i < L; ++i) {
+                    if (i % kBwdChunk == 0) { zm1[c][i / kBwdChunk] = z1; zm2[c][i / kBwdChunk] = z2; }
                     const float x = v[c][i];
                     const float yv = fmaf(b0, x, z1);
                     z1 = fmaf(b1, x, fmaf(na1, yv, z2));
@@ -132,40 +148,35 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
                     s_W[((k * NW + warp) * NCH + c) * 2 + 1] = s2[c];
                 }
             }
-            if (tid == 0) {
-                if (tile > 0) {
-                    wait_flag_ge(pred_flag, k + 1);
-#pragma unroll
-                    for (int q = 0; q < NCH * 2; ++q) s_in[k * NCH * 2 + q] = __ldcg(state_in + k * NCH * 2 + q);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < NCH * 2; ++q) s_in[k * NCH * 2 + q] = 0.0f;
-                }
-            }
+            if (warp == 0 && lane < NCH * 2 && !((s_premask[0] >> (k * NCH * 2 + lane)) & 1u))
+                s_pre[k * NCH * 2 + lane] = mail_wait(state_in + k * NCH * 2 + lane, nowait);  // not prefetched
             __syncthreads();
             // second-level scan over warps -> warp carry-in; publish the tile end state
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 float c1, c2, n1, n2;
-                cross_warp_fwd<NW>(s_W + (k * NW * NCH + c) * 2, NCH * 2, st.P2, s_in[(k * NCH + c) * 2 + 0],
-                                   s_in[(k * NCH + c) * 2 + 1], lane, warp, c1, c2, n1, n2);
-                if (tid == 0) {
-                    state_out[(k * NCH + c) * 2 + 0] = n1;
-                    state_out[(k * NCH + c) * 2 + 1] = n2;
+                cross_warp_fwd<NW>(s_W + (k * NW * NCH + c) * 2, NCH * 2, st.P2, s_pre[(k * NCH + c) * 2 + 0],
+                                   s_pre[(k * NCH + c) * 2 + 1], lane, warp, c1, c2, n1, n2);
+                if (tid == 0) {  // publish: value + tag in one 8-byte store, no fence needed
+                    mail_put(state_out + (k * NCH + c) * 2 + 0, n1);
+                    mail_put(state_out + (k * NCH + c) * 2 + 1, n2);
                 }
                 // lane carry-in = exclusive prefix + P^lane * C_w
                 mat2_apply_acc(st.Ppow[lane], c1, c2, e1[c], e2[c]);
             }
-            if (tid == 0) {
-                __threadfence();
-                st_release(my_flag, k + 1);
-            }
             // add the homogeneous response to the carried-in state
+            float* ssave = a.ssave ? a.ssave + ((long long)row * a.ntiles + tile) * (kNumSections * NCH * 2) * (TILE / kBwdChunk)
+                                   : nullptr;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 float h1 = e1[c], h2 = e2[c];
 #pragma unroll
                 for (int i = 0; i < L; ++i) {
+                    if (i % kBwdChunk == 0 && ssave) {  // true state at this checkpoint
+                        const int tb = tid * NSUB + i / kBwdChunk;
+                        ssave[((k * NCH + c) * 2 + 0) * (TILE / kBwdChunk) + tb] = zm1[c][i / kBwdChunk] + h1;
+                        ssave[((k * NCH + c) * 2 + 1) * (TILE / kBwdChunk) + tb] = zm2[c][i / kBwdChunk] + h2;
+                    }
                     const float t = h1;
                     v[c][i] += t;
                     h1 = fmaf(na1, t, h2);
@@ -182,6 +193,12 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
         }
     }
 
+    if (a.esave) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+            store_chunk<L>(a.esave + (long long)(row * NCH + c) * a.Tp + t0, a.Tp - t0, true, v[c]);
+    }
+
     // ------------------------------ compressor ------------------------------
     if (a.flags & kChainComp) {
         // EQ output into the delay line; its last LA samples go to the successor tile.
@@ -189,7 +206,7 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-            for (int i = 0; i < L; ++i) ebuf[c * ebuf_stride + pidx(LA + tid * L + i)] = v[c][i];
+            for (int i = 0; i < L; ++i) ebuf[c * ebuf_stride + pLA + pb + i] = v[c][i];
             const int off = tid * L - (TILE - LA);
             if (off >= 0) store_chunk<L>(etail_out + c * LA + off, L, (LA & 3) == 0, v[c]);
             else if (off + L > 0) {
@@ -223,18 +240,17 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
         if (lane == 31) s_W[(6 * NW + warp) * NCH * 2] = gs;
         if (tid == 0) {
             if (tile > 0) {
-                wait_flag_ge(pred_flag, kFlagSmooth);
-                s_in[6 * NCH * 2] = __ldcg(state_in + kStateSmooth);
-            } else {
-                s_in[6 * NCH * 2] = 0.0f;
+                wait_flag_ge(pred_flag, kFlagSmooth, nowait);  // predecessor's halo (etail) is complete
+                if (!((s_premask[0] >> kStateSmooth) & 1u)) s_pre[kStateSmooth] = mail_wait(state_in + kStateSmooth, nowait);
             }
         }
         __syncthreads();
         float cw, gend;
-        cross_warp_fwd1<NW>(s_W + 6 * NW * NCH * 2, NCH * 2, tb.a2pow, s_in[6 * NCH * 2], lane, warp, cw, gend);
+        cross_warp_fwd1<NW>(s_W + 6 * NW * NCH * 2, NCH * 2, tb.a2pow, s_pre[kStateSmooth], lane, warp, cw, gend);
         if (tid == 0) {
-            state_out[kStateSmooth] = gend;
-            __threadfence();  // also orders every thread's etail stores (made before the barrier)
+            mail_put(state_out + kStateSmooth, gend);
+            // release is cumulative over the barrier: every thread's etail stores made before the
+            // __syncthreads above are visible to whoever acquires this flag
             st_release(my_flag, kFlagSmooth);
         }
         const float carry = fmaf(tb.a_lane[lane], cw, ex);
@@ -253,7 +269,7 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
             const float gtrue = fmaf(tb.a_i[i], carry, g[i]);
             const float G = fast_exp2(kLog2Per20Db * (gtrue + makeup));
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) v[c][i] = ebuf[c * ebuf_stride + pidx(tid * L + i)] * G;
+            for (int c = 0; c < NCH; ++c) v[c][i] = ebuf[c * ebuf_stride + pb + i] * G;
         }
     }
 

@@ -1,6 +1,7 @@
 // Host-side launch logic of the mix console behind the C ABI (include/diffmst_b200.h).
 #pragma once
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/diffmst_b200.h"
@@ -12,12 +13,27 @@ namespace dmst {
 
 // Tile geometry.  Forward and backward must agree on NT*L per row kind because backward
 // restarts each tile from the carry-in states the forward pass saved.
+#ifndef DMST_TRACK_CFG
+#define DMST_TRACK_CFG 0
+#endif
+#if DMST_TRACK_CFG == 0
 constexpr int kTrackFwdL = 32, kTrackFwdNT = 256;   // 8192-sample tiles
-constexpr int kTrackBwdL = 16, kTrackBwdNT = 512;
+constexpr int kTrackBwdL = 16, kTrackBwdNT = 512, kTrackBwdMinB = 1;
+#elif DMST_TRACK_CFG == 1
+constexpr int kTrackFwdL = 32, kTrackFwdNT = 128;   // 4096-sample tiles, small CTAs
+constexpr int kTrackBwdL = 16, kTrackBwdNT = 256, kTrackBwdMinB = 2;
+#elif DMST_TRACK_CFG == 2
+constexpr int kTrackFwdL = 16, kTrackFwdNT = 256;   // 4096-sample tiles
+constexpr int kTrackBwdL = 16, kTrackBwdNT = 256, kTrackBwdMinB = 2;
+#else
+constexpr int kTrackFwdL = 16, kTrackFwdNT = 128;   // 2048-sample tiles
+constexpr int kTrackBwdL = 16, kTrackBwdNT = 128, kTrackBwdMinB = 4;
+#endif
 constexpr int kMasterL = 16, kMasterNT = 256;       // 4096-sample tiles, 2 channels per thread
 constexpr int kTrackTile = kTrackFwdL * kTrackFwdNT;
 constexpr int kMasterTile = kMasterL * kMasterNT;
 static_assert(kTrackFwdL * kTrackFwdNT == kTrackBwdL * kTrackBwdNT, "forward/backward tiles must agree");
+static_assert(kTrackBwdL == kBwdChunk && kMasterL == kBwdChunk && kTrackFwdL % kBwdChunk == 0, "checkpoint spacing");
 
 #ifdef DMST_EMULATE
 #define DMST_MEMSET_ASYNC(ptr, val, bytes, stream) (memset((ptr), (val), (bytes)), 0)
@@ -77,13 +93,15 @@ struct Carver {
 struct ConsoleWs {
     int* header;          // [0..3] tickets (fwd track, fwd master, bwd master, bwd track)
     RowTab *track_tab, *track_tab_b, *master_tab;  // track_tab: forward L, track_tab_b: backward L
-    float *y, *bus_pre, *dbus;
+    float *y, *bus_pre, *dbus, *esave, *ssave;
     // forward chain (kept for backward)
     int *t_flag, *m_flag;
-    float *t_state, *m_state, *t_tail2, *m_tail2, *t_etail, *m_etail;
+    Mail *t_state, *m_state;
+    float *t_tail2, *m_tail2, *t_etail, *m_etail;
     // backward chain
     int *t_bflag, *m_bflag;
-    float *t_bstate, *m_bstate, *t_dhead, *m_dhead, *t_partial, *m_partial;
+    Mail *t_bstate, *m_bstate;
+    float *t_dhead, *m_dhead, *t_partial, *m_partial;
     size_t flags_begin, flags_end;    // byte range of forward flags (zeroed per forward)
     size_t bflags_begin, bflags_end;  // byte range of backward flags
     int Tp, nt_track, nt_master;
@@ -104,22 +122,24 @@ inline ConsoleWs carve_console(void* base, int B, int N, int T, int la_t, int la
     w.y = c.take<float>(rows * w.Tp);
     w.bus_pre = c.take<float>((size_t)B * 2 * w.Tp);
     w.dbus = c.take<float>((size_t)B * 2 * w.Tp);
-    w.flags_begin = (c.off + 255) & ~size_t(255);
+    w.esave = c.take<float>(rows * w.Tp);
+    w.ssave = c.take<float>(rows * w.nt_track * (size_t)(kNumSections * 2) * (kTrackTile / kBwdChunk));
+    w.flags_begin = (c.off + 255) & ~size_t(255);   // zeroed before every forward
     w.t_flag = c.take<int>(rt);
     w.m_flag = c.take<int>(rm);
+    w.t_state = c.take<Mail>(rt * kStateStride);
+    w.m_state = c.take<Mail>(rm * kStateStride);
     w.flags_end = c.off;
-    w.bflags_begin = (c.off + 255) & ~size_t(255);
+    w.bflags_begin = (c.off + 255) & ~size_t(255);  // zeroed before every backward
     w.t_bflag = c.take<int>(rt);
     w.m_bflag = c.take<int>(rm);
+    w.t_bstate = c.take<Mail>(rt * kStateStride);
+    w.m_bstate = c.take<Mail>(rm * kStateStride);
     w.bflags_end = c.off;
-    w.t_state = c.take<float>(rt * kStateStride);
-    w.m_state = c.take<float>(rm * kStateStride);
     w.t_tail2 = c.take<float>(rt * kTail2Stride);
     w.m_tail2 = c.take<float>(rm * kTail2Stride);
     w.t_etail = c.take<float>(rt * (size_t)la_t + 4);
     w.m_etail = c.take<float>(rm * 2 * (size_t)la_m + 4);
-    w.t_bstate = c.take<float>(rt * kStateStride);
-    w.m_bstate = c.take<float>(rm * kStateStride);
     w.t_dhead = c.take<float>(rt * (size_t)la_t + 4);
     w.m_dhead = c.take<float>(rm * 2 * (size_t)la_m + 4);
     w.t_partial = c.take<float>(rt * kGradCount);
@@ -166,6 +186,7 @@ inline int check_call(const ConsoleCall& k) {
     if (!(k.flags & DMST_USE_TRACK_PANNER)) return DMST_EINVAL;     // broken upstream (modules.py:269)
     if (!(k.flags & DMST_BASIC_CONSOLE) && !k.master_params) return DMST_EINVAL;
     if (k.la_t < 0 || k.la_t > kTrackTile || k.la_m < 0 || k.la_m > kMasterTile) return DMST_EINVAL;
+    if ((k.la_t & 31) || (k.la_m & 31)) return DMST_EINVAL;  // look-ahead must be a multiple of 32 samples
     return 0;
 }
 
@@ -193,19 +214,25 @@ inline void fill_prepare(PrepareArgs& p, const ConsoleCall& k, bool master, Cons
     p.sr = (double)k.sr; p.status = status;
 }
 
+inline unsigned debug_flags() {
+    static const unsigned f = (getenv("DMST_DEBUG_NOWAIT") && getenv("DMST_DEBUG_NOWAIT")[0] == '1') ? kChainDebugNoWait : 0u;
+    return f;
+}
+
 inline void fill_chain(ChainArgs& a, const ConsoleCall& k, bool master, ConsoleWs& w) {
     memset(&a, 0, sizeof(a));
     a.N = k.N; a.T = k.T; a.Tp = w.Tp;
     if (!master) {
-        a.nrows = k.B * k.N; a.ntiles = w.nt_track; a.flags = track_chain_flags(k.flags);
+        a.nrows = k.B * k.N; a.ntiles = w.nt_track; a.flags = track_chain_flags(k.flags) | debug_flags();
         a.lookahead = k.la_t;
         a.src = k.tracks; a.src_batch_stride = k.tbs; a.src_row_stride = k.trs;
         a.src_vec_ok = aligned16(k.tracks) && (k.tbs % 4 == 0) && (k.trs % 4 == 0);
         a.tab = w.track_tab; a.track_tab = w.track_tab; a.y = w.y;
+        if (a.flags & kChainEq) { a.esave = w.esave; a.ssave = w.ssave; }
         a.ticket = w.header + 0; a.flag = w.t_flag; a.state = w.t_state; a.tail2 = w.t_tail2; a.etail = w.t_etail;
         a.partial = w.t_partial; a.bflag = w.t_bflag; a.bstate = w.t_bstate; a.dhead = w.t_dhead;
     } else {
-        a.nrows = k.B; a.ntiles = w.nt_master; a.flags = master_chain_flags(k.flags);
+        a.nrows = k.B; a.ntiles = w.nt_master; a.flags = master_chain_flags(k.flags) | debug_flags();
         a.lookahead = k.la_m;
         a.src = w.y; a.tab = w.master_tab; a.track_tab = w.track_tab; a.bus_pre = w.bus_pre;
         a.ticket = w.header + 1; a.flag = w.m_flag; a.state = w.m_state; a.tail2 = w.m_tail2; a.etail = w.m_etail;
@@ -301,7 +328,7 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
     at.user_vec_ok = (k.T % 4 == 0) && (!gmixed || aligned16(gmixed)) && (!at.gsrc || aligned16(at.gsrc));
     at.ticket = w.header + 3;
     {
-        auto kern = chain_bwd_kernel<1, kTrackBwdL, kTrackBwdNT, false, 1>;
+        auto kern = chain_bwd_kernel<1, kTrackBwdL, kTrackBwdNT, false, kTrackBwdMinB>;
         const size_t smem = bwd_smem_bytes(1, kTrackTile, k.la_t, kTrackBwdNT);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
         at.tab = w.track_tab_b;

@@ -65,9 +65,30 @@ __global__ void mr_loss_kernel(MrLossArgs a) {
     r = block_sum(s_lin, sh); if (threadIdx.x == 0) out[3] = r;
 }
 
+// Second stage of the reductions: one block per row sums that row's block partials in float64
+// (fixed assignment of partials to threads + fixed-shape tree => deterministic).
+struct MrRowSumArgs { const float* partial; int blocks_per_row; double* rowsum; /* [rows][4] */ };
+__global__ void mr_rowsum_kernel(MrRowSumArgs a) {
+    DMST_SHARED_ARRAY(double, sh, 4 * 128);
+    const int row = blockIdx.x, tid = threadIdx.x;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = tid; b < a.blocks_per_row; b += blockDim.x) {
+        const float4 p = *reinterpret_cast<const float4*>(a.partial + ((long long)row * a.blocks_per_row + b) * 4);
+        s[0] += p.x; s[1] += p.y; s[2] += p.z; s[3] += p.w;
+    }
+    for (int j = 0; j < 4; ++j) sh[j * 128 + tid] = s[j];
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (tid < o)
+            for (int j = 0; j < 4; ++j) sh[j * 128 + tid] += sh[j * 128 + tid + o];
+        __syncthreads();
+    }
+    if (tid < 4) a.rowsum[row * 4 + tid] = sh[tid * 128];
+}
+
 struct MrFinalArgs {
-    const float* partial;
-    int rows, blocks_per_row, per_row;
+    const double* rowsum;
+    int rows, per_row;
     float w_sc, w_log, w_lin;
     int n_res, res_index;
     float* loss;        // [0] total (accumulated over resolutions), [1 + 3*r ...] sc, log, lin
@@ -75,35 +96,27 @@ struct MrFinalArgs {
     float* scal;        // [2]: coefficient of sign(log) / |X| and of sign(lin)
 };
 
-// one block of 32*k threads; thread per row for the row sums, then a serial finish
 __global__ void mr_final_kernel(MrFinalArgs a) {
-    DMST_SHARED_ARRAY(double, acc, 4);
-    if (threadIdx.x == 0) { acc[0] = acc[1] = acc[2] = acc[3] = 0.0; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double sc = 0.0, slog = 0.0, slin = 0.0;
-        for (int row = 0; row < a.rows; ++row) {
-            double d2 = 0.0, y2 = 0.0;
-            for (int b = 0; b < a.blocks_per_row; ++b) {
-                const float* p = a.partial + ((long long)row * a.blocks_per_row + b) * 4;
-                d2 += p[0]; y2 += p[1]; slog += p[2]; slin += p[3];
-            }
-            const double num = sqrt(d2), den = sqrt(y2);
-            sc += num / den;
-            // d/d|X| of w_sc * (1/rows) * ||Y|-|X||_F / ||Y||_F = w_sc/(rows) * (|X|-|Y|) / (num*den)
-            a.row_coef[row] = (num > 0.0) ? (float)(a.w_sc / (a.rows * (double)a.n_res * num * den)) : 0.0f;
-        }
-        const double cnt = (double)a.rows * (double)a.per_row;
-        const double l_sc = sc / a.rows, l_log = slog / cnt, l_lin = slin / cnt;
-        const double lr = a.w_sc * l_sc + a.w_log * l_log + a.w_lin * l_lin;
-        a.loss[1 + 3 * a.res_index + 0] = (float)l_sc;
-        a.loss[1 + 3 * a.res_index + 1] = (float)l_log;
-        a.loss[1 + 3 * a.res_index + 2] = (float)l_lin;
-        const float prev = (a.res_index == 0) ? 0.0f : a.loss[0];
-        a.loss[0] = prev + (float)(lr / a.n_res);
-        a.scal[0] = (float)(a.w_log / (a.n_res * cnt));
-        a.scal[1] = (float)(a.w_lin / (a.n_res * cnt));
+    if (threadIdx.x != 0) return;
+    double sc = 0.0, slog = 0.0, slin = 0.0;
+    for (int row = 0; row < a.rows; ++row) {
+        const double d2 = a.rowsum[row * 4 + 0], y2 = a.rowsum[row * 4 + 1];
+        slog += a.rowsum[row * 4 + 2]; slin += a.rowsum[row * 4 + 3];
+        const double num = sqrt(d2), den = sqrt(y2);
+        sc += num / den;
+        // d/d|X| of w_sc * (1/rows) * ||Y|-|X||_F / ||Y||_F = w_sc/(rows) * (|X|-|Y|) / (num*den)
+        a.row_coef[row] = (num > 0.0) ? (float)(a.w_sc / (a.rows * (double)a.n_res * num * den)) : 0.0f;
     }
+    const double cnt = (double)a.rows * (double)a.per_row;
+    const double l_sc = sc / a.rows, l_log = slog / cnt, l_lin = slin / cnt;
+    const double lr = a.w_sc * l_sc + a.w_log * l_log + a.w_lin * l_lin;
+    a.loss[1 + 3 * a.res_index + 0] = (float)l_sc;
+    a.loss[1 + 3 * a.res_index + 1] = (float)l_log;
+    a.loss[1 + 3 * a.res_index + 2] = (float)l_lin;
+    const float prev = (a.res_index == 0) ? 0.0f : a.loss[0];
+    a.loss[0] = prev + (float)(lr / a.n_res);
+    a.scal[0] = (float)(a.w_log / (a.n_res * cnt));
+    a.scal[1] = (float)(a.w_lin / (a.n_res * cnt));
 }
 
 struct MrGradArgs {
@@ -150,7 +163,7 @@ __global__ void mr_grad_kernel(MrGradArgs a) {
 struct MrWs {
     float* frames;    // 2*rows*frames*n
     float2* spec;     // 2*rows*frames*bins
-    float* partial; float* row_coef; float* scal; void* fft_work;
+    float* partial; double* rowsum; float* row_coef; float* scal; void* fft_work;
     size_t total;
 };
 inline int mr_max_dims(const dmst_mrstft_cfg* c, int rows, int T, size_t* fr, size_t* sp, size_t* part, size_t* work) {
@@ -179,6 +192,7 @@ inline int mr_carve(void* base, const dmst_mrstft_cfg* c, int rows, int T, MrWs*
     w->frames = (float*)take(fr * 4);
     w->spec = (float2*)take(sp * 8);
     w->partial = (float*)take(part * 4);
+    w->rowsum = (double*)take((size_t)rows * 4 * 8);
     w->row_coef = (float*)take((size_t)rows * 4);
     w->scal = (float*)take(16);
     w->fft_work = take(work);
@@ -202,10 +216,8 @@ inline int mrstft_run(const float* x, long long xs, const float* y, long long ys
         const int per_row = frames * bins;
         float* fx = w.frames;
         float* fy = w.frames + (size_t)rows * frames * n;
-        FrameArgs fa{x, xs, rows, T, n, hop, wl, frames, win, fx};
-        frame_kernel<<<dim3(frames, rows), 256, 0, stream>>>(fa);
-        FrameArgs fb{y, ys, rows, T, n, hop, wl, frames, win, fy};
-        frame_kernel<<<dim3(frames, rows), 256, 0, stream>>>(fb);
+        FrameArgs fa{x, xs, rows, T, n, hop, wl, frames, win, fx, y, ys, fy};
+        frame_kernel<<<dim3(frames, rows, 2), 256, 0, stream>>>(fa);
         e = exec_r2c(n, 2 * rows * frames, w.frames, w.spec, w.fft_work, stream);
         if (e) return e;
         float2* X = w.spec;
@@ -213,7 +225,9 @@ inline int mrstft_run(const float* x, long long xs, const float* y, long long ys
         const int bpr = (per_row + kMrItemsPerBlock - 1) / kMrItemsPerBlock;
         MrLossArgs la{X, Y, rows, per_row, bpr, c->eps, w.partial};
         mr_loss_kernel<<<dim3(bpr, rows), kMrBlock, 0, stream>>>(la);
-        MrFinalArgs fa2{w.partial, rows, bpr, per_row, c->w_sc, c->w_log_mag, c->w_lin_mag, c->n_res, r,
+        MrRowSumArgs rs{w.partial, bpr, w.rowsum};
+        mr_rowsum_kernel<<<rows, 128, 0, stream>>>(rs);
+        MrFinalArgs fa2{w.rowsum, rows, per_row, c->w_sc, c->w_log_mag, c->w_lin_mag, c->n_res, r,
                         loss, w.row_coef, w.scal};
         mr_final_kernel<<<1, 32, 0, stream>>>(fa2);
         if (grad_x) {

@@ -33,13 +33,17 @@ struct FrameArgs {
     int rows, T, n, hop, win, frames;
     const float* window;   // win
     float* out;            // rows x frames x n
+    const float* x2;       // optional second signal (grid.z == 2)
+    long long row_stride2;
+    float* out2;
 };
 
-// grid: (frames, rows), block: 256
+// grid: (frames, rows, 1 or 2), block: 256
 __global__ void frame_kernel(FrameArgs a) {
     const int f = blockIdx.x, row = blockIdx.y;
-    const float* x = a.x + (long long)row * a.row_stride;
-    float* o = a.out + ((long long)row * a.frames + f) * a.n;
+    const bool second = blockIdx.z != 0;
+    const float* x = second ? a.x2 + (long long)row * a.row_stride2 : a.x + (long long)row * a.row_stride;
+    float* o = (second ? a.out2 : a.out) + ((long long)row * a.frames + f) * a.n;
     const int pad = a.n / 2, wl = (a.n - a.win) / 2;
     for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
         const int wi = i - wl;

@@ -113,6 +113,18 @@ static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) {
     return emul::shfl_generic(v, lane ^ m, true);
 }
 
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    emul::WarpCtx& w = emul::t_block->warps[emul::t_threadIdx.x / 32];
+    int lane = emul::t_threadIdx.x % 32;
+    w.buf[lane] = pred ? 1u : 0u;
+    w.bar->arrive_and_wait();
+    unsigned m = 0;
+    int n = std::min(32, emul::t_block->nthreads - 32 * (int)(emul::t_threadIdx.x / 32));
+    for (int i = 0; i < n; ++i) m |= (w.buf[i] & 1u) << i;
+    w.bar->arrive_and_wait();
+    return m;
+}
+
 static inline int atomicAdd(int* p, int v) {
     return reinterpret_cast<std::atomic<int>*>(p)->fetch_add(v);
 }
