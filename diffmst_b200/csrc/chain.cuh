@@ -16,7 +16,10 @@ constexpr int kStateStride = 32;   // floats per (row, tile): [sec][ch][2] (24) 
 constexpr int kStateSmooth = 24;
 constexpr int kTail2Stride = 32;   // floats per (row, tile): [stage 0..6][ch][2]
 constexpr int kFlagSmooth = 7;
-constexpr int kBwdChunk = 16;      // thread chunk of the backward kernel (state checkpoint spacing)     // flag value meaning "EQ sections 1..6 and smoother published"
+#ifndef DMST_BWD_CHUNK
+#define DMST_BWD_CHUNK 16
+#endif
+constexpr int kBwdChunk = DMST_BWD_CHUNK;  // thread chunk of the track backward kernel (state checkpoint spacing)     // flag value meaning "EQ sections 1..6 and smoother published"
 
 struct ChainArgs {
     // ---- geometry ----
@@ -187,6 +190,36 @@ __device__ __forceinline__ float4 load4(const float* p, int valid, bool vec_ok) 
     r.z = valid > 2 ? __ldg(p + 2) : 0.0f;
     r.w = valid > 3 ? __ldg(p + 3) : 0.0f;
     return r;
+}
+
+// Coalesced tile I/O through the padded shared-memory layout: the CTA moves TILE consecutive
+// floats with fully coalesced 128-bit global accesses, threads then read/write their own
+// L-sample chunk from shared memory (conflict-free thanks to the i + i/32 padding).
+template <int NT, int TILE>
+__device__ __forceinline__ void stage_in(float* stage, const float* g, int valid, bool vec_ok, int tid) {
+#pragma unroll
+    for (int q = tid; q < TILE / 4; q += NT) {
+        const int idx = 4 * q;
+        const float4 val = load4(g + idx, valid - idx, vec_ok);
+        const int p = pidx(idx);
+        stage[p] = val.x; stage[p + 1] = val.y; stage[p + 2] = val.z; stage[p + 3] = val.w;
+    }
+}
+template <int NT, int TILE>
+__device__ __forceinline__ void stage_out(float* g, const float* stage, int valid, bool vec_ok, int tid, float scale = 1.0f) {
+#pragma unroll
+    for (int q = tid; q < TILE / 4; q += NT) {
+        const int idx = 4 * q, p = pidx(idx), left = valid - idx;
+        const float4 val = make_float4(stage[p] * scale, stage[p + 1] * scale, stage[p + 2] * scale, stage[p + 3] * scale);
+        if (vec_ok && left >= 4) {
+            *reinterpret_cast<float4*>(g + idx) = val;
+        } else {
+            if (left > 0) g[idx] = val.x;
+            if (left > 1) g[idx + 1] = val.y;
+            if (left > 2) g[idx + 2] = val.z;
+            if (left > 3) g[idx + 3] = val.w;
+        }
+    }
 }
 
 // Static-curve gain computer of the dasp compressor, branch-free:

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
     // With checkpoints from forward (EQ output + section states every kBwdChunk samples) the
     // forward EQ recompute below is skipped.
     const bool saved = (a.esave != nullptr) && (a.flags & kChainEq);
-    static_assert(L == kBwdChunk, "state checkpoints are spaced by the backward chunk length");
+    static_assert(MASTER || L == kBwdChunk, "state checkpoints are spaced by the backward chunk length");
     const float* ssave = a.ssave ? a.ssave + rt * (kNumSections * NCH * 2) * NT : nullptr;
     float v[NCH][L];
     if (saved) {

@@ -57,35 +57,59 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
     }
 
     const int t0 = tile * TILE + tid * L;  // first sample of this thread's chunk
+    const int tbase = tile * TILE;          // first sample of the tile
+    float* ybuf = ebuf + NCH * ebuf_stride; // [NCH][pidx(TILE) + 1] staging of the chain output
+    const int ybuf_stride = pidx(TILE) + 1;
     float v[NCH][L];
 
+    // Source tile -> shared memory with coalesced accesses (staged in the part of the delay line
+    // that later receives the EQ output of the very same samples).
     if constexpr (!MASTER) {
         const int b = row / a.N, n = row - b * a.N;
-        const float* p = a.src + (long long)b * a.src_batch_stride + (long long)n * a.src_row_stride + t0;
-        load_chunk<L>(p, a.T - t0, a.src_vec_ok != 0, v[0]);
+        const float* p = a.src + (long long)b * a.src_batch_stride + (long long)n * a.src_row_stride + tbase;
+        stage_in<NT, TILE>(ebuf + pLA, p, a.T - tbase, a.src_vec_ok != 0, tid);
     } else {
-        // pan + bus sum (mst/modules.py:262-272): bus_c = sum_n g_c[n] * y[n]
+        // pan + bus sum (mst/modules.py:262-272): bus_c = sum_n g_c[n] * y[n], fixed order;
+        // each thread owns TILE/4/NT float4 columns of the tile, all their loads in flight per track
+        constexpr int NQ = TILE / 4 / NT;
+        float4 accl[NQ], accr[NQ];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-            for (int i = 0; i < L; ++i) v[c][i] = 0.0f;
+        for (int j = 0; j < NQ; ++j) { accl[j] = make_float4(0.f, 0.f, 0.f, 0.f); accr[j] = accl[j]; }
         for (int n = 0; n < a.N; ++n) {
             const int trow = row * a.N + n;
             const float gl = __ldg(&a.track_tab[trow].gL), gr = __ldg(&a.track_tab[trow].gR);
-            float yv[L];
-            load_chunk<L>(a.src + (long long)trow * a.Tp + t0, a.Tp - t0, true, yv);
+            float4 yv[NQ];
 #pragma unroll
-            for (int i = 0; i < L; ++i) {
-                v[0][i] = fmaf(gl, yv[i], v[0][i]);
-                if (NCH > 1) v[NCH - 1][i] = fmaf(gr, yv[i], v[NCH - 1][i]);
+            for (int j = 0; j < NQ; ++j) {
+                const int idx = 4 * (tid + j * NT);
+                yv[j] = load4(a.src + (long long)trow * a.Tp + tbase + idx, a.Tp - tbase - idx, true);
+            }
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+                accl[j].x = fmaf(gl, yv[j].x, accl[j].x); accl[j].y = fmaf(gl, yv[j].y, accl[j].y);
+                accl[j].z = fmaf(gl, yv[j].z, accl[j].z); accl[j].w = fmaf(gl, yv[j].w, accl[j].w);
+                accr[j].x = fmaf(gr, yv[j].x, accr[j].x); accr[j].y = fmaf(gr, yv[j].y, accr[j].y);
+                accr[j].z = fmaf(gr, yv[j].z, accr[j].z); accr[j].w = fmaf(gr, yv[j].w, accr[j].w);
             }
         }
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
-            store_chunk<L>(a.bus_pre + (long long)(row * NCH + c) * a.Tp + t0, a.Tp - t0, true, v[c]);
+        for (int j = 0; j < NQ; ++j) {
+            const int idx = 4 * (tid + j * NT);
+            const int pp = pLA + pidx(idx);
+            ebuf[pp] = accl[j].x; ebuf[pp + 1] = accl[j].y; ebuf[pp + 2] = accl[j].z; ebuf[pp + 3] = accl[j].w;
+            float* er = ebuf + (NCH - 1) * ebuf_stride;
+            er[pp] = accr[j].x; er[pp + 1] = accr[j].y; er[pp + 2] = accr[j].z; er[pp + 3] = accr[j].w;
+            if (tbase + idx < a.Tp) {  // Tp % 4 == 0: whole float4 or nothing
+                *reinterpret_cast<float4*>(a.bus_pre + (long long)(row * NCH + 0) * a.Tp + tbase + idx) = accl[j];
+                *reinterpret_cast<float4*>(a.bus_pre + (long long)(row * NCH + NCH - 1) * a.Tp + tbase + idx) = accr[j];
+            }
+        }
     }
-    __syncthreads();  // table in shared memory
-
+    __syncthreads();  // table and source tile in shared memory
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < L; ++i) v[c][i] = ebuf[c * ebuf_stride + pLA + pb + i];
 
     if (a.flags & kChainGain) {
         const float g = tb.g_in;
@@ -193,7 +217,7 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
         }
     }
 
-    if (a.esave) {
+    if (a.esave && !(a.flags & kChainComp)) {  // (with the compressor on, e is stored from the delay line below)
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
             store_chunk<L>(a.esave + (long long)(row * NCH + c) * a.Tp + t0, a.Tp - t0, true, v[c]);
@@ -201,19 +225,16 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
 
     // ------------------------------ compressor ------------------------------
     if (a.flags & kChainComp) {
-        // EQ output into the delay line; its last LA samples go to the successor tile.
+        // EQ output into the delay line (its last LA samples go to the successor tile, below)
         float* etail_out = a.etail + ((long long)row * a.ntiles + tile) * NCH * LA;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
 #pragma unroll
             for (int i = 0; i < L; ++i) ebuf[c * ebuf_stride + pLA + pb + i] = v[c][i];
+            // halo for the successor: written by the owning threads before the barrier so that the
+            // flag can be released right after it (keeps the inter-tile chain short)
             const int off = tid * L - (TILE - LA);
-            if (off >= 0) store_chunk<L>(etail_out + c * LA + off, L, (LA & 3) == 0, v[c]);
-            else if (off + L > 0) {
-#pragma unroll
-                for (int i = 0; i < L; ++i)
-                    if (off + i >= 0) etail_out[c * LA + off + i] = v[c][i];
-            }
+            if (off >= 0) store_chunk<L>(etail_out + c * LA + off, L, true, v[c]);  // L | LA: whole chunks
         }
         // side-chain level -> static gain curve -> zero-state one-pole smoothing
         float g[L];
@@ -254,6 +275,13 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
             st_release(my_flag, kFlagSmooth);
         }
         const float carry = fmaf(tb.a_lane[lane], cw, ex);
+        // checkpoint of the EQ output for backward: coalesced store from the delay line
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            if (a.esave)
+                stage_out<NT, TILE>(a.esave + (long long)(row * NCH + c) * a.Tp + tbase, ebuf + c * ebuf_stride + pLA,
+                                    a.Tp - tbase, true, tid);
+        }
         // halo: predecessor's last LA EQ outputs (zeros before the start of the signal)
         {
             const float* etail_in = a.etail + ((long long)row * a.ntiles + tile - 1) * NCH * LA;
@@ -275,18 +303,20 @@ __global__ void __launch_bounds__(NT) chain_fwd_kernel(ChainArgs a) {
 
     // ------------------------------ sinks ------------------------------
     if constexpr (!MASTER) {
-        store_chunk<L>(a.y + (long long)row * a.Tp + t0, a.Tp - t0, true, v[0]);
+        // tracks: stage the chain output and store it (and the panned copies) fully coalesced
+#pragma unroll
+        for (int i = 0; i < L; ++i) ybuf[pb + i] = v[0][i];
+        __syncthreads();
+        stage_out<NT, TILE>(a.y + (long long)row * a.Tp + tbase, ybuf, a.Tp - tbase, true, tid);
         if (a.want_mixed) {
             const int b = row / a.N, n = row - b * a.N;
-            float o[L];
-#pragma unroll
-            for (int i = 0; i < L; ++i) o[i] = tb.gL * v[0][i];
-            store_chunk<L>(a.mixed + ((long long)(b * 2 + 0) * a.N + n) * a.T + t0, a.T - t0, a.user_vec_ok != 0, o);
-#pragma unroll
-            for (int i = 0; i < L; ++i) o[i] = tb.gR * v[0][i];
-            store_chunk<L>(a.mixed + ((long long)(b * 2 + 1) * a.N + n) * a.T + t0, a.T - t0, a.user_vec_ok != 0, o);
+            stage_out<NT, TILE>(a.mixed + ((long long)(b * 2 + 0) * a.N + n) * a.T + tbase, ybuf, a.T - tbase,
+                                a.user_vec_ok != 0, tid, tb.gL);
+            stage_out<NT, TILE>(a.mixed + ((long long)(b * 2 + 1) * a.N + n) * a.T + tbase, ybuf, a.T - tbase,
+                                a.user_vec_ok != 0, tid, tb.gR);
         }
     } else {
+        // master: few rows, chain-latency bound; keep the footprint small (more tiles resident)
         if (a.flags & kChainOutGain) {
             const float go = tb.g_out;
 #pragma unroll

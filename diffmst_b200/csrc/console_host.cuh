@@ -25,15 +25,21 @@ constexpr int kTrackBwdL = 16, kTrackBwdNT = 256, kTrackBwdMinB = 2;
 #elif DMST_TRACK_CFG == 2
 constexpr int kTrackFwdL = 16, kTrackFwdNT = 256;   // 4096-sample tiles
 constexpr int kTrackBwdL = 16, kTrackBwdNT = 256, kTrackBwdMinB = 2;
-#else
+#elif DMST_TRACK_CFG == 3
 constexpr int kTrackFwdL = 16, kTrackFwdNT = 128;   // 2048-sample tiles
 constexpr int kTrackBwdL = 16, kTrackBwdNT = 128, kTrackBwdMinB = 4;
+#elif DMST_TRACK_CFG == 4                           // needs -DDMST_BWD_CHUNK=8
+constexpr int kTrackFwdL = 32, kTrackFwdNT = 128;   // 4096-sample tiles
+constexpr int kTrackBwdL = 8, kTrackBwdNT = 512, kTrackBwdMinB = 1;
+#else
+constexpr int kTrackFwdL = 32, kTrackFwdNT = 256;   // 8192-sample tiles, needs -DDMST_BWD_CHUNK=8
+constexpr int kTrackBwdL = 8, kTrackBwdNT = 1024, kTrackBwdMinB = 1;
 #endif
 constexpr int kMasterL = 16, kMasterNT = 256;       // 4096-sample tiles, 2 channels per thread
 constexpr int kTrackTile = kTrackFwdL * kTrackFwdNT;
 constexpr int kMasterTile = kMasterL * kMasterNT;
 static_assert(kTrackFwdL * kTrackFwdNT == kTrackBwdL * kTrackBwdNT, "forward/backward tiles must agree");
-static_assert(kTrackBwdL == kBwdChunk && kMasterL == kBwdChunk && kTrackFwdL % kBwdChunk == 0, "checkpoint spacing");
+static_assert(kTrackBwdL == kBwdChunk && kTrackFwdL % kBwdChunk == 0, "checkpoint spacing");
 
 #ifdef DMST_EMULATE
 #define DMST_MEMSET_ASYNC(ptr, val, bytes, stream) (memset((ptr), (val), (bytes)), 0)
@@ -167,7 +173,10 @@ inline unsigned master_chain_flags(unsigned f) {
     return c;
 }
 
-inline size_t fwd_smem_bytes(int nch, int tile, int la) { return (size_t)nch * (pidx(la + tile) + 1) * 4; }
+inline size_t fwd_smem_bytes(int nch, int tile, int la) {
+    // delay line (+ output staging for the track kernel)
+    return (size_t)(nch * (pidx(la + tile) + 1) + (nch == 1 ? pidx(tile) + 1 : 0)) * 4;
+}
 inline size_t bwd_smem_bytes(int nch, int tile, int la, int nt) {
     return (size_t)(2 * nch * (pidx(la + tile) + 1) + 12 * nch * nt) * 4;
 }
