@@ -343,8 +343,10 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# dram traffic of the track-backward kernel per launch (bytes) from profiles/ncu_r1_summary.md
-TRAFFIC_TRACK_BWD_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum of the track-backward kernel, one launch, from the
+# committed capture profiles/ncu_r1_summary.md (287.2 MB read + 28.8 MB written: the EQ-output and
+# section-state checkpoints forward leaves for backward come on top of the 151 MB algorithmic)
+TRAFFIC_TRACK_BWD_BYTES = 316.0e6
 
 
 def main():
