@@ -69,6 +69,20 @@ def lib():
     l.dmst_afl_backward.argtypes = [vp, ll, ll, vp, vp, fp5, vp, i, i, i, i, vp, vp, sz, vp]
     l.dmst_peak_normalize.restype = i
     l.dmst_peak_normalize.argtypes = [vp, ll, ll, vp, i, i, vp]
+    l.dmst_conv_nchw_to_padded_nhwc.restype = i
+    l.dmst_conv_nchw_to_padded_nhwc.argtypes = [vp, vp, i, i, i, i, vp]
+    l.dmst_conv_repack_weights.restype = i
+    l.dmst_conv_repack_weights.argtypes = [vp, vp, i, i, vp]
+    l.dmst_conv3x3_forward.restype = i
+    l.dmst_conv3x3_forward.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    l.dmst_conv_stats_workspace_bytes.restype = sz
+    l.dmst_conv_stats_workspace_bytes.argtypes = [i, i, i, i]
+    l.dmst_conv_channel_stats.restype = i
+    l.dmst_conv_channel_stats.argtypes = [vp, i, i, i, i, vp, vp, vp, sz, vp]
+    l.dmst_conv_affine_relu.restype = i
+    l.dmst_conv_affine_relu.argtypes = [vp, vp, vp, i, i, i, i, i, vp]
+    l.dmst_conv_avgpool.restype = i
+    l.dmst_conv_avgpool.argtypes = [vp, vp, i, i, i, i, i, i, i, vp]
     l.dmst_profile_enable.restype = i
     l.dmst_profile_enable.argtypes = [i]
     l.dmst_profile_read.restype = i

@@ -1,6 +1,7 @@
 // extern "C" entry points of libdiffmst_b200.so (include/diffmst_b200.h).
 #include "console_host.cuh"
 #include "afl.cuh"
+#include "conv_tc.cuh"
 #include "mrstft.cuh"
 #include "peaknorm.cuh"
 
@@ -144,5 +145,65 @@ int dmst_peak_normalize(const float* x, long long batch_stride, long long ch_str
                         void* stream) {
     return dmst::peak_normalize(x, batch_stride, ch_stride, y, B, T, reinterpret_cast<cudaStream_t>(stream));
 }
+
+// ---- Cnn14 ConvBlock pieces (tensor-core row) ----
+#ifndef DMST_EMULATE
+int dmst_conv_nchw_to_padded_nhwc(const float* x, float* y, int B, int C, int H, int W, void* stream) {
+    if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0) return DMST_EINVAL;
+    const long long total = (long long)B * (H + 2) * (W + 2) * C;
+    dmst::nchw_to_padded_nhwc_kernel<<<dmst::grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, B, C, H, W);
+    return (int)cudaGetLastError();
+}
+int dmst_conv_repack_weights(const float* w, float* w9, int Cout, int Cin, void* stream) {
+    if (!w || !w9 || Cout <= 0 || Cin <= 0) return DMST_EINVAL;
+    dmst::repack_weights_kernel<<<dmst::grid_for(9LL * Cout * Cin), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, w9, Cout, Cin);
+    return (int)cudaGetLastError();
+}
+int dmst_conv3x3_forward(const float* x_padded, const float* w9, const float* scale, const float* shift, float* y_padded,
+                         int B, int H, int W, int Cin, int Cout, int relu, void* stream) {
+    return dmst::conv3x3_forward(x_padded, w9, scale, shift, y_padded, B, H, W, Cin, Cout, relu,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+size_t dmst_conv_stats_workspace_bytes(int B, int H, int W, int C) {
+    const long long P = (long long)B * (H + 2) * (W + 2);
+    return (size_t)((P + dmst::kStatRows - 1) / dmst::kStatRows) * 2 * C * sizeof(float);
+}
+int dmst_conv_channel_stats(const float* y_padded, int B, int H, int W, int C, float* mean, float* var_biased,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    if (!y_padded || !mean || !var_biased || !workspace) return DMST_EINVAL;
+    if (workspace_bytes < dmst_conv_stats_workspace_bytes(B, H, W, C)) return DMST_EINVAL;
+    const int P = B * (H + 2) * (W + 2);
+    const int chunks = (P + dmst::kStatRows - 1) / dmst::kStatRows;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    dmst::channel_partial_kernel<<<chunks, 256, 0, s>>>(y_padded, P, C, reinterpret_cast<float*>(workspace));
+    dmst::channel_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(reinterpret_cast<float*>(workspace), chunks, C,
+                                                               (double)B * H * W, mean, var_biased);
+    return (int)cudaGetLastError();
+}
+int dmst_conv_affine_relu(float* y_padded, const float* scale, const float* shift, int B, int H, int W, int C, int relu,
+                          void* stream) {
+    if (!y_padded || !scale || !shift) return DMST_EINVAL;
+    const int P = B * (H + 2) * (W + 2);
+    dmst::affine_relu_kernel<<<dmst::grid_for((long long)P * C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        y_padded, P, H + 2, W + 2, C, scale, shift, relu);
+    return (int)cudaGetLastError();
+}
+int dmst_conv_avgpool(const float* x_padded, float* y, int B, int C, int H, int W, int kh, int kw, int out_padded_nhwc,
+                      void* stream) {
+    if (!x_padded || !y || kh <= 0 || kw <= 0 || H / kh <= 0 || W / kw <= 0) return DMST_EINVAL;
+    const long long total = (long long)B * (H / kh) * (W / kw) * C;
+    dmst::avgpool_kernel<<<dmst::grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x_padded, y, B, C, H, W, kh, kw,
+                                                                                                   out_padded_nhwc);
+    return (int)cudaGetLastError();
+}
+#else
+int dmst_conv_nchw_to_padded_nhwc(const float*, float*, int, int, int, int, void*) { return DMST_EINVAL; }
+int dmst_conv_repack_weights(const float*, float*, int, int, void*) { return DMST_EINVAL; }
+int dmst_conv3x3_forward(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, void*) { return DMST_EINVAL; }
+size_t dmst_conv_stats_workspace_bytes(int, int, int, int) { return 0; }
+int dmst_conv_channel_stats(const float*, int, int, int, int, float*, float*, void*, size_t, void*) { return DMST_EINVAL; }
+int dmst_conv_affine_relu(float*, const float*, const float*, int, int, int, int, int, void*) { return DMST_EINVAL; }
+int dmst_conv_avgpool(const float*, float*, int, int, int, int, int, int, int, void*) { return DMST_EINVAL; }
+#endif
 
 }  // extern "C"

@@ -1,0 +1,382 @@
+// 3x3 convolution (stride 1, pad 1, no bias) + per-channel affine (folded BatchNorm) + ReLU on the
+// 5th-generation tensor cores: the dense contraction of the Cnn14 ConvBlock (mst/panns.py:27-85).
+//
+// Layout: activations are NHWC float32 with a one-pixel zero border, flattened to a 2-D matrix
+// [P = B*(H+2)*(W+2) pixels, C channels].  The convolution is nine shifted GEMMs accumulated
+// into one TMEM tile:  out[p, n] = sum_{tap=(dy,dx)} sum_c in[p + dy*(W+2) + dx, c] * w[tap][n][c],
+// evaluated for every padded pixel index p (border outputs are overwritten with zeros, which is
+// exactly the zero border the next convolution needs).  So each A operand tile is a plain 2-D TMA
+// box at a shifted row coordinate (out-of-range rows are zero-filled by TMA) and each B tile is
+// a box of the repacked weights [9*Cout, Cin].
+//
+// Kernel: one CTA per (128 pixels x BN channels) tile, 192 threads:
+//   warp 0     TMA producer   (cp.async.bulk.tensor.2d -> 128B-swizzled shared tiles, mbarrier tx)
+//   warp 1     TMEM allocation + MMA issue (tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8;
+//              A and B from shared-memory descriptors, FP32 accumulator in TMEM;
+//              tcgen05.commit releases pipeline stages and finally signals the epilogue)
+//   warps 2-5  epilogue: tcgen05.ld 32x32b -> registers -> scale/shift (+ReLU) -> NHWC store
+// TF32 operands (float32 bits, 10-bit mantissa used by the tensor core) with FP32 accumulation:
+// the numerics class of the reference's cuDNN convolutions (torch enables TF32 convs by default).
+#pragma once
+#include "../../include/diffmst_b200.h"
+#include "common.cuh"
+
+#ifndef DMST_EMULATE
+#include <cuda.h>
+
+namespace dmst {
+
+constexpr int kConvBM = 128;      // pixels per tile (UMMA M)
+constexpr int kConvBK = 32;       // float32 elements per 128-byte swizzled row
+constexpr int kConvStages = 4;
+constexpr int kConvThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4)            // D format: F32
+           | (2u << 7)          // A format: TF32
+           | (2u << 10)         // B format: TF32
+           | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);  // K-major A and B
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct ConvArgs {
+    int P;            // padded pixels = B * Hp * Wp
+    int Hp, Wp;       // H + 2, W + 2
+    int Cin, Cout;
+    const float* scale;   // [Cout] or null (= 1)
+    const float* shift;   // [Cout] or null (= 0)
+    int relu;
+    float* out;       // [P][Cout], zero border written
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvArgs a) {
+    constexpr uint32_t kABytes = kConvBM * kConvBK * 4, kBBytes = BN * kConvBK * 4;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // 1024-byte aligned tiles (128B swizzle atoms)
+    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[kConvStages], empty_bar[kConvStages], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p0 = blockIdx.x * kConvBM, n0 = blockIdx.y * BN;
+    const int kchunks = a.Cin / kConvBK, iters = 9 * kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kConvStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: BN FP32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % kConvStages, round = it / kConvStages;
+                if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+                const int tap = it / kchunks, kc = it - tap * kchunks;
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                unsigned char* sa = tiles + (size_t)s * (kABytes + kBBytes);
+                mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
+                tma_load_2d(sa, &map_a, &full_bar[s], kc * kConvBK, p0 + dy * a.Wp + dx);
+                tma_load_2d(sa + kABytes, &map_b, &full_bar[s], kc * kConvBK, tap * a.Cout + n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(kConvBM, BN);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % kConvStages, round = it / kConvStages;
+                mbar_wait(&full_bar[s], round & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(tiles + (size_t)s * (kABytes + kBBytes));
+                const uint64_t adesc = umma_smem_desc(sa), bdesc = umma_smem_desc(sa + kABytes);
+#pragma unroll
+                for (int k = 0; k < kConvBK / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address
+                    umma_tf32(tmem_base, adesc + (uint64_t)((k * 32) >> 4), bdesc + (uint64_t)((k * 32) >> 4), idesc,
+                              (it | k) != 0);
+                umma_commit(&empty_bar[s]);           // stage free once these MMAs have read it
+            }
+            umma_commit(&tmem_full_bar);              // accumulator complete
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quarter = warp % 4
+        mbar_wait(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3;
+        const int p = p0 + quarter * 32 + lane;
+        bool interior = false;
+        if (p < a.P) {
+            const int rem = p % (a.Hp * a.Wp);
+            const int hp = rem / a.Wp, wp = rem - hp * a.Wp;
+            interior = hp >= 1 && hp <= a.Hp - 2 && wp >= 1 && wp <= a.Wp - 2;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (p < a.P) {
+                float* o = a.out + (size_t)p * a.Cout + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 v;
+                    float* vv = reinterpret_cast<float*>(&v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float x = __int_as_float((int)r[j + q]);
+                        const int n = n0 + c0 + j + q;
+                        if (a.scale) x *= __ldg(a.scale + n);
+                        if (a.shift) x += __ldg(a.shift + n);
+                        if (a.relu) x = fmaxf(x, 0.0f);
+                        vv[q] = interior ? x : 0.0f;
+                    }
+                    *reinterpret_cast<float4*>(o + j) = v;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+}
+
+// ---- small helper kernels around the tensor-core convolution ----
+
+// NCHW (B, C, H, W) -> zero-bordered NHWC (B, H+2, W+2, C); grid covers B*Hp*Wp*C elements
+__global__ void nchw_to_padded_nhwc_kernel(const float* x, float* y, int B, int C, int H, int W) {
+    const int Hp = H + 2, Wp = W + 2;
+    const long long total = (long long)B * Hp * Wp * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int wp = (int)(r % Wp); r /= Wp;
+        const int hp = (int)(r % Hp);
+        const int b = (int)(r / Hp);
+        float v = 0.0f;
+        if (hp >= 1 && hp <= H && wp >= 1 && wp <= W) v = __ldg(x + (((long long)b * C + c) * H + (hp - 1)) * W + (wp - 1));
+        y[i] = v;
+    }
+}
+
+// direct 3x3 convolution for the first layer (Cin is tiny: 1 spectrogram channel), padded NHWC in/out
+__global__ void conv3x3_direct_kernel(const float* x, const float* w9 /*[9][Cout][Cin]*/, const float* scale,
+                                      const float* shift, float* y, int P, int Hp, int Wp, int Cin, int Cout, int relu) {
+    const long long total = (long long)P * Cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i % Cout);
+        const long long p = i / Cout;
+        const int rem = (int)(p % ((long long)Hp * Wp));
+        const int hp = rem / Wp, wp = rem - hp * Wp;
+        float acc = 0.0f;
+        const bool interior = hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2;
+        if (interior) {
+            for (int tap = 0; tap < 9; ++tap) {
+                const long long q = p + (tap / 3 - 1) * Wp + (tap % 3 - 1);
+                for (int c = 0; c < Cin; ++c) acc = fmaf(__ldg(x + q * Cin + c), __ldg(w9 + ((long long)tap * Cout + n) * Cin + c), acc);
+            }
+            if (scale) acc *= __ldg(scale + n);
+            if (shift) acc += __ldg(shift + n);
+            if (relu) acc = fmaxf(acc, 0.0f);
+        }
+        y[i] = acc;
+    }
+}
+
+// average pool (kh x kw, stride = kernel, floor) of padded NHWC -> NCHW (B, C, H/kh, W/kw) or padded NHWC
+__global__ void avgpool_kernel(const float* x, float* y, int B, int C, int H, int W, int kh, int kw, int out_nhwc_padded) {
+    const int Ho = H / kh, Wo = W / kw, Hp = H + 2, Wp = W + 2;
+    const long long total = (long long)B * Ho * Wo * C;
+    const float inv = 1.0f / (float)(kh * kw);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        float s = 0.0f;
+        for (int dy = 0; dy < kh; ++dy)
+            for (int dx = 0; dx < kw; ++dx)
+                s += __ldg(x + (((long long)b * Hp + (ho * kh + dy + 1)) * Wp + (wo * kw + dx + 1)) * C + c);
+        s *= inv;
+        if (out_nhwc_padded) y[(((long long)b * (Ho + 2) + ho + 1) * (Wo + 2) + wo + 1) * C + c] = s;
+        else y[(((long long)b * C + c) * Ho + ho) * Wo + wo] = s;
+    }
+}
+
+// [Cout][Cin][3][3] -> [9][Cout][Cin]
+__global__ void repack_weights_kernel(const float* w, float* w9, int Cout, int Cin) {
+    const int total = 9 * Cout * Cin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % Cin, n = (i / Cin) % Cout, tap = i / (Cin * Cout);
+        w9[i] = __ldg(w + ((long long)n * Cin + c) * 9 + tap);
+    }
+}
+
+
+// ---- training-mode BatchNorm support: per-channel batch statistics of a raw conv output ----
+// The zero border contributes nothing, so sums over all P rows are sums over the B*H*W pixels.
+constexpr int kStatRows = 512;
+__global__ void channel_partial_kernel(const float* y, int P, int C, float* partial /*[chunks][2][C]*/) {
+    const int chunk = blockIdx.x;
+    const int r0 = chunk * kStatRows, r1 = min(r0 + kStatRows, P);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.0f, s2 = 0.0f;
+        for (int r = r0; r < r1; ++r) {
+            const float v = __ldg(y + (size_t)r * C + c);
+            s += v; s2 = fmaf(v, v, s2);
+        }
+        partial[((size_t)chunk * 2 + 0) * C + c] = s;
+        partial[((size_t)chunk * 2 + 1) * C + c] = s2;
+    }
+}
+__global__ void channel_final_kernel(const float* partial, int chunks, int C, double count, float* mean, float* var_biased) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, s2 = 0.0;
+    for (int k = 0; k < chunks; ++k) { s += partial[((size_t)k * 2 + 0) * C + c]; s2 += partial[((size_t)k * 2 + 1) * C + c]; }
+    const double m = s / count;
+    mean[c] = (float)m;
+    var_biased[c] = (float)fmax(s2 / count - m * m, 0.0);
+}
+// in-place y = relu(y * scale[c] + shift[c]) on interior pixels (border stays zero)
+__global__ void affine_relu_kernel(float* y, int P, int Hp, int Wp, int C, const float* scale, const float* shift, int relu) {
+    const long long total = (long long)P * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long p = i / C;
+        const int rem = (int)(p % ((long long)Hp * Wp));
+        const int hp = rem / Wp, wp = rem - hp * Wp;
+        if (hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2) {
+            float v = fmaf(y[i], __ldg(scale + c), __ldg(shift + c));
+            y[i] = relu ? fmaxf(v, 0.0f) : v;
+        }
+    }
+}
+inline int grid_for(long long total) { long long b = (total + 255) / 256; return (int)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b)); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// 2-D float32 row-major matrix [rows][cols], box = [box_rows][32 cols] with 128-byte swizzle
+inline int make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn f = encode_tiled();
+    if (!f) return 2000;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kConvBK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 2001 + (int)r;
+}
+
+inline int conv3x3_forward(const float* x_padded, const float* w9, const float* scale, const float* shift, float* y_padded,
+                           int B, int H, int W, int Cin, int Cout, int relu, cudaStream_t stream) {
+    if (!x_padded || !w9 || !y_padded || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return DMST_EINVAL;
+    const int Hp = H + 2, Wp = W + 2;
+    const long long P = (long long)B * Hp * Wp;
+    if (P > 0x7fffffffLL) return DMST_EINVAL;
+    if (Cin % kConvBK != 0 || Cout % 64 != 0) {   // small / odd channel counts: CUDA-core path
+        const long long total = P * Cout;
+        const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+        conv3x3_direct_kernel<<<blocks, 256, 0, stream>>>(x_padded, w9, scale, shift, y_padded, (int)P, Hp, Wp, Cin, Cout, relu);
+        return (int)cudaGetLastError();
+    }
+    const int BN = (Cout % 128 == 0) ? 128 : 64;
+    CUtensorMap ma, mb;
+    int e = make_map_2d(&ma, x_padded, (uint64_t)P, (uint64_t)Cin, kConvBM);
+    if (e) return e;
+    e = make_map_2d(&mb, w9, (uint64_t)9 * Cout, (uint64_t)Cin, (uint32_t)BN);
+    if (e) return e;
+    ConvArgs a{(int)P, Hp, Wp, Cin, Cout, scale, shift, relu, y_padded};
+    const dim3 grid((unsigned)((P + kConvBM - 1) / kConvBM), (unsigned)(Cout / BN));
+    const size_t smem = (size_t)kConvStages * (kConvBM * kConvBK * 4 + BN * kConvBK * 4) + 1024;
+    if (BN == 128) {
+        e = (int)cudaFuncSetAttribute(conv3x3_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e) return e;
+        conv3x3_tf32_kernel<128><<<grid, kConvThreads, smem, stream>>>(ma, mb, a);
+    } else {
+        e = (int)cudaFuncSetAttribute(conv3x3_tf32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e) return e;
+        conv3x3_tf32_kernel<64><<<grid, kConvThreads, smem, stream>>>(ma, mb, a);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dmst
+#endif

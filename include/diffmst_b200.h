@@ -162,6 +162,26 @@ int dmst_afl_backward(const float* input, long long batch_stride, long long ch_s
 int dmst_peak_normalize(const float* x, long long batch_stride, long long ch_stride, float* y,
                         int B, int T, void* stream);
 
+/* ---- Cnn14 ConvBlock on the tensor cores (mst/panns.py:27-85: conv3x3 -> BatchNorm -> ReLU, twice,
+ *      then average pooling; forward only in this round).  Activations between these calls are
+ *      NHWC float32 with a one-pixel zero border: (B, H+2, W+2, C). ---- */
+int dmst_conv_nchw_to_padded_nhwc(const float* x, float* y, int B, int C, int H, int W, void* stream);
+/* nn.Conv2d weight (Cout, Cin, 3, 3) -> (9, Cout, Cin) */
+int dmst_conv_repack_weights(const float* w, float* w9, int Cout, int Cin, void* stream);
+/* y = [relu](conv3x3(x) * scale[c] + shift[c]); scale/shift may be NULL (1 / 0).  TF32 tensor-core
+ * path (tcgen05 + TMA) when Cin % 32 == 0 and Cout % 64 == 0, CUDA-core path otherwise (first layer). */
+int dmst_conv3x3_forward(const float* x_padded, const float* w9, const float* scale, const float* shift,
+                         float* y_padded, int B, int H, int W, int Cin, int Cout, int relu, void* stream);
+/* training-mode BatchNorm: batch mean and biased variance per channel of a raw conv output */
+size_t dmst_conv_stats_workspace_bytes(int B, int H, int W, int C);
+int dmst_conv_channel_stats(const float* y_padded, int B, int H, int W, int C, float* mean, float* var_biased,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int dmst_conv_affine_relu(float* y_padded, const float* scale, const float* shift, int B, int H, int W, int C,
+                          int relu, void* stream);
+/* F.avg_pool2d(x, (kh, kw)) of a padded NHWC tensor -> NCHW (B, C, H/kh, W/kw), or padded NHWC again */
+int dmst_conv_avgpool(const float* x_padded, float* y, int B, int C, int H, int W, int kh, int kw,
+                      int out_padded_nhwc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
