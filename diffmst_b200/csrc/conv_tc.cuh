@@ -95,27 +95,38 @@ struct ConvArgs {
     float* out;       // [P][Cout], zero border written
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (channel tile
+// fastest, so CTAs running at the same time share A tiles in L2).  The shared-memory ring and
+// its barriers run continuously across tiles; the accumulator is double-buffered in TMEM so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
 template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvArgs a) {
     constexpr uint32_t kABytes = kConvBM * kConvBK * 4, kBBytes = BN * kConvBK * 4;
+    constexpr int kAcc = 2;  // TMEM accumulator stages
     extern __shared__ __align__(1024) unsigned char smem[];
     // 1024-byte aligned tiles (128B swizzle atoms)
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
-    __shared__ __align__(8) uint64_t full_bar[kConvStages], empty_bar[kConvStages], tmem_full_bar;
+    __shared__ __align__(8) uint64_t full_bar[kConvStages], empty_bar[kConvStages], tmem_full_bar[kAcc], tmem_empty_bar[kAcc];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p0 = blockIdx.x * kConvBM, n0 = blockIdx.y * BN;
     const int kchunks = a.Cin / kConvBK, iters = 9 * kchunks;
+    const int tiles_n = a.Cout / BN;
+    const int tiles_m = (a.P + kConvBM - 1) / kConvBM;
+    const int num_tiles = tiles_m * tiles_n;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kConvStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&tmem_full_bar, 1);
+        for (int s = 0; s < kAcc; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: BN FP32 accumulator columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(BN));
+    if (warp == 1) {  // TMEM: kAcc x BN FP32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(kAcc * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -125,83 +136,104 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % kConvStages, round = it / kConvStages;
-                if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-                const int tap = it / kchunks, kc = it - tap * kchunks;
-                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                unsigned char* sa = tiles + (size_t)s * (kABytes + kBBytes);
-                mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
-                tma_load_2d(sa, &map_a, &full_bar[s], kc * kConvBK, p0 + dy * a.Wp + dx);
-                tma_load_2d(sa + kABytes, &map_b, &full_bar[s], kc * kConvBK, tap * a.Cout + n0);
+            uint32_t g = 0;  // ring position, continuous across tiles
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int p0 = (tile / tiles_n) * kConvBM, n0 = (tile % tiles_n) * BN;
+                for (int it = 0; it < iters; ++it, ++g) {
+                    const uint32_t s = g % kConvStages, round = g / kConvStages;
+                    mbar_wait(&empty_bar[s], (round & 1) ^ 1);   // passes immediately on the first round
+                    const int tap = it / kchunks, kc = it - tap * kchunks;
+                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    unsigned char* sa = tiles + (size_t)s * (kABytes + kBBytes);
+                    mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
+                    tma_load_2d(sa, &map_a, &full_bar[s], kc * kConvBK, p0 + dy * a.Wp + dx);
+                    tma_load_2d(sa + kABytes, &map_b, &full_bar[s], kc * kConvBK, tap * a.Cout + n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(kConvBM, BN);
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % kConvStages, round = it / kConvStages;
-                mbar_wait(&full_bar[s], round & 1);
+            uint32_t g = 0, t = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+                const uint32_t acc = t % kAcc;
+                mbar_wait(&tmem_empty_bar[acc], ((t / kAcc) & 1) ^ 1);   // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(tiles + (size_t)s * (kABytes + kBBytes));
-                const uint64_t adesc = umma_smem_desc(sa), bdesc = umma_smem_desc(sa + kABytes);
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int it = 0; it < iters; ++it, ++g) {
+                    const uint32_t s = g % kConvStages, round = g / kConvStages;
+                    mbar_wait(&full_bar[s], round & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(tiles + (size_t)s * (kABytes + kBBytes));
+                    const uint64_t adesc = umma_smem_desc(sa), bdesc = umma_smem_desc(sa + kABytes);
 #pragma unroll
-                for (int k = 0; k < kConvBK / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address
-                    umma_tf32(tmem_base, adesc + (uint64_t)((k * 32) >> 4), bdesc + (uint64_t)((k * 32) >> 4), idesc,
-                              (it | k) != 0);
-                umma_commit(&empty_bar[s]);           // stage free once these MMAs have read it
+                    for (int k = 0; k < kConvBK / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address
+                        umma_tf32(tmem_d, adesc + (uint64_t)((k * 32) >> 4), bdesc + (uint64_t)((k * 32) >> 4), idesc,
+                                  (it | k) != 0);
+                    umma_commit(&empty_bar[s]);           // stage free once these MMAs have read it
+                }
+                umma_commit(&tmem_full_bar[acc]);          // accumulator complete
             }
-            umma_commit(&tmem_full_bar);              // accumulator complete
         }
     } else {
         // epilogue warps 2..5: TMEM lane quarter = warp % 4
-        mbar_wait(&tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quarter = warp & 3;
-        const int p = p0 + quarter * 32 + lane;
-        bool interior = false;
-        if (p < a.P) {
-            const int rem = p % (a.Hp * a.Wp);
-            const int hp = rem / a.Wp, wp = rem - hp * a.Wp;
-            interior = hp >= 1 && hp <= a.Hp - 2 && wp >= 1 && wp <= a.Wp - 2;
-        }
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+            const int p0 = (tile / tiles_n) * kConvBM, n0 = (tile % tiles_n) * BN;
+            const uint32_t acc = t % kAcc;
+            mbar_wait(&tmem_full_bar[acc], (t / kAcc) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int p = p0 + quarter * 32 + lane;
+            bool interior = false;
             if (p < a.P) {
-                float* o = a.out + (size_t)p * a.Cout + n0 + c0;
+                const int rem = p % (a.Hp * a.Wp);
+                const int hp = rem / a.Wp, wp = rem - hp * a.Wp;
+                interior = hp >= 1 && hp <= a.Hp - 2 && wp >= 1 && wp <= a.Wp - 2;
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 32 >= BN) {  // accumulator fully read: hand it back to the MMA warp before the stores
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                if (p < a.P) {
+                    float* o = a.out + (size_t)p * a.Cout + n0 + c0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 v;
-                    float* vv = reinterpret_cast<float*>(&v);
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v;
+                        float* vv = reinterpret_cast<float*>(&v);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float x = __int_as_float((int)r[j + q]);
-                        const int n = n0 + c0 + j + q;
-                        if (a.scale) x *= __ldg(a.scale + n);
-                        if (a.shift) x += __ldg(a.shift + n);
-                        if (a.relu) x = fmaxf(x, 0.0f);
-                        vv[q] = interior ? x : 0.0f;
+                        for (int q = 0; q < 4; ++q) {
+                            float x = __int_as_float((int)r[j + q]);
+                            const int n = n0 + c0 + j + q;
+                            if (a.scale) x *= __ldg(a.scale + n);
+                            if (a.shift) x += __ldg(a.shift + n);
+                            if (a.relu) x = fmaxf(x, 0.0f);
+                            vv[q] = interior ? x : 0.0f;
+                        }
+                        *reinterpret_cast<float4*>(o + j) = v;
                     }
-                    *reinterpret_cast<float4*>(o + j) = v;
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAcc * BN));
 }
 
 // ---- small helper kernels around the tensor-core convolution ----
@@ -364,7 +396,14 @@ inline int conv3x3_forward(const float* x_padded, const float* w9, const float* 
     e = make_map_2d(&mb, w9, (uint64_t)9 * Cout, (uint64_t)Cin, (uint32_t)BN);
     if (e) return e;
     ConvArgs a{(int)P, Hp, Wp, Cin, Cout, scale, shift, relu, y_padded};
-    const dim3 grid((unsigned)((P + kConvBM - 1) / kConvBM), (unsigned)(Cout / BN));
+    const long long num_tiles = ((P + kConvBM - 1) / kConvBM) * (Cout / BN);
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));  // persistent: one CTA per SM
     const size_t smem = (size_t)kConvStages * (kConvBM * kConvBK * 4 + BN * kConvBK * 4) + 1024;
     if (BN == 128) {
         e = (int)cudaFuncSetAttribute(conv3x3_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
