@@ -152,6 +152,49 @@ __device__ __forceinline__ float mail_wait(const Mail* p, bool skip = false) {
 // padded shared-memory index: conflict-free when lane l touches element l*L + i
 __host__ __device__ __forceinline__ int pidx(int i) { return i + (i >> 5); }
 
+// padded shared-memory index for 128-bit accesses: 4 floats of padding per 32, so that lane l reading
+// float4 #j of its own L-sample chunk (L = 16 or 32), or thread q moving float4 #q of a tile, is
+// conflict-free, and every float4 stays 16-byte aligned (targets of cp.async)
+__host__ __device__ __forceinline__ int pidx4(int i) { return i + ((i >> 5) << 2); }
+
+// ---------------------------------------------------------------------------------
+// Asynchronous global -> shared copies (LDGSTS) used to prefetch the next tile of a persistent CTA
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+#ifdef DMST_EMULATE
+    memcpy(smem_dst, gsrc, 16);
+#else
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+#ifdef DMST_EMULATE
+    memcpy(smem_dst, gsrc, 4);
+#else
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef DMST_EMULATE
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef DMST_EMULATE
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+// counter += v with release semantics (cumulative over a preceding __syncthreads, like st_release)
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+#ifdef DMST_EMULATE
+    reinterpret_cast<std::atomic<int>*>(p)->fetch_add(v, std::memory_order_release);
+#else
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+
 // 2^x by the MUFU unit (ex2.approx: relative error below 2^-22, flushes subnormal results)
 __device__ __forceinline__ float fast_exp2(float x) {
 #ifdef DMST_EMULATE

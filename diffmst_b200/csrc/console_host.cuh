@@ -21,7 +21,10 @@ constexpr int kTrackFwdL = 32, kTrackFwdNT = 256;   // 8192-sample tiles
 constexpr int kTrackBwdL = 16, kTrackBwdNT = 512, kTrackBwdMinB = 1;
 #elif DMST_TRACK_CFG == 1
 constexpr int kTrackFwdL = 32, kTrackFwdNT = 128;   // 4096-sample tiles, small CTAs
-constexpr int kTrackBwdL = 16, kTrackBwdNT = 256, kTrackBwdMinB = 2;
+#ifndef DMST_BWD_MINB
+#define DMST_BWD_MINB 2
+#endif
+constexpr int kTrackBwdL = 16, kTrackBwdNT = 256, kTrackBwdMinB = DMST_BWD_MINB;
 #elif DMST_TRACK_CFG == 2
 constexpr int kTrackFwdL = 16, kTrackFwdNT = 256;   // 4096-sample tiles
 constexpr int kTrackBwdL = 16, kTrackBwdNT = 256, kTrackBwdMinB = 2;
@@ -101,7 +104,7 @@ struct ConsoleWs {
     RowTab *track_tab, *track_tab_b, *master_tab;  // track_tab: forward L, track_tab_b: backward L
     float *y, *bus_pre, *dbus, *esave, *ssave;
     // forward chain (kept for backward)
-    int *t_flag, *m_flag;
+    int *t_flag, *m_flag, *t_done;
     Mail *t_state, *m_state;
     float *t_tail2, *m_tail2, *t_etail, *m_etail;
     // backward chain
@@ -133,6 +136,7 @@ inline ConsoleWs carve_console(void* base, int B, int N, int T, int la_t, int la
     w.flags_begin = (c.off + 255) & ~size_t(255);   // zeroed before every forward
     w.t_flag = c.take<int>(rt);
     w.m_flag = c.take<int>(rm);
+    w.t_done = c.take<int>((size_t)B * w.nt_track);
     w.t_state = c.take<Mail>(rt * kStateStride);
     w.m_state = c.take<Mail>(rm * kStateStride);
     w.flags_end = c.off;
@@ -173,9 +177,25 @@ inline unsigned master_chain_flags(unsigned f) {
     return c;
 }
 
-inline size_t fwd_smem_bytes(int nch, int tile, int la) {
-    // delay line (+ output staging for the track kernel)
-    return (size_t)(nch * (pidx(la + tile) + 1) + (nch == 1 ? pidx(tile) + 1 : 0)) * 4;
+inline size_t fwd_smem_bytes(int la_t, int la_m) {
+    // delay line(s) of either role + the prefetch buffer of a track tile
+    return (size_t)(fwd_ebuf_floats(kTrackTile, la_t, kMasterTile, la_m) + pidx4(kTrackTile)) * 4;
+}
+static_assert(kTrackTile % kMasterTile == 0 && kMasterNT == kTrackFwdNT, "forward kernel runs both roles in one CTA shape");
+
+// CTAs of a persistent kernel: as many as are co-resident on the device
+template <class Kernel>
+inline int persistent_ctas(Kernel kern, int threads, size_t smem) {
+#ifdef DMST_EMULATE
+    (void)kern; (void)threads; (void)smem;
+    return 2;
+#else
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess) return 0;
+    return sms * per_sm;
+#endif
 }
 inline size_t bwd_smem_bytes(int nch, int tile, int la, int nt) {
     return (size_t)(2 * nch * (pidx(la + tile) + 1) + 12 * nch * nt) * 4;
@@ -274,27 +294,28 @@ inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* 
     if (!k.master_params) { pm.kind = 3; pm.np = 0; }
     DMST_LAUNCH(prepare_kernel, dim3(pm.rows), dim3(256), 0, stream, pm);
 
-    ChainArgs at, am;
-    fill_chain(at, k, false, w);
-    at.want_mixed = (k.flags & DMST_WANT_MIXED_TRACKS) ? 1 : 0;
-    at.mixed = mixed;
-    at.user_vec_ok = mixed && aligned16(mixed) && (k.T % 4 == 0);
+    FwdArgs f;
+    memset(&f, 0, sizeof(f));
+    fill_chain(f.t, k, false, w);
+    f.t.want_mixed = (k.flags & DMST_WANT_MIXED_TRACKS) ? 1 : 0;
+    f.t.mixed = mixed;
+    f.t.user_vec_ok = mixed && aligned16(mixed) && (k.T % 4 == 0);
+    fill_chain(f.m, k, true, w);
+    f.m.mix = mix;
+    f.m.user_vec_ok = aligned16(mix) && (k.T % 4 == 0);
+    f.B = k.B; f.R = kTrackTile / kMasterTile;
+    f.group = k.B * f.R + k.B * k.N;
+    f.total = (w.nt_track + 1) * f.group;
+    f.ticket = w.header + 0; f.done = w.t_done;
     {
-        auto kern = chain_fwd_kernel<1, kTrackFwdL, kTrackFwdNT, false>;
-        const size_t smem = fwd_smem_bytes(1, kTrackTile, k.la_t);
+        auto kern = console_fwd_kernel<kTrackFwdL, kMasterL, kTrackFwdNT>;
+        const size_t smem = fwd_smem_bytes(k.la_t, k.la_m);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
+        int ctas = persistent_ctas(kern, kTrackFwdNT, smem);
+        if (ctas <= 0) return DMST_EINVAL;
+        if (ctas > f.total) ctas = f.total;
         ScopedTimer tm(0, stream);
-        DMST_LAUNCH(kern, dim3(at.nrows * at.ntiles), dim3(kTrackFwdNT), smem, stream, at);
-    }
-    fill_chain(am, k, true, w);
-    am.mix = mix;
-    am.user_vec_ok = aligned16(mix) && (k.T % 4 == 0);
-    {
-        auto kern = chain_fwd_kernel<2, kMasterL, kMasterNT, true>;
-        const size_t smem = fwd_smem_bytes(2, kMasterTile, k.la_m);
-        DMST_CHECK(DMST_SET_SMEM(kern, smem));
-        ScopedTimer tm(1, stream);
-        DMST_LAUNCH(kern, dim3(am.nrows * am.ntiles), dim3(kMasterNT), smem, stream, am);
+        DMST_LAUNCH(kern, dim3(ctas), dim3(kTrackFwdNT), smem, stream, f);
     }
     return DMST_LAST_ERROR();
 }
