@@ -4,8 +4,9 @@
 // decomposition of a chain into (row, time tile) work items.
 //
 // Work items are claimed through an atomic ticket in an order that interleaves both kinds:
-// group g holds the master tiles that cover track time-tile g-1 (for every batch item), then the
-// track tiles of time-tile g (for every track).  A work item only ever waits for items with a
+// group g holds the master tiles that cover track time-tile g-lag (for every batch item), then the
+// track tiles of time-tile g (for every track); the lag is chosen so that the track tiles a master
+// tile sums have normally finished by the time it is claimed.  A work item only ever waits for items with a
 // lower ticket (its predecessor tile in time; for a master tile also the N track tiles it sums),
 // so whatever a running CTA waits for is running or finished: no deadlock, no co-residency
 // assumption.  The master bus is chain-latency bound (few rows); interleaved like this its
@@ -28,7 +29,8 @@ struct FwdArgs {
     int B;            // batch items
     int R;            // master tiles per track tile
     int group;        // tickets per group = B*R + B*N
-    int total;        // (track tiles + 1) * group
+    int lag;          // the master tiles in group g cover track time-tile g - lag
+    int total;        // (track tiles + lag) * group
     int* ticket;
     int* done;        // [B * track tiles]: tracks of the item that finished the time tile
 };
@@ -40,10 +42,10 @@ __device__ __forceinline__ FwdWork fwd_decode(const FwdArgs& f, int ticket) {
     if (ticket >= f.total) return w;
     const int g = ticket / f.group, r = ticket - g * f.group;
     const int nm = f.B * f.R;
-    if (r < nm) {  // master tiles of track time-tile g-1, earlier tile first
+    if (r < nm) {  // master tiles of track time-tile g-lag, earlier tile first
         const int mi = r / f.B, b = r - mi * f.B;
-        const int mt = (g - 1) * f.R + mi;
-        if (g >= 1 && mt < f.m.ntiles) { w.role = 2; w.row = b; w.tile = mt; }
+        const int mt = (g - f.lag) * f.R + mi;
+        if (g >= f.lag && mt < f.m.ntiles) { w.role = 2; w.row = b; w.tile = mt; }
     } else if (g < f.t.ntiles) {
         w.role = 1; w.row = r - nm; w.tile = g;
     }

@@ -305,7 +305,6 @@ inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* 
     f.m.user_vec_ok = aligned16(mix) && (k.T % 4 == 0);
     f.B = k.B; f.R = kTrackTile / kMasterTile;
     f.group = k.B * f.R + k.B * k.N;
-    f.total = (w.nt_track + 1) * f.group;
     f.ticket = w.header + 0; f.done = w.t_done;
     {
         auto kern = console_fwd_kernel<kTrackFwdL, kMasterL, kTrackFwdNT>;
@@ -313,6 +312,12 @@ inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* 
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
         int ctas = persistent_ctas(kern, kTrackFwdNT, smem);
         if (ctas <= 0) return DMST_EINVAL;
+        // a master tile claimed `lag` groups after the track tiles it sums normally finds them finished
+        // (measured optimum on B200: one more group than the CTAs in flight span)
+        f.lag = (ctas + f.group - 1) / f.group;
+        if (f.lag < 1) f.lag = 1;
+        if (const char* e = getenv("DMST_FWD_LAG")) f.lag = atoi(e) > 0 ? atoi(e) : f.lag;  // tuning aid
+        f.total = (w.nt_track + f.lag) * f.group;
         if (ctas > f.total) ctas = f.total;
         ScopedTimer tm(0, stream);
         DMST_LAUNCH(kern, dim3(ctas), dim3(kTrackFwdNT), smem, stream, f);
