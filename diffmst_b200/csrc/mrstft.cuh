@@ -16,6 +16,48 @@ namespace dmst {
 constexpr int kMrBlock = 256;
 constexpr int kMrItemsPerBlock = 4096;  // spectrum elements per block
 
+// ---------------------------------------------------------------------------------
+// Framing with 128-bit accesses: thread g handles samples [4*i4, 4*i4+4) of frame f of one row.
+// grid: (ceil(frames*n/4 / 256), rows, 2 signals)
+// ---------------------------------------------------------------------------------
+struct Frame4Args {
+    const float* x[2];        // the two signals, rows x T each
+    long long row_stride[2];
+    int vec_ok[2];            // 16-byte aligned base and row stride % 4 == 0
+    float* out[2];            // rows x frames x n
+    int rows, T, n, hop, win, frames;
+    const float* window;      // win
+};
+__global__ void frame4_kernel(Frame4Args a) {
+    const int row = blockIdx.y, z = blockIdx.z;
+    const int nq = a.n >> 2;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.frames * nq) return;
+    const int f = g / nq, i = (g - f * nq) << 2;
+    // (kernel-parameter arrays are only ever indexed with constants: a dynamic index would force a local copy)
+    const float* x = (z ? a.x[1] : a.x[0]) + (long long)row * (z ? a.row_stride[1] : a.row_stride[0]);
+    float* o = (z ? a.out[1] : a.out[0]) + ((long long)row * a.frames + f) * a.n + i;
+    const bool vec_ok = (z ? a.vec_ok[1] : a.vec_ok[0]) != 0;
+    const int pad = a.n >> 1, wl = (a.n - a.win) >> 1;
+    const int t = f * a.hop + i - pad;
+    float4 xv, wv;
+    if (vec_ok && t >= 0 && t + 3 < a.T && (t & 3) == 0) {
+        xv = __ldg(reinterpret_cast<const float4*>(x + t));
+    } else {
+        xv.x = __ldg(x + reflect_index(t, a.T)); xv.y = __ldg(x + reflect_index(t + 1, a.T));
+        xv.z = __ldg(x + reflect_index(t + 2, a.T)); xv.w = __ldg(x + reflect_index(t + 3, a.T));
+    }
+    if (wl == 0) {
+        wv = __ldg(reinterpret_cast<const float4*>(a.window + i));
+    } else {
+        float w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const int wi = i + e - wl; w[e] = (wi >= 0 && wi < a.win) ? __ldg(a.window + wi) : 0.0f; }
+        wv = make_float4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<float4*>(o) = make_float4(xv.x * wv.x, xv.y * wv.y, xv.z * wv.z, xv.w * wv.w);
+}
+
 struct MrLossArgs {
     const float2* X;  // rows x frames x bins
     const float2* Y;
@@ -47,15 +89,26 @@ __global__ void mr_loss_kernel(MrLossArgs a) {
     const int begin = blockIdx.x * kMrItemsPerBlock;
     const int end = min(begin + kMrItemsPerBlock, a.per_row);
     float s_d2 = 0.f, s_y2 = 0.f, s_log = 0.f, s_lin = 0.f;
-    for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
-        const float2 x = a.X[base + i], y = a.Y[base + i];
-        const float px = fmaxf(fmaf(x.x, x.x, x.y * x.y), a.eps), py = fmaxf(fmaf(y.x, y.x, y.y * y.y), a.eps);
-        const float mx = sqrtf(px), my = sqrtf(py);
-        const float d = my - mx;
-        s_d2 = fmaf(d, d, s_d2);
-        s_y2 += py;
-        s_log += fabsf(0.5f * (logf(px) - logf(py)));
-        s_lin += fabsf(d);
+    constexpr int U = 4;  // independent loads in flight per thread
+    for (int i0 = begin + threadIdx.x; i0 < end; i0 += U * kMrBlock) {
+        float2 x[U], y[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kMrBlock;
+            if (i < end) { x[u] = __ldg(a.X + base + i); y[u] = __ldg(a.Y + base + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * kMrBlock >= end) continue;
+            const float px = fmaxf(fmaf(x[u].x, x[u].x, x[u].y * x[u].y), a.eps);
+            const float py = fmaxf(fmaf(y[u].x, y[u].x, y[u].y * y[u].y), a.eps);
+            const float mx = sqrtf(px), my = sqrtf(py);
+            const float d = my - mx;
+            s_d2 = fmaf(d, d, s_d2);
+            s_y2 += py;
+            s_log += fabsf(0.5f * (logf(px) - logf(py)));
+            s_lin += fabsf(d);
+        }
     }
     float* out = a.partial + ((long long)row * a.blocks_per_row + blockIdx.x) * 4;
     float r;
@@ -65,41 +118,44 @@ __global__ void mr_loss_kernel(MrLossArgs a) {
     r = block_sum(s_lin, sh); if (threadIdx.x == 0) out[3] = r;
 }
 
-// Second stage of the reductions: one block per row sums that row's block partials in float64
-// (fixed assignment of partials to threads + fixed-shape tree => deterministic).
-struct MrRowSumArgs { const float* partial; int blocks_per_row; double* rowsum; /* [rows][4] */ };
-__global__ void mr_rowsum_kernel(MrRowSumArgs a) {
-    DMST_SHARED_ARRAY(double, sh, 4 * 128);
-    const int row = blockIdx.x, tid = threadIdx.x;
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int b = tid; b < a.blocks_per_row; b += blockDim.x) {
-        const float4 p = *reinterpret_cast<const float4*>(a.partial + ((long long)row * a.blocks_per_row + b) * 4);
-        s[0] += p.x; s[1] += p.y; s[2] += p.z; s[3] += p.w;
-    }
-    for (int j = 0; j < 4; ++j) sh[j * 128 + tid] = s[j];
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-        if (tid < o)
-            for (int j = 0; j < 4; ++j) sh[j * 128 + tid] += sh[j * 128 + tid + o];
-        __syncthreads();
-    }
-    if (tid < 4) a.rowsum[row * 4 + tid] = sh[tid * 128];
-}
-
+// Second stage of the reductions and the loss terms of one resolution, one block: warp w sums the
+// block partials of rows w, w+nwarps, ... in float64 (fixed assignment of partials to lanes + fixed
+// shuffle tree => deterministic), then thread 0 forms the terms and the gradient coefficients.
 struct MrFinalArgs {
-    const double* rowsum;
+    const float* partial;
+    int blocks_per_row;
+    double* rowsum;     // [rows][4] scratch
     int rows, per_row;
     float w_sc, w_log, w_lin;
-    int n_res, res_index;
-    float* loss;        // [0] total (accumulated over resolutions), [1 + 3*r ...] sc, log, lin
+    int n_res;
+    float* res_loss;    // [4]: this resolution's contribution to the total, then its sc, log, lin terms
     float* row_coef;    // [rows]: d(total)/d|X| coefficient of (|X|-|Y|) for the SC term
     float* scal;        // [2]: coefficient of sign(log) / |X| and of sign(lin)
 };
-
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 __global__ void mr_final_kernel(MrFinalArgs a) {
-    if (threadIdx.x != 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int row = warp; row < a.rows; row += nwarps) {
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int b = lane; b < a.blocks_per_row; b += 32) {
+            const float4 p = __ldg(reinterpret_cast<const float4*>(a.partial + ((long long)row * a.blocks_per_row + b) * 4));
+            s[0] += p.x; s[1] += p.y; s[2] += p.z; s[3] += p.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s[j] = warp_sum_f64(s[j]);
+            if (lane == 0) a.rowsum[row * 4 + j] = s[j];
+        }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    // lanes over rows (fixed assignment), then a fixed shuffle tree: deterministic
     double sc = 0.0, slog = 0.0, slin = 0.0;
-    for (int row = 0; row < a.rows; ++row) {
+    for (int row = lane; row < a.rows; row += 32) {
         const double d2 = a.rowsum[row * 4 + 0], y2 = a.rowsum[row * 4 + 1];
         slog += a.rowsum[row * 4 + 2]; slin += a.rowsum[row * 4 + 3];
         const double num = sqrt(d2), den = sqrt(y2);
@@ -107,14 +163,13 @@ __global__ void mr_final_kernel(MrFinalArgs a) {
         // d/d|X| of w_sc * (1/rows) * ||Y|-|X||_F / ||Y||_F = w_sc/(rows) * (|X|-|Y|) / (num*den)
         a.row_coef[row] = (num > 0.0) ? (float)(a.w_sc / (a.rows * (double)a.n_res * num * den)) : 0.0f;
     }
+    sc = warp_sum_f64(sc); slog = warp_sum_f64(slog); slin = warp_sum_f64(slin);
+    if (lane != 0) return;
     const double cnt = (double)a.rows * (double)a.per_row;
     const double l_sc = sc / a.rows, l_log = slog / cnt, l_lin = slin / cnt;
     const double lr = a.w_sc * l_sc + a.w_log * l_log + a.w_lin * l_lin;
-    a.loss[1 + 3 * a.res_index + 0] = (float)l_sc;
-    a.loss[1 + 3 * a.res_index + 1] = (float)l_log;
-    a.loss[1 + 3 * a.res_index + 2] = (float)l_lin;
-    const float prev = (a.res_index == 0) ? 0.0f : a.loss[0];
-    a.loss[0] = prev + (float)(lr / a.n_res);
+    a.res_loss[0] = (float)(lr / a.n_res);
+    a.res_loss[1] = (float)l_sc; a.res_loss[2] = (float)l_log; a.res_loss[3] = (float)l_lin;
     a.scal[0] = (float)(a.w_log / (a.n_res * cnt));
     a.scal[1] = (float)(a.w_lin / (a.n_res * cnt));
 }
@@ -129,75 +184,190 @@ struct MrGradArgs {
     int use_log, use_lin;
 };
 
-// grid: (ceil(per_row/256), rows)
+// grid: (ceil(per_row/(256*U)), rows)
+constexpr int kMrGradU = 4;
 __global__ void mr_grad_kernel(MrGradArgs a) {
     const int row = blockIdx.y;
     const int per_row = a.frames * a.bins;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= per_row) return;
-    const long long idx = (long long)row * per_row + i;
-    const int bin = i % a.bins;
-    const float2 x = a.X[idx], y = a.Y[idx];
-    const float px_raw = fmaf(x.x, x.x, x.y * x.y);
-    float2 z = make_float2(0.0f, 0.0f);
-    if (px_raw >= a.eps) {  // clamp passes gradient only where it is inactive
-        const float py = fmaxf(fmaf(y.x, y.x, y.y * y.y), a.eps);
-        const float mx = sqrtf(px_raw), my = sqrtf(py);
-        float g = a.row_coef[row] * (mx - my);
-        if (a.use_log) {
-            const float dl = logf(px_raw) - logf(py);
-            g += a.scal[0] * ((dl > 0.0f) - (dl < 0.0f)) / mx;
-        }
-        if (a.use_lin) g += a.scal[1] * ((mx > my) - (mx < my));
-        const float s = g / mx;
-        z.x = s * x.x; z.y = s * x.y;
+    const long long base = (long long)row * per_row;
+    const int i0 = blockIdx.x * (kMrBlock * kMrGradU) + threadIdx.x;
+    const float rc = __ldg(a.row_coef + row), c_log = __ldg(a.scal), c_lin = __ldg(a.scal + 1);
+    float2 x[kMrGradU], y[kMrGradU];
+#pragma unroll
+    for (int u = 0; u < kMrGradU; ++u) {
+        const int i = i0 + u * kMrBlock;
+        if (i < per_row) { x[u] = a.X[base + i]; y[u] = __ldg(a.Y + base + i); }
     }
-    // adjoint of the onesided real FFT expressed through an unnormalised C2R transform:
-    // DC and Nyquist keep their real part, interior bins are halved
-    if (bin == 0 || bin == a.bins - 1) z.y = 0.0f;
-    else { z.x *= 0.5f; z.y *= 0.5f; }
-    a.X[idx] = z;
+#pragma unroll
+    for (int u = 0; u < kMrGradU; ++u) {
+        const int i = i0 + u * kMrBlock;
+        if (i >= per_row) continue;
+        const int bin = i % a.bins;
+        const float px_raw = fmaf(x[u].x, x[u].x, x[u].y * x[u].y);
+        float2 z = make_float2(0.0f, 0.0f);
+        if (px_raw >= a.eps) {  // clamp passes gradient only where it is inactive
+            const float py = fmaxf(fmaf(y[u].x, y[u].x, y[u].y * y[u].y), a.eps);
+            const float mx = sqrtf(px_raw), my = sqrtf(py);
+            float g = rc * (mx - my);
+            if (a.use_log) {
+                const float dl = logf(px_raw) - logf(py);
+                g += c_log * ((dl > 0.0f) - (dl < 0.0f)) / mx;
+            }
+            if (a.use_lin) g += c_lin * ((mx > my) - (mx < my));
+            const float s = g / mx;
+            z.x = s * x[u].x; z.y = s * x[u].y;
+        }
+        // adjoint of the onesided real FFT expressed through an unnormalised C2R transform:
+        // DC and Nyquist keep their real part, interior bins are halved
+        if (bin == 0 || bin == a.bins - 1) z.y = 0.0f;
+        else { z.x *= 0.5f; z.y *= 0.5f; }
+        a.X[base + i] = z;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Overlap-add adjoint of all resolutions in one pass over the gradient (written once), plus the
+// total loss.  Gather form, fixed order => deterministic.  grid: (ceil(T/4 / 256), rows)
+// ---------------------------------------------------------------------------------
+struct OlaMultiArgs {
+    int n_res, rows, T;
+    const float* dframes[DMST_MRSTFT_MAX_RES];   // rows x frames x n
+    const float* window[DMST_MRSTFT_MAX_RES];
+    int n[DMST_MRSTFT_MAX_RES], hop[DMST_MRSTFT_MAX_RES], win[DMST_MRSTFT_MAX_RES], frames[DMST_MRSTFT_MAX_RES];
+    float* gx;                 // rows x T (contiguous), or null
+    int gx_vec_ok;
+    const float* res_loss;     // [n_res][4]
+    float* loss;               // [0] total, [1 + 3*r ...] sc, log, lin
+};
+__global__ void ola_multi_kernel(OlaMultiArgs a) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        float tot = 0.0f;
+        for (int r = 0; r < a.n_res; ++r) {
+            tot += a.res_loss[4 * r];
+            a.loss[1 + 3 * r + 0] = a.res_loss[4 * r + 1];
+            a.loss[1 + 3 * r + 1] = a.res_loss[4 * r + 2];
+            a.loss[1 + 3 * r + 2] = a.res_loss[4 * r + 3];
+        }
+        a.loss[0] = tot;
+    }
+    if (!a.gx) return;
+    const int row = blockIdx.y;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) << 2;
+    if (t >= a.T) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < DMST_MRSTFT_MAX_RES; ++r) {  // fully unrolled: kernel-parameter arrays indexed with constants
+        if (r >= a.n_res) break;
+        const int n = a.n[r], hop = a.hop[r], pad = n >> 1, frames = a.frames[r];
+        const float* df = a.dframes[r] + (long long)row * frames * n;
+        OlaArgs oa{df, a.rows, a.T, n, hop, a.win[r], frames, a.window[r], nullptr, 0, 1.0f};
+        const bool fast = (a.win[r] == n) && ((hop & 3) == 0) && ((n & 7) == 0) && (t + 3 < a.T);
+        if (fast) {
+            const int j = t + pad;  // padded position of the first of the 4 samples (multiple of 4)
+            int f_hi = j / hop;
+            if (f_hi > frames - 1) f_hi = frames - 1;
+            int f_lo = (j + 3 - n + hop) / hop;
+            if (j + 3 - n + 1 <= 0) f_lo = 0;
+            for (int f = f_lo; f <= f_hi; ++f) {
+                const int i = j - f * hop;  // multiple of 4; the 4 samples lie in [0, n) by the choice of f_lo, f_hi
+                if (i < 0 || i + 3 >= n) {  // frame covers only part of the quad (cannot happen when 4 | hop, kept for safety)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int ie = i + e;
+                        if (ie >= 0 && ie < n) acc[e] = fmaf(__ldg(df + (long long)f * n + ie), __ldg(a.window[r] + ie), acc[e]);
+                    }
+                    continue;
+                }
+                const float4 d = __ldg(reinterpret_cast<const float4*>(df + (long long)f * n + i));
+                const float4 w = __ldg(reinterpret_cast<const float4*>(a.window[r] + i));
+                acc[0] = fmaf(d.x, w.x, acc[0]); acc[1] = fmaf(d.y, w.y, acc[1]);
+                acc[2] = fmaf(d.z, w.z, acc[2]); acc[3] = fmaf(d.w, w.w, acc[3]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (t + e < a.T) acc[e] += ola_at(oa, df, t + e + pad);
+        }
+        // reflected padding folds back onto the first / last `pad` samples
+        if (t <= pad || t + 3 >= a.T - 1 - pad) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int te = t + e;
+                if (te >= 1 && te <= pad && te < a.T) acc[e] += ola_at(oa, df, pad - te);
+                const int jr = pad + 2 * a.T - 2 - te;
+                if (te <= a.T - 2 && jr >= pad + a.T && jr < a.T + 2 * pad) acc[e] += ola_at(oa, df, jr);
+            }
+        }
+    }
+    float* g = a.gx + (long long)row * a.T + t;
+    if (a.gx_vec_ok && t + 3 < a.T) {
+        *reinterpret_cast<float4*>(g) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (t + e < a.T) g[e] = acc[e];
+    }
 }
 
 #ifndef DMST_EMULATE
-struct MrWs {
+// Per-resolution slice of the workspace: the resolutions run concurrently on side streams
+struct MrResWs {
     float* frames;    // 2*rows*frames*n
     float2* spec;     // 2*rows*frames*bins
     float* partial; double* rowsum; float* row_coef; float* scal; void* fft_work;
+};
+struct MrWs {
+    MrResWs res[DMST_MRSTFT_MAX_RES];
+    float* res_loss;  // [n_res][4]
     size_t total;
 };
-inline int mr_max_dims(const dmst_mrstft_cfg* c, int rows, int T, size_t* fr, size_t* sp, size_t* part, size_t* work) {
-    *fr = *sp = *part = *work = 0;
-    for (int r = 0; r < c->n_res; ++r) {
-        const int n = c->fft_size[r], hop = c->hop_size[r], win = c->win_length[r];
-        if (n <= 0 || hop <= 0 || win <= 0 || win > n || (n & 1) || n / 2 >= T) return DMST_EINVAL;
-        const size_t frames = 1 + T / hop, bins = n / 2 + 1;
-        *fr = max(*fr, (size_t)2 * rows * frames * n);
-        *sp = max(*sp, (size_t)2 * rows * frames * bins);
-        const size_t bpr = (frames * bins + kMrItemsPerBlock - 1) / kMrItemsPerBlock;
-        *part = max(*part, (size_t)rows * bpr * 4);
-        const size_t w1 = plan_work_bytes(n, 2 * rows * (int)frames), w2 = plan_work_bytes(n, rows * (int)frames);
-        if (w1 == (size_t)-1 || w2 == (size_t)-1) return 1002;
-        *work = max(*work, max(w1, w2));
-    }
-    return 0;
-}
 inline int mr_carve(void* base, const dmst_mrstft_cfg* c, int rows, int T, MrWs* w) {
-    size_t fr, sp, part, work;
-    int e = mr_max_dims(c, rows, T, &fr, &sp, &part, &work);
-    if (e) return e;
     unsigned char* b = reinterpret_cast<unsigned char*>(base);
     size_t off = 0;
     auto take = [&](size_t bytes) { off = (off + 255) & ~size_t(255); void* p = b ? b + off : nullptr; off += bytes; return p; };
-    w->frames = (float*)take(fr * 4);
-    w->spec = (float2*)take(sp * 8);
-    w->partial = (float*)take(part * 4);
-    w->rowsum = (double*)take((size_t)rows * 4 * 8);
-    w->row_coef = (float*)take((size_t)rows * 4);
-    w->scal = (float*)take(16);
-    w->fft_work = take(work);
+    w->res_loss = (float*)take(sizeof(float) * 4 * DMST_MRSTFT_MAX_RES);
+    for (int r = 0; r < c->n_res; ++r) {
+        const int n = c->fft_size[r], hop = c->hop_size[r], win = c->win_length[r];
+        if (n <= 0 || hop <= 0 || win <= 0 || win > n || (n & 7) || n / 2 >= T) return DMST_EINVAL;
+        const size_t frames = 1 + T / hop, bins = n / 2 + 1;
+        const size_t bpr = (frames * bins + kMrItemsPerBlock - 1) / kMrItemsPerBlock;
+        const size_t w1 = plan_work_bytes(n, 2 * rows * (int)frames), w2 = plan_work_bytes(n, rows * (int)frames);
+        if (w1 == (size_t)-1 || w2 == (size_t)-1) return 1002;
+        MrResWs& s = w->res[r];
+        s.frames = (float*)take((size_t)2 * rows * frames * n * 4);
+        s.spec = (float2*)take((size_t)2 * rows * frames * bins * 8);
+        s.partial = (float*)take((size_t)rows * bpr * 4 * 4);
+        s.rowsum = (double*)take((size_t)rows * 4 * 8);
+        s.row_coef = (float*)take((size_t)rows * 4);
+        s.scal = (float*)take(16);
+        s.fft_work = take(max(w1, w2));
+    }
     w->total = (off + 255) & ~size_t(255);
     return 0;
+}
+
+// Side streams / events for the fork-join over resolutions (created once per device)
+struct MrStreams {
+    cudaStream_t side[DMST_MRSTFT_MAX_RES];
+    cudaEvent_t start, done[DMST_MRSTFT_MAX_RES];
+    bool ok = false;
+};
+inline MrStreams* mr_streams() {
+    static std::mutex mu;
+    static std::map<int, MrStreams> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    MrStreams& s = cache[dev];
+    if (!s.ok) {
+        if (cudaEventCreateWithFlags(&s.start, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int r = 0; r < DMST_MRSTFT_MAX_RES; ++r) {
+            if (cudaStreamCreateWithFlags(&s.side[r], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&s.done[r], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        s.ok = true;
+    }
+    return &s;
 }
 
 inline int mrstft_run(const float* x, long long xs, const float* y, long long ys, const float* windows,
@@ -209,38 +379,60 @@ inline int mrstft_run(const float* x, long long xs, const float* y, long long ys
     int e = mr_carve(ws, c, rows, T, &w);
     if (e) return e;
     if (ws_bytes < w.total) return DMST_EINVAL;
+    MrStreams* st = mr_streams();
+    if (!st) return (int)cudaGetLastError();
+    static const bool serial = getenv("DMST_MRSTFT_SERIAL") && getenv("DMST_MRSTFT_SERIAL")[0] == '1';  // tuning aid
+    // fork: resolution 0 stays on the caller's stream, the others run on side streams
+    if (c->n_res > 1 && !serial && cudaEventRecord(st->start, stream) != cudaSuccess) return (int)cudaGetLastError();
+    OlaMultiArgs oa;
+    memset(&oa, 0, sizeof(oa));
     const float* win = windows;
     for (int r = 0; r < c->n_res; ++r) {
+        cudaStream_t s = (r == 0 || serial) ? stream : st->side[r];
+        if (r > 0 && !serial && cudaStreamWaitEvent(s, st->start, 0) != cudaSuccess) return (int)cudaGetLastError();
         const int n = c->fft_size[r], hop = c->hop_size[r], wl = c->win_length[r];
         const int frames = 1 + T / hop, bins = n / 2 + 1;
         const int per_row = frames * bins;
-        float* fx = w.frames;
-        float* fy = w.frames + (size_t)rows * frames * n;
-        FrameArgs fa{x, xs, rows, T, n, hop, wl, frames, win, fx, y, ys, fy};
-        frame_kernel<<<dim3(frames, rows, 2), 256, 0, stream>>>(fa);
-        e = exec_r2c(n, 2 * rows * frames, w.frames, w.spec, w.fft_work, stream);
+        MrResWs& q = w.res[r];
+        float* fx = q.frames;
+        float* fy = q.frames + (size_t)rows * frames * n;
+        Frame4Args fa;
+        fa.x[0] = x; fa.x[1] = y; fa.row_stride[0] = xs; fa.row_stride[1] = ys;
+        fa.vec_ok[0] = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (xs % 4 == 0) && (hop % 4 == 0);
+        fa.vec_ok[1] = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && (ys % 4 == 0) && (hop % 4 == 0);
+        fa.out[0] = fx; fa.out[1] = fy;
+        fa.rows = rows; fa.T = T; fa.n = n; fa.hop = hop; fa.win = wl; fa.frames = frames; fa.window = win;
+        frame4_kernel<<<dim3((frames * (n / 4) + 255) / 256, rows, 2), 256, 0, s>>>(fa);
+        e = exec_r2c(n, 2 * rows * frames, q.frames, q.spec, q.fft_work, s);
         if (e) return e;
-        float2* X = w.spec;
-        float2* Y = w.spec + (size_t)rows * per_row;
+        float2* X = q.spec;
+        float2* Y = q.spec + (size_t)rows * per_row;
         const int bpr = (per_row + kMrItemsPerBlock - 1) / kMrItemsPerBlock;
-        MrLossArgs la{X, Y, rows, per_row, bpr, c->eps, w.partial};
-        mr_loss_kernel<<<dim3(bpr, rows), kMrBlock, 0, stream>>>(la);
-        MrRowSumArgs rs{w.partial, bpr, w.rowsum};
-        mr_rowsum_kernel<<<rows, 128, 0, stream>>>(rs);
-        MrFinalArgs fa2{w.rowsum, rows, per_row, c->w_sc, c->w_log_mag, c->w_lin_mag, c->n_res, r,
-                        loss, w.row_coef, w.scal};
-        mr_final_kernel<<<1, 32, 0, stream>>>(fa2);
+        MrLossArgs la{X, Y, rows, per_row, bpr, c->eps, q.partial};
+        mr_loss_kernel<<<dim3(bpr, rows), kMrBlock, 0, s>>>(la);
+        MrFinalArgs fa2{q.partial, bpr, q.rowsum, rows, per_row, c->w_sc, c->w_log_mag, c->w_lin_mag, c->n_res,
+                        w.res_loss + 4 * r, q.row_coef, q.scal};
+        mr_final_kernel<<<1, 512, 0, s>>>(fa2);
         if (grad_x) {
-            MrGradArgs ga{X, Y, rows, frames, bins, c->eps, w.row_coef, w.scal, c->w_log_mag != 0.0f,
+            MrGradArgs ga{X, Y, rows, frames, bins, c->eps, q.row_coef, q.scal, c->w_log_mag != 0.0f,
                           c->w_lin_mag != 0.0f};
-            mr_grad_kernel<<<dim3((per_row + 255) / 256, rows), 256, 0, stream>>>(ga);
-            e = exec_c2r(n, rows * frames, X, fx, w.fft_work, stream);
+            mr_grad_kernel<<<dim3((per_row + kMrBlock * kMrGradU - 1) / (kMrBlock * kMrGradU), rows), kMrBlock, 0, s>>>(ga);
+            e = exec_c2r(n, rows * frames, X, fx, q.fft_work, s);
             if (e) return e;
-            OlaArgs oa{fx, rows, T, n, hop, wl, frames, win, grad_x, r > 0 ? 1 : 0, 1.0f};
-            ola_kernel<<<dim3((T + 255) / 256, rows), 256, 0, stream>>>(oa);
+        }
+        oa.dframes[r] = fx; oa.window[r] = win; oa.n[r] = n; oa.hop[r] = hop; oa.win[r] = wl; oa.frames[r] = frames;
+        if (r > 0 && !serial) {
+            if (cudaEventRecord(st->done[r], s) != cudaSuccess) return (int)cudaGetLastError();
+            if (cudaStreamWaitEvent(stream, st->done[r], 0) != cudaSuccess) return (int)cudaGetLastError();
         }
         win += wl;
     }
+    // join: overlap-add of every resolution's frame gradients + the total loss, one pass
+    oa.n_res = c->n_res; oa.rows = rows; oa.T = T;
+    oa.gx = grad_x; oa.gx_vec_ok = grad_x && ((reinterpret_cast<uintptr_t>(grad_x) & 15) == 0) && (T % 4 == 0);
+    oa.res_loss = w.res_loss; oa.loss = loss;
+    const dim3 grid(grad_x ? ((T + 3) / 4 + 255) / 256 : 1, grad_x ? rows : 1);
+    ola_multi_kernel<<<grid, 256, 0, stream>>>(oa);
     return (int)cudaGetLastError();
 }
 #endif

@@ -29,3 +29,7 @@ print("mixed rel-max", rel(mixed, omixed.detach()))
 def rl2(a, b):
     a = torch.as_tensor(a).double(); return float((a - b).norm() / b.norm())
 print("gtp rel-l2", rl2(gtp, tpd.grad), "gmp rel-l2", rl2(gmp, mpd.grad), "gtracks rel-l2", rl2(gtr, trd.grad))
+if "-v" in sys.argv:
+    np.set_printoptions(precision=3, linewidth=200)
+    print("gmp ours  ", np.asarray(gmp)[0]); print("gmp oracle", mpd.grad.numpy()[0])
+    print("gtp ours  ", np.asarray(gtp)[0, 0]); print("gtp oracle", tpd.grad.numpy()[0, 0])
