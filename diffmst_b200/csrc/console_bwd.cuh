@@ -1,5 +1,11 @@
-// Backward chain kernel (adjoint of console_fwd.cuh), one CTA per (row, time tile), tiles
-// claimed in REVERSE time order.  Per tile it
+// Backward pass of one chain kind of the mix console (adjoint of console_fwd.cuh): a persistent
+// kernel whose CTAs claim (row, time tile) work items through an atomic ticket in REVERSE time
+// order (so the successor tile of any running item is running or finished: no deadlock), and
+// prefetch the next item's inputs (row table, EQ-output checkpoint, look-ahead halo, upstream
+// gradient) into shared memory with cp.async while the current one is processed.  Launched once
+// for the master bus (NCH = 2; produces the bus gradient) and once for the tracks (NCH = 1).
+//
+// Per tile the kernel
 //   1. recomputes the forward chain from the tile carry-in states the forward pass left in
 //      the workspace (no forward chaining needed),
 //   2. runs the adjoint of the compressor (reverse one-pole recursion for the smoothed
@@ -16,47 +22,143 @@
 // Gradient definitions follow the float64 autograd of the oracle (tests/golden).
 #pragma once
 #include "chain.cuh"
+#include "console_fwd.cuh"   // lds_chunk / sts_chunk
 
 namespace dmst {
 
 constexpr int kBFlagComp = 1;  // reverse smoother state + dhead halo published (section states use mailboxes)
 
-template <int NCH, int L, int NT, bool MASTER, int MINB>
-__global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
+struct BwdArgs {
+    ChainArgs a;
+    int total;        // rows * tiles
+    int area;         // floats of the per-tile buffer area in dynamic shared memory (sE follows it)
+    int* ticket;
+};
+
+// `count` (multiple of 4) consecutive floats of a global row -> shared memory (pidx4 layout), zero
+// beyond `valid`; 16-byte copies when the source allows it
+template <int NT>
+__device__ __forceinline__ void cp_tile(float* dst, const float* src, int count, int valid, bool vec_ok, int tid) {
+    for (int q = tid; q < (count >> 2); q += NT) {
+        const int idx = q << 2;
+        float* d = dst + pidx4(idx);
+        if (vec_ok && valid - idx >= 4) {
+            cp_async16(d, src + idx);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (idx + e < valid) cp_async4(d + e, src + idx + e);
+                else d[e] = 0.0f;
+            }
+        }
+    }
+}
+
+template <int NT, int NCH>
+struct BwdShared {
+    float W[8 * (NT / 32) * NCH * 2];     // warp aggregates, slot 7 = reverse smoother
+    float nb[3 * (NT / 32) * NCH * 2];    // last two samples of each warp: [section parity 0/1, chain output]
+    float pre[kStateStride];              // successor's reverse states (prefetched)
+    float fst[kStateStride];              // predecessor's forward end states (saved by forward)
+    unsigned premask[2];                  // [0] published mailboxes at tile start, [1] successor flag
+    float part[(NT / 32) * kGradCount];
+    int next;                             // next ticket of this CTA
+};
+
+// Sum four values over the warp with 6 shuffles: the two halves (then quarters) of the warp exchange
+// the values they do not keep.  Afterwards lanes with (lane & 7) == 0 hold the totals: lane 0 -> a0,
+// lane 16 -> a1, lane 8 -> a2, lane 24 -> a3 (fixed tree => deterministic).
+__device__ __forceinline__ float warp_sum4(float a0, float a1, float a2, float a3, int lane) {
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+    float p = h16 ? a1 : a0, ps = h16 ? a0 : a1;
+    float q = h16 ? a3 : a2, qs = h16 ? a2 : a3;
+    p += __shfl_xor_sync(0xffffffffu, ps, 16);
+    q += __shfl_xor_sync(0xffffffffu, qs, 16);
+    float r = h8 ? q : p, rs = h8 ? p : q;
+    r += __shfl_xor_sync(0xffffffffu, rs, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+__device__ __forceinline__ int warp_sum4_slot(int lane) { return ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1); }
+
+// Start the asynchronous copies of the inputs of work item `ticket` into the (free) buffer area.
+template <int NCH, int L, int NT, bool MASTER>
+__device__ __forceinline__ void bwd_prefetch(const BwdArgs& f, int ticket, float* area, float* tabbuf, int tid) {
+    constexpr int TILE = NT * L;
+    if (ticket < f.total) {
+        const ChainArgs& a = f.a;
+        const int tile = a.ntiles - 1 - ticket / a.nrows;
+        const int row = ticket % a.nrows;
+        const float* tsrc = reinterpret_cast<const float*>(a.tab + row);
+        for (int i = tid; i < int(sizeof(RowTab) / 16); i += NT) cp_async16(tabbuf + 4 * i, tsrc + 4 * i);
+        const int LA = a.lookahead;
+        const int es = pidx4(LA + TILE), gs = pidx4(TILE);
+        const int tbase = tile * TILE;
+        const bool saved = (a.esave != nullptr) && (a.flags & kChainEq);
+        const long long rt = (long long)row * a.ntiles + tile;
+        const int bb = MASTER ? row : row / a.N;
+        float* gbuf = area + 2 * NCH * es;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            float* e = area + c * es;
+            // chain input of the tile (EQ-output checkpoint when forward left one)
+            if (saved || MASTER) {
+                const float* src = (saved ? a.esave : a.src) + (long long)(row * NCH + c) * a.Tp + tbase;
+                cp_tile<NT>(e + pidx4(LA), src, TILE, a.Tp - tbase, true, tid);
+            } else {
+                const int n = row - bb * a.N;
+                const float* src = a.src + (long long)bb * a.src_batch_stride + (long long)n * a.src_row_stride + tbase;
+                cp_tile<NT>(e + pidx4(LA), src, TILE, a.T - tbase, a.src_vec_ok != 0, tid);
+            }
+            // look-ahead halo: predecessor's last LA EQ outputs (zeros before the start of the signal)
+            if (a.flags & kChainComp)
+                cp_tile<NT>(e, a.etail + (rt - 1) * NCH * LA + c * LA, LA, tile > 0 ? LA : 0, true, tid);
+        }
+        // upstream gradient (zero beyond the end of the signal): master: caller's grad_mix (B,2,T);
+        // tracks: bus gradient (B*2,Tp) written by the master launch
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const long long len = MASTER ? a.T : a.Tp;
+            cp_tile<NT>(gbuf + c * gs, a.gout + (long long)(bb * 2 + c) * len + tbase, TILE, a.T - tbase,
+                        MASTER ? (a.user_vec_ok != 0) : true, tid);
+        }
+    }
+    cp_async_commit();
+}
+
+// One (row, tile) of a chain.  Returns the next ticket of this CTA (claimed on the way, inputs prefetched).
+template <int NCH, int L, int NT, bool MASTER>
+__device__ __forceinline__ int bwd_tile(const BwdArgs& f, const int row, const int tile, float* area,
+                                        const RowTab& tb, float* tab_next, BwdShared<NT, NCH>& sh) {
     constexpr int NW = NT / 32;
     constexpr int TILE = NT * L;
-    static_assert(L % 4 == 0 && L <= kMaxL, "chunk length");
-
-    DMST_DYN_SMEM(smem_raw);
-    DMST_SHARED_ARRAY(float, s_W, 8 * NW * NCH * 2);       // warp aggregates, slot 7 = reverse smoother
-    DMST_SHARED_ARRAY(float, s_nb, 3 * NW * NCH * 2);       // last two samples of each warp: [section parity 0/1, chain output]
-    DMST_SHARED_ARRAY(float, s_pre, kStateStride);   // successor's reverse states (prefetched)
-    DMST_SHARED_ARRAY(float, s_fst, kStateStride);   // predecessor's forward end states (saved by forward)
-    DMST_SHARED_ARRAY(unsigned, s_premask, 2);       // [0] published mailboxes at tile start, [1] successor flag
-    DMST_SHARED_ARRAY(float, s_part, NW * kGradCount);
-    DMST_SHARED_ARRAY(int, s_ticket, 1);
-    DMST_SHARED_ARRAY(float, s_tabf, sizeof(RowTab) / 4);
-    const RowTab& tb = *reinterpret_cast<const RowTab*>(s_tabf);
+    static_assert(L % 4 == 0 && L <= kMaxL && 32 % L == 0, "chunk length");
+    const ChainArgs& a = f.a;
+    float* s_W = sh.W;
+    float* s_nb = sh.nb;
+    float* s_pre = sh.pre;
+    float* s_fst = sh.fst;
+    unsigned* s_premask = sh.premask;
+    float* s_part = sh.part;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_ticket[0] = atomicAdd(a.ticket, 1);
-    __syncthreads();
-    const int ticket = s_ticket[0];
-    const int tile = a.ntiles - 1 - ticket / a.nrows;
-    const int row = ticket % a.nrows;
     const int LA = a.lookahead;
-    const int buf_stride = pidx(LA + TILE) + 1;
-    // LA % 32 == 0 and L | 32 (checked on the host): pidx(LA + tid*L + i) = pLA + pb + i
-    const int pLA = pidx(LA), pb = pidx(tid * L);
-    float* ebuf = reinterpret_cast<float*>(smem_raw);          // [NCH][buf_stride]  e delay line
+    const int buf_stride = pidx4(LA + TILE);
+    const int gbuf_stride = pidx4(TILE);
+    // LA % 32 == 0 and L | 32 (checked on the host): pidx4(LA + tid*L + i) = pLA + pb + i
+    const int pLA = pidx4(LA), pb = pidx4(tid * L);
+    float* ebuf = area;                                         // [NCH][buf_stride]  e delay line
     float* dbuf = ebuf + NCH * buf_stride;                      // [NCH][buf_stride]  dy*G, future halo
-    float* sE = dbuf + NCH * buf_stride;                        // [6*NCH*2][NT] forward lane carry-ins
+    float* gbuf = dbuf + NCH * buf_stride;                      // [2][gbuf_stride]   upstream gradient
+    float* sE = area + f.area;                                  // [6*NCH*2][NT] forward lane carry-ins (no checkpoints)
 
-    {
-        const float* src = reinterpret_cast<const float*>(a.tab + row);
-        for (int i = tid; i < int(sizeof(RowTab) / 4); i += NT) s_tabf[i] = __ldg(src + i);
-        for (int i = tid; i < NW * kGradCount; i += NT) s_part[i] = 0.0f;
-    }
+    // Claim the next work item now; the ticket stays in a register until it is handed to the other
+    // threads at the barrier that frees the buffer area (never waits for the atomic's latency).
+    int claimed = 0;
+    if (tid == 0) claimed = atomicAdd(f.ticket, 1);
+    for (int i = tid; i < NW * kGradCount; i += NT) s_part[i] = 0.0f;
     const int t0 = tile * TILE + tid * L;
     const bool has_pred = tile > 0, has_succ = tile < a.ntiles - 1;
     const long long rt = (long long)row * a.ntiles + tile;
@@ -85,20 +187,10 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
     const bool saved = (a.esave != nullptr) && (a.flags & kChainEq);
     static_assert(MASTER || L == kBwdChunk, "state checkpoints are spaced by the backward chunk length");
     const float* ssave = a.ssave ? a.ssave + rt * (kNumSections * NCH * 2) * NT : nullptr;
+    (void)uvec;
     float v[NCH][L];
-    if (saved) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
-            load_chunk<L>(a.esave + (long long)(row * NCH + c) * a.Tp + t0, a.Tp - t0, true, v[c]);
-    } else if constexpr (!MASTER) {
-        load_chunk<L>(a.src + (long long)bb * a.src_batch_stride + (long long)nn * a.src_row_stride + t0,
-                      a.T - t0, a.src_vec_ok != 0, v[0]);
-    } else {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-            load_chunk<L>(a.src + (long long)(row * NCH + c) * a.Tp + t0, a.Tp - t0, true, v[c]);
-    }
-    __syncthreads();
+    for (int c = 0; c < NCH; ++c) lds_chunk<L>(ebuf + c * buf_stride + pLA + pb, v[c]);  // prefetched; landed before the caller's barrier
     if (!saved && (a.flags & kChainGain)) {
         const float g = tb.g_in;
 #pragma unroll
@@ -106,6 +198,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
 #pragma unroll
             for (int i = 0; i < L; ++i) v[c][i] *= g;
     }
+    __syncthreads();  // prefetched states and zeroed partial sums visible
 
     // ---------------- forward recompute of the EQ cascade ----------------
     if ((a.flags & kChainEq) && !saved) {
@@ -170,74 +263,49 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
 
     float u[NCH][L];
     float acc_gout = 0.0f, acc_gl = 0.0f, acc_gr = 0.0f;
-    float acc_comp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // alpha, thr, ratio, knee, makeup
+    float acc_alpha = 0.0f, acc_thr = 0.0f, acc_ratio = 0.0f, acc_knee = 0.0f, acc_makeup = 0.0f;
 
-    // Pass over the chunk that forms, per sample, the gradient w.r.t. the compressor output
-    // (tracks: gL*dbusL + gR*dbusR [+ grad of mixed_tracks]; master: g_out * dmix) and hands it
-    // with the compressor output `o` (or the EQ output when the compressor is off) to `fn`.
-    auto for_each_upstream = [&](auto&& out_of, auto&& fn) {
+    // Upstream gradient of samples [i0, i0+4) of the chunk w.r.t. the chain output (tracks: gL*dbusL +
+    // gR*dbusR [+ grad of mixed_tracks]; master: g_out * dmix), given the chain output `o` of those
+    // samples; accumulates the gain gradients on the way.  (The prefetch zero-fills beyond the signal.)
+    auto upstream4 = [&](int i0, const float (&o)[NCH][4], float (&dc)[NCH][4]) {
+        if constexpr (MASTER) {
 #pragma unroll
-        for (int i0 = 0; i0 < L; i0 += 4) {
-            float d[NCH][4];
-            float bl[4] = {0.f, 0.f, 0.f, 0.f}, br[4] = {0.f, 0.f, 0.f, 0.f};
-            if constexpr (MASTER) {
+            for (int c = 0; c < NCH; ++c) {
+                const float4 g4 = *reinterpret_cast<const float4*>(gbuf + c * gbuf_stride + pb + i0);
+                const float gq[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    const float4 g4 = load4(a.gout + (long long)(row * NCH + c) * a.T + t0 + i0, a.T - t0 - i0, uvec);
-                    d[c][0] = g4.x; d[c][1] = g4.y; d[c][2] = g4.z; d[c][3] = g4.w;
+                for (int j = 0; j < 4; ++j) {
+                    float g = gq[j];
+                    if (a.flags & kChainOutGain) { acc_gout = fmaf(g, o[c][j] * tb.g_out, acc_gout); g *= tb.g_out; }
+                    dc[c][j] = g;
                 }
-            } else {
-                const float4 l4 = load4(a.gout + (long long)(bb * 2 + 0) * a.Tp + t0 + i0, a.Tp - t0 - i0, true);
-                const float4 r4 = load4(a.gout + (long long)(bb * 2 + 1) * a.Tp + t0 + i0, a.Tp - t0 - i0, true);
-                bl[0] = l4.x; bl[1] = l4.y; bl[2] = l4.z; bl[3] = l4.w;
-                br[0] = r4.x; br[1] = r4.y; br[2] = r4.z; br[3] = r4.w;
-                if (a.gmixed) {
-                    const float4 ml = load4(a.gmixed + ((long long)(bb * 2 + 0) * a.N + nn) * a.T + t0 + i0, a.T - t0 - i0, uvec);
-                    const float4 mr = load4(a.gmixed + ((long long)(bb * 2 + 1) * a.N + nn) * a.T + t0 + i0, a.T - t0 - i0, uvec);
-                    bl[0] += ml.x; bl[1] += ml.y; bl[2] += ml.z; bl[3] += ml.w;
-                    br[0] += mr.x; br[1] += mr.y; br[2] += mr.z; br[3] += mr.w;
-                }
-#pragma unroll
-                for (int c = 0; c < NCH; ++c)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) d[c][j] = 0.0f;
+            }
+        } else {
+            const float4 l4 = *reinterpret_cast<const float4*>(gbuf + pb + i0);
+            const float4 r4 = *reinterpret_cast<const float4*>(gbuf + gbuf_stride + pb + i0);
+            float bl[4] = {l4.x, l4.y, l4.z, l4.w}, br[4] = {r4.x, r4.y, r4.z, r4.w};
+            if (a.gmixed) {
+                const float4 ml = load4(a.gmixed + ((long long)(bb * 2 + 0) * a.N + nn) * a.T + t0 + i0, a.T - t0 - i0, uvec);
+                const float4 mr = load4(a.gmixed + ((long long)(bb * 2 + 1) * a.N + nn) * a.T + t0 + i0, a.T - t0 - i0, uvec);
+                bl[0] += ml.x; bl[1] += ml.y; bl[2] += ml.z; bl[3] += ml.w;
+                br[0] += mr.x; br[1] += mr.y; br[2] += mr.z; br[3] += mr.w;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int i = i0 + j;
-                const bool live = (t0 + i) < a.T;
-                float dc[NCH], o[NCH];
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    o[c] = out_of(c, i);
-                    if constexpr (MASTER) {
-                        float g = live ? d[c][j] : 0.0f;
-                        if (a.flags & kChainOutGain) { acc_gout = fmaf(g, o[c] * tb.g_out, acc_gout); g *= tb.g_out; }
-                        dc[c] = g;
-                    } else {
-                        const float l = live ? bl[j] : 0.0f, r = live ? br[j] : 0.0f;
-                        acc_gl = fmaf(l, o[c], acc_gl);
-                        acc_gr = fmaf(r, o[c], acc_gr);
-                        dc[c] = fmaf(tb.gL, l, tb.gR * r);
-                    }
-                }
-                fn(i, dc, o);
+                acc_gl = fmaf(bl[j], o[0][j], acc_gl);
+                acc_gr = fmaf(br[j], o[0][j], acc_gr);
+                dc[0][j] = fmaf(tb.gL, bl[j], tb.gR * br[j]);
             }
         }
     };
 
     if (a.flags & kChainComp) {
-        // ---- forward recompute: delay line, smoothed gain ----
+        // ---- forward recompute: smoothed gain.  The look-ahead halo was prefetched into the delay line;
+        // so was the EQ output when forward left a checkpoint, otherwise it was just recomputed ----
+        if (!saved) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-            for (int i = 0; i < L; ++i) ebuf[c * buf_stride + pLA + pb + i] = v[c][i];
-        {
-            const float* etail_in = a.etail + (rt - 1) * NCH * LA;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c)
-                for (int j = tid; j < LA; j += NT)
-                    ebuf[c * buf_stride + pidx(j)] = has_pred ? __ldg(etail_in + c * LA + j) : 0.0f;
+            for (int c = 0; c < NCH; ++c) sts_chunk<L>(ebuf + c * buf_stride + pLA + pb, v[c]);
         }
         float gs[L];
         float gz = 0.0f;
@@ -269,24 +337,30 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
         // ---- adjoint: output -> (delayed signal path, gain path) ----
         float q[L];
         float* dhead_out = a.dhead + rt * NCH * LA;
-        float Gi = 0.0f;
-        for_each_upstream(
-            [&](int c, int i) {
-                if (c == 0) Gi = fast_exp2(kLog2Per20Db * (gs[i] + tb.makeup));
-                return ebuf[c * buf_stride + pb + i] * Gi;
-            },
-            [&](int i, const float* dc, const float* o) {
-                float r = 0.0f;
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    r = fmaf(dc[c], o[c], r);
-                    const float dyG = dc[c] * Gi;
-                    dbuf[c * buf_stride + pb + i] = dyG;
-                    if (tid * L < LA) dhead_out[c * LA + tid * L + i] = dyG;  // whole chunk: L | LA
-                }
-                q[i] = r * kLn10Over20;
-                acc_comp[4] += q[i];
-            });
+        for (int i0 = 0; i0 < L; i0 += 4) {
+            float G[4], o[NCH][4], dc[NCH][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) G[j] = fast_exp2(kLog2Per20Db * (gs[i0 + j] + tb.makeup));
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float4 e4 = *reinterpret_cast<const float4*>(ebuf + c * buf_stride + pb + i0);  // x[n - LA]
+                o[c][0] = e4.x * G[0]; o[c][1] = e4.y * G[1]; o[c][2] = e4.z * G[2]; o[c][3] = e4.w * G[3];
+            }
+            upstream4(i0, o, dc);
+            float r[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float dyG[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { r[j] = fmaf(dc[c][j], o[c][j], r[j]); dyG[j] = dc[c][j] * G[j]; }
+                const float4 d4 = make_float4(dyG[0], dyG[1], dyG[2], dyG[3]);
+                *reinterpret_cast<float4*>(dbuf + c * buf_stride + pb + i0) = d4;
+                if (tid * L < LA) *reinterpret_cast<float4*>(dhead_out + c * LA + tid * L + i0) = d4;  // whole chunk: L | LA
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { q[i0 + j] = r[j] * kLn10Over20; acc_makeup += q[i0 + j]; }
+        }
         // ---- reverse one-pole: p[n] = q[n] + alpha p[n+1] ----
         float pz = 0.0f;
 #pragma unroll
@@ -302,15 +376,18 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
         // successor already published its smoother state and halo (the common case): fetch the
         // halo now and save a barrier; otherwise wait for it and fetch after the barrier
         const bool halo_early = s_premask[1] >= (unsigned)kBFlagComp;
-        if (halo_early) {
+        auto fetch_halo = [&]() {
             const float* dhead_in = a.dhead + (rt + 1) * NCH * LA;
 #pragma unroll
             for (int c = 0; c < NCH; ++c)
-                for (int j = tid; j < LA; j += NT)
-                    dbuf[c * buf_stride + pidx(TILE + j)] = has_succ ? __ldcg(dhead_in + c * LA + j) : 0.0f;
-        } else if (tid == 0) {
-            wait_flag_ge(succ_flag, kBFlagComp, nowait);
-        }
+                for (int j = 4 * tid; j < LA; j += 4 * NT) {
+                    const float4 h = has_succ ? __ldcg(reinterpret_cast<const float4*>(dhead_in + c * LA + j))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(dbuf + c * buf_stride + pidx4(TILE + j)) = h;
+                }
+        };
+        if (halo_early) fetch_halo();
+        else if (tid == 0) wait_flag_ge(succ_flag, kBFlagComp, nowait);
         if (tid == 0 && has_succ && !((s_premask[0] >> kStateSmooth) & 1u))
             s_pre[kStateSmooth] = mail_wait(bstate_in + kStateSmooth, nowait);
         __syncthreads();  // dbuf (own tile), reverse aggregates, successor state visible
@@ -324,13 +401,14 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
         }
         const float pcarry = fmaf(tb.a_lane[31 - lane], pc, px);  // p at the first sample after this chunk
         if (!halo_early) {  // halo of dy*G from the successor tile
-            const float* dhead_in = a.dhead + (rt + 1) * NCH * LA;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c)
-                for (int j = tid; j < LA; j += NT)
-                    dbuf[c * buf_stride + pidx(TILE + j)] = has_succ ? __ldcg(dhead_in + c * LA + j) : 0.0f;
+            fetch_halo();
             __syncthreads();
         }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) lds_chunk<L>(dbuf + c * buf_stride + pLA + pb, u[c]);  // dy*G of x[n] = (dy*G)[n + LA]
+        // static-curve sums: S1 = sum p*tc, S2 = sum p*tc^2, S3 = sum p*lin (p = smoothed-gain adjoint)
+        float S1 = 0.0f, S2 = 0.0f, S3 = 0.0f;
+        const float cside = beta * tb.slope * tb.inv_knee * k20OverLn10;
         float gprev = gcarry;
 #pragma unroll
         for (int i = 0; i < L; ++i) {
@@ -339,35 +417,45 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
             if (NCH > 1) side += v[NCH - 1][i];
             float tc, lin;
             const float gc = gain_computer(side, tb, tc, lin);
-            acc_comp[0] = fmaf(p, gprev - gc, acc_comp[0]);
+            acc_alpha = fmaf(p, gprev - gc, acc_alpha);
             gprev = gs[i];
-            const float dgc = beta * p;
-            const float dcurve = tb.slope * tc * tb.inv_knee;                 // d g_c / d x_db
-            acc_comp[1] = fmaf(dgc, -dcurve, acc_comp[1]);                    // threshold
-            acc_comp[2] = fmaf(dgc, -fmaf(tc * tc, tb.inv_2knee, lin) * tb.inv_ratio2, acc_comp[2]);  // ratio
-            acc_comp[3] = fmaf(dgc, tb.slope * tc * tb.inv_2knee * (1.0f - tc * tb.inv_knee), acc_comp[3]);  // knee
-            const float dside = (fabsf(side) > kCompEps) ? __fdividef(dgc * dcurve * k20OverLn10, side) : 0.0f;
+            const float m = p * tc;
+            S1 += m;
+            S2 = fmaf(m, tc, S2);
+            S3 = fmaf(p, lin, S3);
+            // d g_c / d side = slope * tc / knee * 20/(ln10 * side)
+            const float dside = (fabsf(side) > kCompEps) ? __fdividef(m * cside, side) : 0.0f;
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) u[c][i] = dbuf[c * buf_stride + pLA + pb + i] + dside;
+            for (int c = 0; c < NCH; ++c) u[c][i] += dside;
         }
+        // d g_c/d thr = -slope*tc/knee; d g_c/d ratio = -(tc^2/(2 knee) + lin)/ratio^2;
+        // d g_c/d knee = slope*tc/(2 knee) * (1 - tc/knee); each times d L/d g_c = beta * p
+        acc_thr = -beta * tb.slope * tb.inv_knee * S1;
+        acc_ratio = -beta * tb.inv_ratio2 * fmaf(tb.inv_2knee, S2, S3);
+        acc_knee = beta * tb.slope * tb.inv_2knee * fmaf(-tb.inv_knee, S2, S1);
     } else {
         // no compressor: chain output = EQ output
-        for_each_upstream([&](int c, int i) { return v[c][i]; },
-                          [&](int i, const float* dc, const float*) {
 #pragma unroll
-                              for (int c = 0; c < NCH; ++c) u[c][i] = dc[c];
-                          });
+        for (int i0 = 0; i0 < L; i0 += 4) {
+            float o[NCH][4], dc[NCH][4];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[c][j] = v[c][i0 + j];
+            upstream4(i0, o, dc);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) u[c][i0 + j] = dc[c][j];
+        }
     }
     {
-        float t;
-        t = warp_sum(acc_comp[0]); if (lane == 0) s_part[warp * kGradCount + kGradAlpha] = t;
-        t = warp_sum(acc_comp[1]); if (lane == 0) s_part[warp * kGradCount + kGradThr] = t;
-        t = warp_sum(acc_comp[2]); if (lane == 0) s_part[warp * kGradCount + kGradRatio] = t;
-        t = warp_sum(acc_comp[3]); if (lane == 0) s_part[warp * kGradCount + kGradKnee] = t;
-        t = warp_sum(acc_comp[4]); if (lane == 0) s_part[warp * kGradCount + kGradMakeup] = t;
-        t = warp_sum(acc_gout); if (lane == 0) s_part[warp * kGradCount + kGradGout] = t;
-        t = warp_sum(acc_gl); if (lane == 0) s_part[warp * kGradCount + kGradGL] = t;
-        t = warp_sum(acc_gr); if (lane == 0) s_part[warp * kGradCount + kGradGR] = t;
+        float t = warp_sum4(acc_alpha, acc_thr, acc_ratio, acc_knee, lane);
+        if ((lane & 7) == 0) s_part[warp * kGradCount + kGradAlpha + warp_sum4_slot(lane)] = t;
+        t = warp_sum4(acc_makeup, acc_gout, acc_gl, acc_gr, lane);
+        const int sl = warp_sum4_slot(lane);
+        const int idx = sl == 0 ? kGradMakeup : (sl == 1 ? kGradGout : (sl == 2 ? kGradGL : kGradGR));
+        if ((lane & 7) == 0) s_part[warp * kGradCount + idx] = t;
     }
 
     // ---------------- adjoint of the EQ cascade, sections 5..0 ----------------
@@ -382,7 +470,10 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
                 ym2[c] = __shfl_up_sync(0xffffffffu, v[c][L - 2], 1);
                 if (lane == 31) { nb0[(warp * NCH + c) * 2 + 0] = v[c][L - 1]; nb0[(warp * NCH + c) * 2 + 1] = v[c][L - 2]; }
             }
+            if (tid == 0) sh.next = claimed;
             __syncthreads();
+            // the buffer area is no longer read by this tile: start the copies of the next item's inputs
+            bwd_prefetch<NCH, L, NT, MASTER>(f, sh.next, area, tab_next, tid);
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 if (lane == 0) {
@@ -519,10 +610,11 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
                 for (int i = 0; i < L; ++i) v[c][i] = xin[c][i];
                 ym1[c] = xm1[c]; ym2[c] = xm2[c];
             }
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const float t = warp_sum(acc[j]);
-                if (lane == 0) s_part[warp * kGradCount + kGradEq + 5 * k + j] = t;
+            {
+                const float t4 = warp_sum4(acc[0], acc[1], acc[2], acc[3], lane);
+                if ((lane & 7) == 0) s_part[warp * kGradCount + kGradEq + 5 * k + warp_sum4_slot(lane)] = t4;
+                const float t1 = warp_sum(acc[4]);
+                if (lane == 0) s_part[warp * kGradCount + kGradEq + 5 * k + 4] = t1;
             }
         }
     }
@@ -550,11 +642,49 @@ __global__ void __launch_bounds__(NT, MINB) chain_bwd_kernel(ChainArgs a) {
             store_chunk<L>(a.gsrc + (long long)row * a.T + t0, a.T - t0, uvec, u[0]);
         }
     }
+    const bool late_hand_off = !(a.flags & kChainEq);  // no EQ adjoint: the area was in use until here
+    if (late_hand_off && tid == 0) sh.next = claimed;
     __syncthreads();
+    if (late_hand_off) bwd_prefetch<NCH, L, NT, MASTER>(f, sh.next, area, tab_next, tid);
     if (tid < kGradCount) {
         float s = 0.0f;
         for (int w = 0; w < NW; ++w) s += s_part[w * kGradCount + tid];
         a.partial[rt * kGradCount + tid] = s;
+    }
+    return sh.next;
+}
+
+// Floats of the per-tile buffer area: delay line + dy*G line (per channel) + upstream gradient
+__host__ __device__ inline int bwd_area_floats(int nch, int tile, int la) {
+    return 2 * nch * pidx4(la + tile) + 2 * pidx4(tile);
+}
+
+template <int NCH, int L, int NT, bool MASTER>
+__global__ void __launch_bounds__(NT, 1) chain_bwd_kernel(BwdArgs f) {
+    DMST_DYN_SMEM(smem_raw);
+    float* area = reinterpret_cast<float*>(smem_raw);
+    DMST_SHARED_ARRAY(float, s_tabf, 2 * (sizeof(RowTab) / 4));
+    DMST_SHARED_ARRAY(int, s_first, 1);
+    typedef BwdShared<NT, NCH> Shared;
+    DMST_SHARED_ARRAY(Shared, sh_p, 1);
+    Shared& sh = sh_p[0];
+    const int tid = threadIdx.x;
+
+    if (tid == 0) s_first[0] = atomicAdd(f.ticket, 1);
+    __syncthreads();
+    int cur = s_first[0];
+    int par = 0;
+    bwd_prefetch<NCH, L, NT, MASTER>(f, cur, area, s_tabf, tid);
+    while (true) {
+        cp_async_wait_all();
+        __syncthreads();  // this item's inputs have landed; the previous item is completely done
+        if (cur >= f.total) break;
+        const int tile = f.a.ntiles - 1 - cur / f.a.nrows;
+        const int row = cur % f.a.nrows;
+        const RowTab& tb = *reinterpret_cast<const RowTab*>(s_tabf + par * (sizeof(RowTab) / 4));
+        float* tab_next = s_tabf + (par ^ 1) * (sizeof(RowTab) / 4);
+        cur = bwd_tile<NCH, L, NT, MASTER>(f, row, tile, area, tb, tab_next, sh);
+        par ^= 1;
     }
 }
 

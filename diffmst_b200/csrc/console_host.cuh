@@ -197,8 +197,9 @@ inline int persistent_ctas(Kernel kern, int threads, size_t smem) {
     return sms * per_sm;
 #endif
 }
-inline size_t bwd_smem_bytes(int nch, int tile, int la, int nt) {
-    return (size_t)(2 * nch * (pidx(la + tile) + 1) + 12 * nch * nt) * 4;
+inline size_t bwd_smem_bytes(int nch, int tile, int la, int nt, bool master) {
+    // per-tile buffer area (+ the forward lane carry-ins of a chain without checkpoints)
+    return (size_t)(bwd_area_floats(nch, tile, la) + (master ? 12 * nch * nt : 0)) * 4;
 }
 
 struct ConsoleCall {
@@ -336,18 +337,26 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
     DMST_CHECK(DMST_MEMSET_ASYNC(w.header, 0, 64 * sizeof(int), stream));
     DMST_CHECK(DMST_MEMSET_ASYNC(base + w.bflags_begin, 0, w.bflags_end - w.bflags_begin, stream));
 
-    ChainArgs am, at;
+    BwdArgs fm, ft;
+    memset(&fm, 0, sizeof(fm));
+    memset(&ft, 0, sizeof(ft));
+    ChainArgs& am = fm.a;
+    ChainArgs& at = ft.a;
     fill_chain(am, k, true, w);
     am.src = w.bus_pre;
     am.gout = gmix; am.gsrc = w.dbus;
     am.user_vec_ok = aligned16(gmix) && (k.T % 4 == 0);
-    am.ticket = w.header + 2;
+    fm.total = am.nrows * am.ntiles; fm.ticket = w.header + 2;
+    fm.area = bwd_area_floats(2, kMasterTile, k.la_m);
     {
-        auto kern = chain_bwd_kernel<2, kMasterL, kMasterNT, true, 1>;
-        const size_t smem = bwd_smem_bytes(2, kMasterTile, k.la_m, kMasterNT);
+        auto kern = chain_bwd_kernel<2, kMasterL, kMasterNT, true>;
+        const size_t smem = bwd_smem_bytes(2, kMasterTile, k.la_m, kMasterNT, true);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
+        int ctas = persistent_ctas(kern, kMasterNT, smem);
+        if (ctas <= 0) return DMST_EINVAL;
+        if (ctas > fm.total) ctas = fm.total;
         ScopedTimer tm(2, stream);
-        DMST_LAUNCH(kern, dim3(am.nrows * am.ntiles), dim3(kMasterNT), smem, stream, am);
+        DMST_LAUNCH(kern, dim3(ctas), dim3(kMasterNT), smem, stream, fm);
     }
     if (gmp && k.master_params) {
         EpilogueArgs e;
@@ -361,14 +370,18 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
     at.gout = w.dbus; at.gmixed = gmixed;
     at.gsrc = (k.flags & DMST_WANT_GRAD_TRACKS) ? gtracks : nullptr;
     at.user_vec_ok = (k.T % 4 == 0) && (!gmixed || aligned16(gmixed)) && (!at.gsrc || aligned16(at.gsrc));
-    at.ticket = w.header + 3;
+    at.tab = w.track_tab_b;
+    ft.total = at.nrows * at.ntiles; ft.ticket = w.header + 3;
+    ft.area = bwd_area_floats(1, kTrackTile, k.la_t);
     {
-        auto kern = chain_bwd_kernel<1, kTrackBwdL, kTrackBwdNT, false, kTrackBwdMinB>;
-        const size_t smem = bwd_smem_bytes(1, kTrackTile, k.la_t, kTrackBwdNT);
+        auto kern = chain_bwd_kernel<1, kTrackBwdL, kTrackBwdNT, false>;
+        const size_t smem = bwd_smem_bytes(1, kTrackTile, k.la_t, kTrackBwdNT, false);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
-        at.tab = w.track_tab_b;
+        int ctas = persistent_ctas(kern, kTrackBwdNT, smem);
+        if (ctas <= 0) return DMST_EINVAL;
+        if (ctas > ft.total) ctas = ft.total;
         ScopedTimer tm(3, stream);
-        DMST_LAUNCH(kern, dim3(at.nrows * at.ntiles), dim3(kTrackBwdNT), smem, stream, at);
+        DMST_LAUNCH(kern, dim3(ctas), dim3(kTrackBwdNT), smem, stream, ft);
     }
     {
         EpilogueArgs e;

@@ -13,6 +13,7 @@
 
 namespace dmst {
 
+#ifndef DMST_EMULATE   // (cuFFT-fed: not part of the host-emulated build)
 constexpr int kMrBlock = 256;
 constexpr int kMrItemsPerBlock = 4096;  // spectrum elements per block
 
@@ -66,20 +67,6 @@ struct MrLossArgs {
     float eps;
     float* partial;      // [rows][blocks_per_row][4]: sum (|Y|-|X|)^2, sum |Y|^2, sum |log|, sum |lin|
 };
-
-__device__ __forceinline__ float block_sum(float v, float* sh) {
-    v = warp_sum(v);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) sh[warp] = v;
-    __syncthreads();
-    float r = 0.0f;
-    if (warp == 0) {
-        r = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.0f;
-        r = warp_sum(r);
-    }
-    __syncthreads();
-    return r;  // valid in warp 0
-}
 
 // grid: (blocks_per_row, rows)
 __global__ void mr_loss_kernel(MrLossArgs a) {
@@ -309,7 +296,6 @@ __global__ void ola_multi_kernel(OlaMultiArgs a) {
     }
 }
 
-#ifndef DMST_EMULATE
 // Per-resolution slice of the workspace: the resolutions run concurrently on side streams
 struct MrResWs {
     float* frames;    // 2*rows*frames*n

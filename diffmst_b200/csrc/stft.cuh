@@ -27,6 +27,20 @@ __host__ __device__ __forceinline__ int reflect_index(int j, int T) {
     return j;
 }
 
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    float r = 0.0f;
+    if (warp == 0) {
+        r = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.0f;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;  // valid in warp 0
+}
+
 struct FrameArgs {
     const float* x;        // rows x T (row stride)
     long long row_stride;
