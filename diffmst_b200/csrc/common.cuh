@@ -141,7 +141,10 @@ __device__ __forceinline__ float mail_wait(const Mail* p, bool skip = false) {
     while (!mail_try(p, v)) {
         if (skip) break;
 #ifndef DMST_EMULATE
-        __nanosleep(32);
+#ifndef DMST_MAIL_SLEEP
+#define DMST_MAIL_SLEEP 32
+#endif
+        if (DMST_MAIL_SLEEP > 0) __nanosleep(DMST_MAIL_SLEEP);
 #else
         __nanosleep(0);
 #endif

@@ -39,6 +39,18 @@ struct BwdArgs {
 // beyond `valid`; 16-byte copies when the source allows it
 template <int NT>
 __device__ __forceinline__ void cp_tile(float* dst, const float* src, int count, int valid, bool vec_ok, int tid) {
+    static_assert(NT % 8 == 0, "constant shared-memory stride per iteration");
+    if (vec_ok && valid >= count) {
+        // interior tile: thread q moves float4 #q, #q+NT, ...; pidx4(4(q+NT)) - pidx4(4q) is constant
+        float* d = dst + pidx4(tid << 2);
+        const float* p = src + (tid << 2);
+        for (int q = tid; q < (count >> 2); q += NT) {
+            cp_async16(d, p);
+            d += 4 * NT + (NT >> 1);
+            p += 4 * NT;
+        }
+        return;
+    }
     for (int q = tid; q < (count >> 2); q += NT) {
         const int idx = q << 2;
         float* d = dst + pidx4(idx);
@@ -498,6 +510,7 @@ __device__ __forceinline__ int bwd_tile(const BwdArgs& f, const int row, const i
             const SectionTab& st = tb.sec[k];
             float* nb = s_nb + (k & 1) * NW * NCH * 2;  // double-buffered: one barrier per section
             const float b0 = st.b0, b1 = st.b1, b2 = st.b2, na1 = -st.a1, na2 = -st.a2, inv_b0 = st.inv_b0;
+            const float qb1 = -b1 * inv_b0, qb2 = -b2 * inv_b0, qa1 = st.a1 * inv_b0, qa2 = st.a2 * inv_b0;
             float xin[NCH][L];
             float r1[NCH], r2[NCH];
 #pragma unroll
@@ -514,22 +527,24 @@ __device__ __forceinline__ int bwd_tile(const BwdArgs& f, const int row, const i
                     s1 = sE[((k * NCH + c) * 2 + 0) * NT + tid];
                     s2 = sE[((k * NCH + c) * 2 + 1) * NT + tid];
                 }
+                // (states carried as n = -s/b0: x = y/b0 + n1 is a single fma)
+                float n1 = -s1 * inv_b0, n2 = -s2 * inv_b0;
 #pragma unroll
                 for (int i = 0; i < L; ++i) {
                     const float yv = v[c][i];
-                    const float x = (yv - s1) * inv_b0;
-                    s1 = fmaf(b1, x, fmaf(na1, yv, s2));
-                    s2 = fmaf(b2, x, na2 * yv);
+                    const float x = fmaf(yv, inv_b0, n1);
+                    n1 = fmaf(qb1, x, fmaf(qa1, yv, n2));
+                    n2 = fmaf(qb2, x, qa2 * yv);
                     xin[c][i] = x;
                 }
                 if (lane == 31) { nb[(warp * NCH + c) * 2 + 0] = xin[c][L - 1]; nb[(warp * NCH + c) * 2 + 1] = xin[c][L - 2]; }
                 // (b) reverse-time all-pole recursion, zero right-hand state
+                // (only its end state is needed: the recursion is run again from the true state below)
                 float g1 = 0.0f, g2 = 0.0f;
 #pragma unroll
                 for (int i = L - 1; i >= 0; --i) {
                     const float gh = fmaf(na1, g1, fmaf(na2, g2, u[c][i]));
                     g2 = g1; g1 = gh;
-                    u[c][i] = gh;
                 }
                 r1[c] = g1; r2[c] = g2;
             }
@@ -577,18 +592,12 @@ __device__ __forceinline__ int bwd_tile(const BwdArgs& f, const int row, const i
             float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                // add the homogeneous reverse response, then FIR B^T and the correlations
-                float h1 = x1[c], h2 = x2[c];
-#pragma unroll
-                for (int i = L - 1; i >= 0; --i) {
-                    const float t = fmaf(na1, h1, na2 * h2);
-                    u[c][i] += t;
-                    h2 = h1; h1 = t;
-                }
+                // reverse all-pole recursion from the true right-hand state, FIR B^T and the correlations
                 float gp1 = x1[c], gp2 = x2[c];  // g[i+1], g[i+2]
+                float dxp = ((L >= 2) ? xin[c][L - 2] : xm1[c]) - xin[c][L - 1];  // x[i-1] - x[i]
 #pragma unroll
                 for (int i = L - 1; i >= 0; --i) {
-                    const float gh = u[c][i];
+                    const float gh = fmaf(na1, gp1, fmaf(na2, gp2, u[c][i]));
                     const float xa = xin[c][i];
                     const float xb = (i >= 1) ? xin[c][i - 1] : xm1[c];
                     const float xc = (i >= 2) ? xin[c][i - 2] : (i == 1 ? xm1[c] : xm2[c]);
@@ -598,11 +607,13 @@ __device__ __forceinline__ int bwd_tile(const BwdArgs& f, const int row, const i
                     // p = a1+a2, q = a2: for poles/zeros near z = 1 the plain (b, a) gradients
                     // are huge and cancel in the parameter Jacobian; differencing the signals
                     // per sample before accumulating keeps float32 sums well conditioned.
+                    const float dxn = xc - xb;  // first difference one sample earlier (next iteration's dxp)
                     acc[0] = fmaf(gh, xa, acc[0]);
-                    acc[1] = fmaf(gh, xb - xa, acc[1]);
-                    acc[2] = fmaf(gh, (xa - xb) - (xb - xc), acc[2]);
+                    acc[1] = fmaf(gh, dxp, acc[1]);
+                    acc[2] = fmaf(gh, dxn - dxp, acc[2]);
                     acc[3] = fmaf(-gh, ya, acc[3]);
                     acc[4] = fmaf(-gh, yb - ya, acc[4]);
+                    dxp = dxn;
                     u[c][i] = fmaf(b0, gh, fmaf(b1, gp1, b2 * gp2));
                     gp2 = gp1; gp1 = gh;
                 }

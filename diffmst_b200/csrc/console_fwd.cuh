@@ -111,17 +111,28 @@ __device__ __forceinline__ void fwd_prefetch(const FwdArgs& f, const FwdWork& w,
         const float* p = a.src + (long long)b * a.src_batch_stride + (long long)n * a.src_row_stride + tbase;
         const int valid = a.T - tbase;
         const bool vec = a.src_vec_ok != 0;
+        if (vec && valid >= TILE_T) {
+            // interior tile: pidx4(4(q+NT)) - pidx4(4q) is constant, no per-copy index arithmetic
+            float* d = inbuf + pidx4(tid << 2);
+            const float* s = p + (tid << 2);
 #pragma unroll
-        for (int q = tid; q < TILE_T / 4; q += NT) {
-            const int idx = 4 * q;
-            float* d = inbuf + pidx4(idx);
-            if (vec && valid - idx >= 4) {
-                cp_async16(d, p + idx);
-            } else {
+            for (int q = 0; q < TILE_T / 4 / NT; ++q) {
+                cp_async16(d, s);
+                d += 4 * NT + (NT >> 1);
+                s += 4 * NT;
+            }
+        } else {
+            for (int q = tid; q < TILE_T / 4; q += NT) {
+                const int idx = 4 * q;
+                float* d = inbuf + pidx4(idx);
+                if (vec && valid - idx >= 4) {
+                    cp_async16(d, p + idx);
+                } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (idx + e < valid) cp_async4(d + e, p + idx + e);
-                    else d[e] = 0.0f;
+                    for (int e = 0; e < 4; ++e) {
+                        if (idx + e < valid) cp_async4(d + e, p + idx + e);
+                        else d[e] = 0.0f;
+                    }
                 }
             }
         }
