@@ -39,6 +39,14 @@ constexpr int kTrackFwdL = 32, kTrackFwdNT = 256;   // 8192-sample tiles, needs 
 constexpr int kTrackBwdL = 8, kTrackBwdNT = 1024, kTrackBwdMinB = 1;
 #endif
 constexpr int kMasterL = 16, kMasterNT = 256;       // 4096-sample tiles, 2 channels per thread
+// The master bus has few rows and is bound by the tile-to-tile chain: backward spreads a tile over
+// more threads (shorter chunks) to shorten every stage of that chain.
+#ifndef DMST_MASTER_BWD_NT
+#define DMST_MASTER_BWD_NT 256
+#endif
+constexpr int kMasterBwdNT = DMST_MASTER_BWD_NT;
+constexpr int kMasterBwdL = kMasterL * kMasterNT / kMasterBwdNT;
+static_assert(kMasterBwdL * kMasterBwdNT == kMasterL * kMasterNT && kMasterBwdL % 4 == 0, "master tile in the backward CTA shape");
 constexpr int kTrackTile = kTrackFwdL * kTrackFwdNT;
 constexpr int kMasterTile = kMasterL * kMasterNT;
 static_assert(kTrackFwdL * kTrackFwdNT == kTrackBwdL * kTrackBwdNT, "forward/backward tiles must agree");
@@ -101,7 +109,7 @@ struct Carver {
 
 struct ConsoleWs {
     int* header;          // [0..3] tickets (fwd track, fwd master, bwd master, bwd track)
-    RowTab *track_tab, *track_tab_b, *master_tab;  // track_tab: forward L, track_tab_b: backward L
+    RowTab *track_tab, *track_tab_b, *master_tab, *master_tab_b;  // *_b: tables for the backward chunk length
     float *y, *bus_pre, *dbus, *esave, *ssave;
     // forward chain (kept for backward)
     int *t_flag, *m_flag, *t_done;
@@ -128,6 +136,7 @@ inline ConsoleWs carve_console(void* base, int B, int N, int T, int la_t, int la
     w.track_tab = c.take<RowTab>(rows);
     w.track_tab_b = (kTrackBwdL == kTrackFwdL) ? w.track_tab : c.take<RowTab>(rows);
     w.master_tab = c.take<RowTab>(B);
+    w.master_tab_b = (kMasterBwdL == kMasterL) ? w.master_tab : c.take<RowTab>(B);
     w.y = c.take<float>(rows * w.Tp);
     w.bus_pre = c.take<float>((size_t)B * 2 * w.Tp);
     w.dbus = c.take<float>((size_t)B * 2 * w.Tp);
@@ -240,6 +249,7 @@ inline void fill_prepare(PrepareArgs& p, const ConsoleCall& k, bool master, Cons
         p.np = DMST_NUM_MASTER_PARAMS; p.kind = 2;
         for (int i = 0; i < DMST_NUM_MASTER_PARAMS; ++i) { p.lo[i] = k.ranges->master_lo[i]; p.hi[i] = k.ranges->master_hi[i]; }
         p.L[0] = kMasterL; p.tab[0] = w.master_tab; p.status_base = 1000;
+        if (w.master_tab_b != w.master_tab) { p.L[1] = kMasterBwdL; p.tab[1] = w.master_tab_b; }
     }
     p.sr = (double)k.sr; p.status = status;
 }
@@ -343,20 +353,20 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
     ChainArgs& am = fm.a;
     ChainArgs& at = ft.a;
     fill_chain(am, k, true, w);
-    am.src = w.bus_pre;
+    am.src = w.bus_pre; am.tab = w.master_tab_b;
     am.gout = gmix; am.gsrc = w.dbus;
     am.user_vec_ok = aligned16(gmix) && (k.T % 4 == 0);
     fm.total = am.nrows * am.ntiles; fm.ticket = w.header + 2;
     fm.area = bwd_area_floats(2, kMasterTile, k.la_m);
     {
-        auto kern = chain_bwd_kernel<2, kMasterL, kMasterNT, true>;
-        const size_t smem = bwd_smem_bytes(2, kMasterTile, k.la_m, kMasterNT, true);
+        auto kern = chain_bwd_kernel<2, kMasterBwdL, kMasterBwdNT, true>;
+        const size_t smem = bwd_smem_bytes(2, kMasterTile, k.la_m, kMasterBwdNT, true);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
-        int ctas = persistent_ctas(kern, kMasterNT, smem);
+        int ctas = persistent_ctas(kern, kMasterBwdNT, smem);
         if (ctas <= 0) return DMST_EINVAL;
         if (ctas > fm.total) ctas = fm.total;
         ScopedTimer tm(2, stream);
-        DMST_LAUNCH(kern, dim3(ctas), dim3(kMasterNT), smem, stream, fm);
+        DMST_LAUNCH(kern, dim3(ctas), dim3(kMasterBwdNT), smem, stream, fm);
     }
     if (gmp && k.master_params) {
         EpilogueArgs e;
