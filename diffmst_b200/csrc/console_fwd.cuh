@@ -187,7 +187,7 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
     // the other threads a few barriers later, so the atomic's latency is never waited for.  (Not at the
     // very start of the tile: items claimed long before they run unbalance the tail of the launch.)
     int claimed = 0;
-    if (!has_eq && tid == 0) claimed = atomicAdd(f.ticket, 1);
+    if (!MASTER && !has_eq && tid == 0) claimed = atomicAdd(f.ticket, 1);
 
     const int t0 = tile * TILE + tid * L;  // first sample of this thread's chunk
     const int tbase = tile * TILE;          // first sample of the tile
@@ -242,6 +242,9 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) lds_chunk<L>(ebuf + c * ebuf_stride + pLA + pb, v[c]);
+        // a bus tile claims its next item only now: while it waited for its tracks and summed them, an item
+        // claimed earlier would have been withheld from the CTAs that are free to run it
+        if (tid == 0) claimed = atomicAdd(f.ticket, 1);
     }
 
     if (a.flags & kChainGain) {
@@ -269,7 +272,7 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
             constexpr int NSUB = (L + kBwdChunk - 1) / kBwdChunk;  // state checkpoints per thread chunk
             float zm1[NCH][NSUB], zm2[NCH][NSUB];                  // zero-state states at the checkpoints
             if (tid == 0) {
-                if (k == 1) claimed = atomicAdd(f.ticket, 1);
+                if (!MASTER && k == 1) claimed = atomicAdd(f.ticket, 1);
                 if (k == kNumSections - 2) sh.next = claimed;  // visible after this section's barrier
             }
             // zero-state pass over the thread chunk (transposed direct form II)

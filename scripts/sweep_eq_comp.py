@@ -16,7 +16,8 @@ con = AdvancedMixConsole(44100).cuda()
 con.materialize_tracks = False
 con.check_ranges = False
 rows = []
-for N in (1, 8, 64):
+NS = [int(v) for v in sys.argv[1].split(',')] if len(sys.argv) > 1 else [1, 8, 64]
+for N in NS:
     for T in (65536, 262144, 1048576):
         B = 1
         g = torch.Generator().manual_seed(N * 7 + T)
