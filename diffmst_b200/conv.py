@@ -1,4 +1,4 @@
-"""Cnn14 convolution blocks on the B200 tensor cores (forward).
+"""Cnn14 convolution blocks on the B200 tensor cores.
 
 ``ConvBlock`` and ``Cnn14`` mirror mst/panns.py:27-85 and :126-209: same constructor arguments,
 same sub-module / parameter names (``conv1.weight``, ``bn1.running_mean`` ..., ``fc.weight``), so a
@@ -8,14 +8,19 @@ BatchNorm is folded into the epilogue in eval mode and applied from batch statis
 mode; activations stay in zero-bordered NHWC between the layers of a block (and between blocks
 inside ``Cnn14``).
 
-Round-1 limitation (stated, not hidden): forward only.  Calling these modules with autograd
-enabled on tensors that require grad raises; the backward kernels (dgrad / wgrad) are the next row.
+Training: with autograd enabled the 3x3 convolution is a ``torch.autograd.Function`` whose forward
+and input gradient (dgrad = the same shifted-GEMM kernel run on the output gradient with the taps
+flipped and the channel roles swapped) run on tcgen05; the weight gradient is nine plain GEMMs
+``dz^T @ x_shifted`` over the flattened zero-bordered NHWC tensors (library GEMM, cuBLAS through
+torch.matmul - a hand-written split-K tcgen05 wgrad is the next step); BatchNorm / ReLU / pooling
+of the differentiable path are PyTorch ops on NHWC views.
 """
 import ctypes
 from typing import List
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib
 from .console import _ptr, _require_cuda
@@ -87,7 +92,73 @@ def _conv_bn_relu(x_pad, conv: nn.Conv2d, bn, training: bool):
     return y
 
 
+class _Conv3x3Function(torch.autograd.Function):
+    """z = conv3x3(x) on zero-bordered NHWC tensors (no bias, stride 1, padding 1; mst/panns.py:33-47)."""
+
+    @staticmethod
+    def forward(ctx, x_pad, weight):
+        lib = _lib.lib()
+        B, Hp, Wp, Cin = x_pad.shape
+        Cout = weight.shape[0]
+        x_pad = x_pad.contiguous()
+        w9 = _repack(weight)
+        z = torch.empty(B, Hp, Wp, Cout, dtype=torch.float32, device=x_pad.device)
+        _lib.check(lib.dmst_conv3x3_forward(_ptr(x_pad), _ptr(w9), None, None, _ptr(z), B, Hp - 2, Wp - 2, Cin, Cout, 0,
+                                            _stream(x_pad.device)), "dmst_conv3x3_forward")
+        ctx.save_for_backward(x_pad, w9)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        lib = _lib.lib()
+        x_pad, w9 = ctx.saved_tensors
+        B, Hp, Wp, Cin = x_pad.shape
+        Cout = w9.shape[1]
+        gz = gz.contiguous()
+        # the border of the output is padding: whatever gradient arrives there does not exist upstream
+        gz[:, 0, :, :] = 0; gz[:, -1, :, :] = 0; gz[:, :, 0, :] = 0; gz[:, :, -1, :] = 0
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            # dgrad: correlation with the flipped taps, channel roles swapped -> the same kernel
+            w9t = w9.flip(0).transpose(1, 2).contiguous()          # [tap][Cin][Cout]
+            gx = torch.empty_like(x_pad)
+            _lib.check(lib.dmst_conv3x3_forward(_ptr(gz), _ptr(w9t), None, None, _ptr(gx), B, Hp - 2, Wp - 2, Cout, Cin, 0,
+                                                _stream(gz.device)), "dmst_conv3x3_forward (dgrad)")
+        if ctx.needs_input_grad[1]:
+            # wgrad: dW[tap] = dz^T @ x shifted by the tap (a constant row offset in the flattened layout;
+            # dz is zero on the border, so rows that would cross an image edge contribute nothing)
+            P = B * Hp * Wp
+            gzf, xf = gz.view(P, Cout), x_pad.view(P, Cin)
+            g9 = torch.empty(9, Cout, Cin, dtype=torch.float32, device=gz.device)
+            for t in range(9):
+                off = (t // 3 - 1) * Wp + (t % 3 - 1)
+                lo, hi = max(0, -off), min(P, P - off)
+                torch.matmul(gzf[lo:hi].t(), xf[lo + off:hi + off], out=g9[t])
+            gw = g9.permute(1, 2, 0).reshape(Cout, Cin, 3, 3)
+        return gx, gw
+
+
+def _needs_grad(x, *modules):
+    if not torch.is_grad_enabled():
+        return False
+    return x.requires_grad or any(p.requires_grad for m in modules if isinstance(m, nn.Module) for p in m.parameters())
+
+
+def _conv_bn_relu_autograd(x_pad, conv: nn.Conv2d, bn, training: bool):
+    """Differentiable twin of _conv_bn_relu: tensor-core conv Function + PyTorch BatchNorm/ReLU on NHWC views."""
+    z = _Conv3x3Function.apply(x_pad, conv.weight)
+    zi = z[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)                     # NCHW view of the interior (channels-last memory)
+    if isinstance(bn, nn.BatchNorm2d):
+        zi = bn(zi) if bn.training == training else F.batch_norm(
+            zi, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, bn.momentum or 0.0, bn.eps)
+    y = F.relu(zi).permute(0, 2, 3, 1)
+    return F.pad(y, (0, 0, 1, 1, 1, 1))                              # back to zero-bordered NHWC
+
+
 def _avgpool(x_pad, kh, kw, out_padded_nhwc):
+    if torch.is_grad_enabled() and x_pad.requires_grad:
+        y = F.avg_pool2d(x_pad[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2), kernel_size=(kh, kw))
+        return F.pad(y.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)) if out_padded_nhwc else y.contiguous()
     lib = _lib.lib()
     B, Hp, Wp, C = x_pad.shape
     H, W = Hp - 2, Wp - 2
@@ -101,11 +172,10 @@ def _avgpool(x_pad, kh, kw, out_padded_nhwc):
     return y
 
 
-def _check_no_grad(x, module):
-    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
-        raise NotImplementedError(
-            "diffmst_b200 ConvBlock/Cnn14: forward only in this round (tensor-core dgrad/wgrad are not built yet); "
-            "call under torch.no_grad() or freeze the encoder")
+def _to_padded_nhwc_any(x, grad: bool):
+    if grad:
+        return F.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()
+    return _to_padded_nhwc(x)
 
 
 def init_layer(layer):
@@ -141,14 +211,14 @@ class ConvBlock(nn.Module):
             init_bn(self.bn2)
 
     def forward_nhwc(self, x_pad, pool_size, out_padded_nhwc: bool):
-        x = _conv_bn_relu(x_pad, self.conv1, self.bn1, self.training)
-        x = _conv_bn_relu(x, self.conv2, self.bn2, self.training)
+        unit = _conv_bn_relu_autograd if _needs_grad(x_pad, self) else _conv_bn_relu
+        x = unit(x_pad, self.conv1, self.bn1, self.training)
+        x = unit(x, self.conv2, self.bn2, self.training)
         return _avgpool(x, int(pool_size[0]), int(pool_size[1]), out_padded_nhwc)
 
     def forward(self, input: torch.Tensor, pool_size: List[int]):
         _require_cuda(input, "input")
-        _check_no_grad(input, self)
-        return self.forward_nhwc(_to_padded_nhwc(input), pool_size, out_padded_nhwc=False)
+        return self.forward_nhwc(_to_padded_nhwc_any(input, _needs_grad(input, self)), pool_size, out_padded_nhwc=False)
 
 
 class Cnn14(nn.Module):
@@ -167,8 +237,7 @@ class Cnn14(nn.Module):
 
     def forward(self, x: torch.Tensor):
         _require_cuda(x, "x")
-        _check_no_grad(x, self)
-        h = _to_padded_nhwc(x)
+        h = _to_padded_nhwc_any(x, _needs_grad(x, self))
         for i, pool in enumerate(self.POOLS):
             h = getattr(self, f"conv_block{i + 1}").forward_nhwc(h, pool, out_padded_nhwc=(i < 5))
         h = torch.mean(h, dim=2)            # mean across stft bins
