@@ -96,7 +96,10 @@ def test_golden_cases(golden, name):
     assert np.allclose(ours["tpd"]["compressor"]["threshold_db"].detach().cpu().numpy(), d["denorm_threshold_db"], rtol=1e-6)
 
 
-@pytest.mark.parametrize("shape", [(2, 4, 65536), (1, 5, 44100), (3, 1, 20000)])
+# (the last three stress the work-item schedule of the persistent kernels: many tracks per item, more items than
+# tracks, a ragged last tile, fewer work items than CTAs)
+@pytest.mark.parametrize("shape", [(2, 4, 65536), (1, 5, 44100), (3, 1, 20000), (1, 40, 36871), (5, 2, 49153),
+                                   (1, 1, 32768)])
 def test_seeded_vs_float64_oracle(shape):
     B, N, T = shape
     g = torch.Generator().manual_seed(100 + T)
@@ -297,3 +300,25 @@ def test_full_size_properties():
         assert torch.equal(m2, 2 * m1)
         z = con(torch.zeros_like(x), tp, fp, mp, use_fx_bus=False)[1]
         assert float(z.abs().max()) == 0.0
+
+
+def test_random_mix_helpers_on_device():
+    """naive_random_mix keeps the reference's signature / 8-tuple (mst/mixing.py:35-94) with parameters drawn on
+    the device; random_reference_mix is the target pipeline of mst/system.py:232-253."""
+    from diffmst_b200 import AdvancedMixConsole, batch_stereo_peak_normalize, naive_random_mix, random_reference_mix
+    con = AdvancedMixConsole(SR).cuda()
+    tracks = (torch.randn(2, 3, 40000, generator=torch.Generator().manual_seed(2)) * 0.1).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    out = naive_random_mix(tracks, con, use_fx_bus=False, use_ouput_fader=True, generator=gen)
+    assert len(out) == 8
+    mixed, mix, tpd, fxd, mpd, tp, fp, mp = out
+    assert tp.shape == (2, 3, 27) and fp.shape == (2, 25) and mp.shape == (2, 26)
+    assert tp.is_cuda and float(tp.min()) >= 0.0 and float(tp.max()) <= 1.0
+    assert mix.shape == (2, 2, 40000) and not mix.requires_grad and torch.isfinite(mix).all()
+    # same parameters through the console directly give the same mix, bit for bit
+    assert torch.equal(mix, con(tracks, tp, fp, mp, use_fx_bus=False)[1])
+    gen.manual_seed(7)
+    ref_mix, has_nan, params = random_reference_mix(tracks, con, generator=gen, use_fx_bus=False)
+    assert torch.equal(params[0], tp) and not bool(has_nan)
+    assert torch.equal(ref_mix, batch_stereo_peak_normalize(mix))
+    assert abs(float(ref_mix.abs().amax(dim=(1, 2)).min()) - 1.0) < 1e-6
