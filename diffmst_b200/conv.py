@@ -244,3 +244,35 @@ class Cnn14(nn.Module):
         x1, _ = torch.max(h, dim=2)
         x2 = torch.mean(h, dim=2)
         return self.fc(x1 + x2)
+
+
+class SpectrogramEncoder(nn.Module):
+    """mst/modules.py:740-806: waveform -> STFT (2048/512, Hann) -> (|X| + 1e-8)^0.3 -> Cnn14 -> embedding.
+
+    Same constructor arguments, buffer (``window``) and sub-module names (``model``, ``bn``) as the
+    reference, so its checkpoints load with ``load_state_dict``.  The convolution trunk is the
+    tensor-core ``Cnn14`` above; the spectrogram front-end is cuFFT through ``torch.stft`` followed
+    by one fused magnitude-compression kernel from PyTorch (plumbing; fusing it into conv_block1's
+    loader is the next step)."""
+
+    def __init__(self, embed_dim: int = 128, n_inputs: int = 1, n_fft: int = 2048, hop_length: int = 512,
+                 input_batchnorm: bool = False, encoder_batchnorm: bool = True) -> None:
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.n_inputs = n_inputs
+        self.n_fft = n_fft
+        self.hop_length = hop_length
+        self.input_batchnorm = input_batchnorm
+        self.register_buffer("window", torch.hann_window(window_length=int(n_fft)))
+        self.model = Cnn14(n_inputs=n_inputs, num_classes=embed_dim, use_batchnorm=encoder_batchnorm)
+        self.bn = nn.BatchNorm2d(3) if input_batchnorm else nn.Identity()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        bs, chs, seq_len = x.size()
+        X = torch.stft(x.reshape(-1, seq_len), n_fft=self.n_fft, hop_length=self.hop_length, window=self.window,
+                       return_complex=True)
+        X = X.view(bs, chs, X.shape[-2], X.shape[-1])
+        X = torch.pow(X.abs() + 1e-8, 0.3)
+        if self.input_batchnorm:
+            X = self.bn(X)
+        return self.model(X)

@@ -162,3 +162,22 @@ def test_cnn14_forward_full_stack():
         got = ours(x)
     assert got.shape == (2, 512)
     assert relmax(got, want) <= 1e-2, relmax(got, want)   # 12 TF32 layers deep
+
+
+def test_spectrogram_encoder_matches_reference_composition():
+    """mst/modules.py:740-806: STFT 2048/512 -> (|X|+1e-8)^0.3 -> Cnn14; state dict names as upstream
+    (window, model.conv_block*.{conv,bn}*, model.fc)."""
+    from diffmst_b200 import SpectrogramEncoder
+    g = torch.Generator().manual_seed(21)
+    enc = SpectrogramEncoder(embed_dim=64, n_inputs=1).cuda().eval()
+    ref = OracleCnn14(num_classes=64).cuda().eval()
+    ref.load_state_dict(enc.model.state_dict(), strict=True)
+    assert set(k.split(".")[0] for k in enc.state_dict()) == {"window", "model"}
+    x = (torch.randn(2, 1, 131072, generator=g) * 0.1).cuda()
+    with torch.no_grad():
+        got = enc(x)
+        X = torch.stft(x.view(-1, 131072), n_fft=2048, hop_length=512, window=torch.hann_window(2048).cuda(),
+                       return_complex=True).view(2, 1, 1025, -1)
+        want = ref(torch.pow(X.abs() + 1e-8, 0.3))
+    assert got.shape == (2, 64)
+    assert relmax(got, want) <= 1e-2, relmax(got, want)
