@@ -28,7 +28,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    extra = [f"-D{k}={os.environ[k]}" for k in ("DMST_TRACK_CFG", "DMST_BWD_CHUNK", "DMST_FWD_MINB", "DMST_BWD_MINB", "DMST_EXP", "DMST_MAIL_SLEEP", "DMST_MASTER_BWD_NT") if k in os.environ]  # tuning experiments
+    extra = [f"-D{k}={os.environ[k]}" for k in ("DMST_MAIL_SLEEP", "DMST_MASTER_BWD_NT") if k in os.environ]  # tuning experiments
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES + ["-lcufft"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

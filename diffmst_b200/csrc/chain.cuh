@@ -16,10 +16,7 @@ constexpr int kStateStride = 32;   // floats per (row, tile): [sec][ch][2] (24) 
 constexpr int kStateSmooth = 24;
 constexpr int kTail2Stride = 32;   // floats per (row, tile): [stage 0..6][ch][2]
 constexpr int kFlagSmooth = 7;
-#ifndef DMST_BWD_CHUNK
-#define DMST_BWD_CHUNK 16
-#endif
-constexpr int kBwdChunk = DMST_BWD_CHUNK;  // thread chunk of the track backward kernel (state checkpoint spacing)     // flag value meaning "EQ sections 1..6 and smoother published"
+constexpr int kBwdChunk = 16;  // thread chunk of the track backward kernel = spacing of forward's state checkpoints
 
 struct ChainArgs {
     // ---- geometry ----

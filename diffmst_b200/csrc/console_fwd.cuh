@@ -20,10 +20,6 @@
 
 namespace dmst {
 
-#ifndef DMST_EXP
-#define DMST_EXP 0
-#endif
-
 struct FwdArgs {
     ChainArgs t, m;   // per-track chains / master bus chains
     int B;            // batch items
@@ -104,7 +100,7 @@ __device__ __forceinline__ void fwd_prefetch(const FwdArgs& f, const FwdWork& w,
         const float* src = reinterpret_cast<const float*>(a.tab + w.row);
         for (int i = tid; i < int(sizeof(RowTab) / 16); i += NT) cp_async16(tabbuf + 4 * i, src + 4 * i);
     }
-    if (w.role == 1 && !(DMST_EXP & 1)) {
+    if (w.role == 1) {
         const ChainArgs& a = f.t;
         const int b = w.row / a.N, n = w.row - b * a.N;
         const int tbase = w.tile * TILE_T;
@@ -194,12 +190,7 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
     float v[NCH][L];
 
     if constexpr (!MASTER) {
-        if (DMST_EXP & 1) {
-#pragma unroll
-            for (int i = 0; i < L; ++i) v[0][i] = 0.01f * (i & 7);
-        } else {
-            lds_chunk<L>(inbuf + pb, v[0]);  // prefetched source samples (landed before the caller's barrier)
-        }
+        lds_chunk<L>(inbuf + pb, v[0]);  // prefetched source samples (landed before the caller's barrier)
     } else {
         // the N track tiles this bus tile sums must be complete
         if (tid == 0) wait_flag_ge(f.done + (long long)row * f.t.ntiles + tbase / TILE_T, a.N, nowait);
@@ -331,7 +322,7 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
                 mat2_apply_acc(st.Ppow[lane], c1, c2, e1[c], e2[c]);
             }
             // add the homogeneous response to the carried-in state
-            float* ssave = (a.ssave && !(DMST_EXP & 2))
+            float* ssave = a.ssave
                                ? a.ssave + ((long long)row * a.ntiles + tile) * (kNumSections * NCH * 2) * (TILE / kBwdChunk)
                                : nullptr;
 #pragma unroll
@@ -424,7 +415,7 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
         }
         const float carry = fmaf(tb.a_lane[lane], cw, ex);
         // checkpoint of the EQ output for backward: coalesced store from the delay line
-        if (a.esave && !(DMST_EXP & 2)) {
+        if (a.esave) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c)
                 stage_out4<NT, TILE>(a.esave + (long long)(row * NCH + c) * a.Tp + tbase, ebuf + c * ebuf_stride + pLA,
@@ -464,7 +455,7 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
         __syncthreads();  // every thread has read its delayed samples
         sts_chunk<L>(ebuf + pb, v[0]);
         __syncthreads();
-        if (!(DMST_EXP & 4)) stage_out4<NT, TILE>(a.y + (long long)row * a.Tp + tbase, ebuf, a.Tp - tbase, true, tid);
+        stage_out4<NT, TILE>(a.y + (long long)row * a.Tp + tbase, ebuf, a.Tp - tbase, true, tid);
         if (a.want_mixed) {
             const int b = row / a.N, n = row - b * a.N;
             stage_out4<NT, TILE>(a.mixed + ((long long)(b * 2 + 0) * a.N + n) * a.T + tbase, ebuf, a.T - tbase,

@@ -13,31 +13,10 @@ namespace dmst {
 
 // Tile geometry.  Forward and backward must agree on NT*L per row kind because backward
 // restarts each tile from the carry-in states the forward pass saved.
-#ifndef DMST_TRACK_CFG
-#define DMST_TRACK_CFG 0
-#endif
-#if DMST_TRACK_CFG == 0
+// (Measured on B200: 2048...8192-sample tiles and 128...512-thread CTAs are within 5 % of each other for
+// the track chain; occupancy above 16 warps per SM does not pay)
 constexpr int kTrackFwdL = 32, kTrackFwdNT = 256;   // 8192-sample tiles
-constexpr int kTrackBwdL = 16, kTrackBwdNT = 512, kTrackBwdMinB = 1;
-#elif DMST_TRACK_CFG == 1
-constexpr int kTrackFwdL = 32, kTrackFwdNT = 128;   // 4096-sample tiles, small CTAs
-#ifndef DMST_BWD_MINB
-#define DMST_BWD_MINB 2
-#endif
-constexpr int kTrackBwdL = 16, kTrackBwdNT = 256, kTrackBwdMinB = DMST_BWD_MINB;
-#elif DMST_TRACK_CFG == 2
-constexpr int kTrackFwdL = 16, kTrackFwdNT = 256;   // 4096-sample tiles
-constexpr int kTrackBwdL = 16, kTrackBwdNT = 256, kTrackBwdMinB = 2;
-#elif DMST_TRACK_CFG == 3
-constexpr int kTrackFwdL = 16, kTrackFwdNT = 128;   // 2048-sample tiles
-constexpr int kTrackBwdL = 16, kTrackBwdNT = 128, kTrackBwdMinB = 4;
-#elif DMST_TRACK_CFG == 4                           // needs -DDMST_BWD_CHUNK=8
-constexpr int kTrackFwdL = 32, kTrackFwdNT = 128;   // 4096-sample tiles
-constexpr int kTrackBwdL = 8, kTrackBwdNT = 512, kTrackBwdMinB = 1;
-#else
-constexpr int kTrackFwdL = 32, kTrackFwdNT = 256;   // 8192-sample tiles, needs -DDMST_BWD_CHUNK=8
-constexpr int kTrackBwdL = 8, kTrackBwdNT = 1024, kTrackBwdMinB = 1;
-#endif
+constexpr int kTrackBwdL = 16, kTrackBwdNT = 512;
 constexpr int kMasterL = 16, kMasterNT = 256;       // 4096-sample tiles, 2 channels per thread
 // The master bus has few rows and is bound by the tile-to-tile chain: backward spreads a tile over
 // more threads (shorter chunks) to shorten every stage of that chain.
