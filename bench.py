@@ -334,6 +334,11 @@ def run_ours(args):
                     # from profiles/ (ncu --set full); None until a capture of this build exists
                     "traffic": TRAFFIC_TRACK_BWD_BYTES,
                     "kernel_ms": kern_ms,
+                    # honest co-limit: the kernel is bound by instruction issue, not by HBM:
+                    # executed warp-instructions of one launch (ncu, profiles/) / (4 schedulers x SMs x SM clock)
+                    "issue_rate": {"warp_instructions_per_launch": TRACK_BWD_WARP_INSTRUCTIONS,
+                                   "peak_warp_instructions_per_s": 4 * 148 * 1.965e9,
+                                   "frac": TRACK_BWD_WARP_INSTRUCTIONS / (kern_ms["track_bwd"] * 1e-3) / (4 * 148 * 1.965e9)},
                     "step_frac_of_hbm_roofline": (BYTES_FWD + BYTES_BWD) * samples / (ms_max / args.steps * 1e-3) / 1e9 / peak}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -362,9 +367,11 @@ def run_ours(args):
 GPU_LAUNCHES_PER_STEP = 20
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the track-backward kernel, one launch, from the
-# committed capture profiles/ncu_r1_summary.md (287.2 MB read + 28.8 MB written: the EQ-output and
+# committed capture profiles/ncu_r1_summary.md (287.4 MB read + 30.6 MB written: the EQ-output and
 # section-state checkpoints forward leaves for backward come on top of the 151 MB algorithmic)
-TRAFFIC_TRACK_BWD_BYTES = 316.0e6
+TRAFFIC_TRACK_BWD_BYTES = 318.0e6
+# smsp__inst_executed.sum of the same launch (profiles/ncu_r1_summary.md)
+TRACK_BWD_WARP_INSTRUCTIONS = 344.7e6
 
 
 def main():

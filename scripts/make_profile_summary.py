@@ -26,14 +26,14 @@ md = [f'# profiles/ - round {tag} (B200, ncu, `--clock-control none`)\n',
       'Workload: BASELINE configs[1] - AdvancedMixConsole fwd+bwd + MRSTFT, B=8, N=16, T=262144, float32, bus-only mode.\n',
       'Commands (under gpurun):\n```\n'
       f'ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step_{tag}.csv python scripts/prof_step.py 3\n'
-      f'ncu --set full --clock-control none --import-source on -k regex:chain -s 4 -c 4 -o gpurun_out/prof_{tag} python scripts/prof_once.py 8 16 262144 2\n'
-      'python scripts/sweep_eq_comp.py\npython bench.py --steps 50 --warmup 5 ; python bench.py --impl reference --steps 3 --warmup 1\n```\n',
+      f'ncu --set full --clock-control none --import-source on -k regex:"console_fwd|chain_bwd" -s 3 -c 3 -o gpurun_out/prof_{tag} python scripts/prof_once.py 8 16 262144 2\n'
+      'python scripts/sweep_eq_comp.py ; python scripts/conv_bench.py\npython bench.py --steps 50 --warmup 5 ; python bench.py --impl reference --steps 3 --warmup 1\n```\n',
       '## 1. Launch list of one step (ncu per-launch times are cold-cache and serialised: compare shares)\n',
       '| us | share | kernel |\n|---:|---:|---|']
 for n, v in step:
     md.append(f'| {v/1000:.1f} | {100*v/tot:.1f}% | `{n[:110]}` |')
 md.append(f'| **{tot/1000:.1f}** | 100% | total (device-timed step without a profiler: `bench_{tag}.json` `ms_per_step`) |\n')
-md.append('## 2. `ncu --set full` of the four console chain kernels (one launch each)\n')
+md.append('## 2. `ncu --set full` of the three console chain kernels (one launch each)\n')
 md.append('| kernel | us | regs | warps active % | SM throughput % | FMA pipe % | DRAM throughput % | DRAM read MB | DRAM write MB | warp-instructions |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|')
 for d in kern:
     f = lambda k: float(str(d[k]).replace(',', ''))
