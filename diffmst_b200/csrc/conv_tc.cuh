@@ -5,9 +5,14 @@
 // [P = B*(H+2)*(W+2) pixels, C channels].  The convolution is nine shifted GEMMs accumulated
 // into one TMEM tile:  out[p, n] = sum_{tap=(dy,dx)} sum_c in[p + dy*(W+2) + dx, c] * w[tap][n][c],
 // evaluated for every padded pixel index p (border outputs are overwritten with zeros, which is
-// exactly the zero border the next convolution needs).  So each A operand tile is a plain 2-D TMA
+// exactly the zero border the next convolution needs).  So an A operand tile is a plain 2-D TMA
 // box at a shifted row coordinate (out-of-range rows are zero-filled by TMA) and each B tile is
-// a box of the repacked weights [9*Cout, Cin].
+// a box of the repacked weights [9*Cout, Cin].  The three horizontal taps of one kernel row read
+// pixel rows that differ by one: ONE 136-row A tile per (kernel row, k-chunk) serves all three, the
+// MMA descriptors start 0, 1 and 2 rows (128 bytes) into it (the 128-byte swizzle is a function of the
+// absolute shared-memory address bits, so a start address that is not 1024-byte aligned reads the
+// rows TMA wrote - measured: the descriptor's base-offset field must stay 0).  That cuts the TMA traffic per tile by 1/3 - 2/5;
+// the kernel was bound by L2 -> shared-memory bandwidth, not by the tensor pipe.
 //
 // Kernel: one CTA per (128 pixels x BN channels) tile, 192 threads:
 //   warp 0     TMA producer   (cp.async.bulk.tensor.2d -> 128B-swizzled shared tiles, mbarrier tx)
@@ -28,7 +33,7 @@ namespace dmst {
 
 constexpr int kConvBM = 128;      // pixels per tile (UMMA M)
 constexpr int kConvBK = 32;       // float32 elements per 128-byte swizzled row
-constexpr int kConvStages = 4;
+constexpr int kConvARows = 136;   // A tile rows: 128 + 2 (horizontal taps), rounded up to the 8-row swizzle atom
 constexpr int kConvThreads = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,7 +111,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvArgs a) {
-    constexpr uint32_t kABytes = kConvBM * kConvBK * 4, kBBytes = BN * kConvBK * 4;
+    constexpr uint32_t kABytes = kConvARows * kConvBK * 4, kBBytes = BN * kConvBK * 4;
+    constexpr uint32_t kStageBytes = kABytes + 3 * kBBytes;   // one A tile + the weights of the 3 horizontal taps
+    constexpr int kConvStages = (BN == 128) ? 3 : 4;
     constexpr int kAcc = 2;  // TMEM accumulator stages
     extern __shared__ __align__(1024) unsigned char smem[];
     // 1024-byte aligned tiles (128B swizzle atoms)
@@ -115,7 +122,7 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kchunks = a.Cin / kConvBK, iters = 9 * kchunks;
+    const int kchunks = a.Cin / kConvBK, iters = 3 * kchunks;   // (kernel row, k-chunk) stages per tile
     const int tiles_n = a.Cout / BN;
     const int tiles_m = (a.P + kConvBM - 1) / kConvBM;
     const int num_tiles = tiles_m * tiles_n;
@@ -142,12 +149,14 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int it = 0; it < iters; ++it, ++g) {
                     const uint32_t s = g % kConvStages, round = g / kConvStages;
                     mbar_wait(&empty_bar[s], (round & 1) ^ 1);   // passes immediately on the first round
-                    const int tap = it / kchunks, kc = it - tap * kchunks;
-                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                    unsigned char* sa = tiles + (size_t)s * (kABytes + kBBytes);
-                    mbar_expect_tx(&full_bar[s], kABytes + kBBytes);
-                    tma_load_2d(sa, &map_a, &full_bar[s], kc * kConvBK, p0 + dy * a.Wp + dx);
-                    tma_load_2d(sa + kABytes, &map_b, &full_bar[s], kc * kConvBK, tap * a.Cout + n0);
+                    const int ky = it / kchunks, kc = it - ky * kchunks;
+                    unsigned char* sa = tiles + (size_t)s * kStageBytes;
+                    mbar_expect_tx(&full_bar[s], kStageBytes);
+                    // pixel rows p0 + (ky-1)*Wp - 1 ... + 135: horizontal tap kx reads rows kx ... kx+127 of this tile
+                    tma_load_2d(sa, &map_a, &full_bar[s], kc * kConvBK, p0 + (ky - 1) * a.Wp - 1);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+                        tma_load_2d(sa + kABytes + kx * kBBytes, &map_b, &full_bar[s], kc * kConvBK, (ky * 3 + kx) * a.Cout + n0);
                 }
             }
         }
@@ -164,12 +173,17 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const uint32_t s = g % kConvStages, round = g / kConvStages;
                     mbar_wait(&full_bar[s], round & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sa = smem_u32(tiles + (size_t)s * (kABytes + kBBytes));
-                    const uint64_t adesc = umma_smem_desc(sa), bdesc = umma_smem_desc(sa + kABytes);
+                    const uint32_t sa = smem_u32(tiles + (size_t)s * kStageBytes);
 #pragma unroll
-                    for (int k = 0; k < kConvBK / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address
-                        umma_tf32(tmem_d, adesc + (uint64_t)((k * 32) >> 4), bdesc + (uint64_t)((k * 32) >> 4), idesc,
-                                  (it | k) != 0);
+                    for (int kx = 0; kx < 3; ++kx) {
+                        // A: start kx rows (128 bytes each) into the tile
+                        const uint64_t adesc = umma_smem_desc(sa + kx * 128);
+                        const uint64_t bdesc = umma_smem_desc(sa + kABytes + kx * kBBytes);
+#pragma unroll
+                        for (int k = 0; k < kConvBK / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address
+                            umma_tf32(tmem_d, adesc + (uint64_t)((k * 32) >> 4), bdesc + (uint64_t)((k * 32) >> 4), idesc,
+                                      (it | kx | k) != 0);
+                    }
                     umma_commit(&empty_bar[s]);           // stage free once these MMAs have read it
                 }
                 umma_commit(&tmem_full_bar[acc]);          // accumulator complete
@@ -391,7 +405,7 @@ inline int conv3x3_forward(const float* x_padded, const float* w9, const float* 
     }
     const int BN = (Cout % 128 == 0) ? 128 : 64;
     CUtensorMap ma, mb;
-    int e = make_map_2d(&ma, x_padded, (uint64_t)P, (uint64_t)Cin, kConvBM);
+    int e = make_map_2d(&ma, x_padded, (uint64_t)P, (uint64_t)Cin, kConvARows);
     if (e) return e;
     e = make_map_2d(&mb, w9, (uint64_t)9 * Cout, (uint64_t)Cin, (uint32_t)BN);
     if (e) return e;
@@ -404,7 +418,7 @@ inline int conv3x3_forward(const float* x_padded, const float* w9, const float* 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));  // persistent: one CTA per SM
-    const size_t smem = (size_t)kConvStages * (kConvBM * kConvBK * 4 + BN * kConvBK * 4) + 1024;
+    const size_t smem = (size_t)(BN == 128 ? 3 : 4) * (kConvARows * kConvBK * 4 + 3 * BN * kConvBK * 4) + 1024;
     if (BN == 128) {
         e = (int)cudaFuncSetAttribute(conv3x3_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e) return e;
