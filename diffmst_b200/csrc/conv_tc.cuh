@@ -108,12 +108,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // fastest, so CTAs running at the same time share A tiles in L2).  The shared-memory ring and
 // its barriers run continuously across tiles; the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
-template <int BN>
+__host__ __device__ constexpr int conv_stage_bytes(int BN, int MT) { return MT * kConvARows * kConvBK * 4 + 3 * BN * kConvBK * 4; }
+__host__ __device__ constexpr int conv_stages(int BN, int MT) {
+    return (220 * 1024 / conv_stage_bytes(BN, MT)) > 4 ? 4 : (220 * 1024 / conv_stage_bytes(BN, MT));
+}
+
+// MT = 1 or 2 pixel sub-tiles of 128 per CTA tile: with MT = 2 the weight tiles of a stage feed two
+// accumulators, which halves the weight traffic per flop (the big layers are bound by L2 -> shared
+// memory bandwidth); small layers keep MT = 1 to have enough tiles for all SMs.
+template <int BN, int MT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvArgs a) {
     constexpr uint32_t kABytes = kConvARows * kConvBK * 4, kBBytes = BN * kConvBK * 4;
-    constexpr uint32_t kStageBytes = kABytes + 3 * kBBytes;   // one A tile + the weights of the 3 horizontal taps
-    constexpr int kConvStages = (BN == 128) ? 3 : 4;
+    constexpr uint32_t kStageBytes = MT * kABytes + 3 * kBBytes;   // MT A tiles + the weights of the 3 horizontal taps
+    constexpr int kConvStages = conv_stages(BN, MT);
+    constexpr int kTileM = MT * kConvBM;
     constexpr int kAcc = 2;  // TMEM accumulator stages
     extern __shared__ __align__(1024) unsigned char smem[];
     // 1024-byte aligned tiles (128B swizzle atoms)
@@ -124,7 +133,7 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kchunks = a.Cin / kConvBK, iters = 3 * kchunks;   // (kernel row, k-chunk) stages per tile
     const int tiles_n = a.Cout / BN;
-    const int tiles_m = (a.P + kConvBM - 1) / kConvBM;
+    const int tiles_m = (a.P + kTileM - 1) / kTileM;
     const int num_tiles = tiles_m * tiles_n;
 
     if (threadIdx.x == 0) {
@@ -132,8 +141,8 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int s = 0; s < kAcc; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: kAcc x BN FP32 accumulator columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(kAcc * BN));
+    if (warp == 1) {  // TMEM: kAcc x MT x BN FP32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(kAcc * MT * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -145,7 +154,7 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             uint32_t g = 0;  // ring position, continuous across tiles
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int p0 = (tile / tiles_n) * kConvBM, n0 = (tile % tiles_n) * BN;
+                const int p0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
                 for (int it = 0; it < iters; ++it, ++g) {
                     const uint32_t s = g % kConvStages, round = g / kConvStages;
                     mbar_wait(&empty_bar[s], (round & 1) ^ 1);   // passes immediately on the first round
@@ -153,10 +162,12 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     unsigned char* sa = tiles + (size_t)s * kStageBytes;
                     mbar_expect_tx(&full_bar[s], kStageBytes);
                     // pixel rows p0 + (ky-1)*Wp - 1 ... + 135: horizontal tap kx reads rows kx ... kx+127 of this tile
-                    tma_load_2d(sa, &map_a, &full_bar[s], kc * kConvBK, p0 + (ky - 1) * a.Wp - 1);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        tma_load_2d(sa + m * kABytes, &map_a, &full_bar[s], kc * kConvBK, p0 + m * kConvBM + (ky - 1) * a.Wp - 1);
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx)
-                        tma_load_2d(sa + kABytes + kx * kBBytes, &map_b, &full_bar[s], kc * kConvBK, (ky * 3 + kx) * a.Cout + n0);
+                        tma_load_2d(sa + MT * kABytes + kx * kBBytes, &map_b, &full_bar[s], kc * kConvBK, (ky * 3 + kx) * a.Cout + n0);
                 }
             }
         }
@@ -168,7 +179,7 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const uint32_t acc = t % kAcc;
                 mbar_wait(&tmem_empty_bar[acc], ((t / kAcc) & 1) ^ 1);   // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tmem_d = tmem_base + acc * BN;
+                const uint32_t tmem_d = tmem_base + acc * (MT * BN);
                 for (int it = 0; it < iters; ++it, ++g) {
                     const uint32_t s = g % kConvStages, round = g / kConvStages;
                     mbar_wait(&full_bar[s], round & 1);
@@ -176,13 +187,16 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const uint32_t sa = smem_u32(tiles + (size_t)s * kStageBytes);
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
-                        // A: start kx rows (128 bytes each) into the tile
-                        const uint64_t adesc = umma_smem_desc(sa + kx * 128);
-                        const uint64_t bdesc = umma_smem_desc(sa + kABytes + kx * kBBytes);
+                        const uint64_t bdesc = umma_smem_desc(sa + MT * kABytes + kx * kBBytes);
 #pragma unroll
-                        for (int k = 0; k < kConvBK / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address
-                            umma_tf32(tmem_d, adesc + (uint64_t)((k * 32) >> 4), bdesc + (uint64_t)((k * 32) >> 4), idesc,
-                                      (it | kx | k) != 0);
+                        for (int m = 0; m < MT; ++m) {
+                            // A: start kx rows (128 bytes each) into the sub-tile
+                            const uint64_t adesc = umma_smem_desc(sa + m * kABytes + kx * 128);
+#pragma unroll
+                            for (int k = 0; k < kConvBK / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address
+                                umma_tf32(tmem_d + m * BN, adesc + (uint64_t)((k * 32) >> 4), bdesc + (uint64_t)((k * 32) >> 4),
+                                          idesc, (it | kx | k) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[s]);           // stage free once these MMAs have read it
                 }
@@ -194,52 +208,55 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int quarter = warp & 3;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-            const int p0 = (tile / tiles_n) * kConvBM, n0 = (tile % tiles_n) * BN;
+            const int p0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
             const uint32_t acc = t % kAcc;
             mbar_wait(&tmem_full_bar[acc], (t / kAcc) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int p = p0 + quarter * 32 + lane;
-            bool interior = false;
-            if (p < a.P) {
-                const int rem = p % (a.Hp * a.Wp);
-                const int hp = rem / a.Wp, wp = rem - hp * a.Wp;
-                interior = hp >= 1 && hp <= a.Hp - 2 && wp >= 1 && wp <= a.Wp - 2;
-            }
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + (uint32_t)c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 32 >= BN) {  // accumulator fully read: hand it back to the MMA warp before the stores
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-                }
+            for (int m = 0; m < MT; ++m) {
+                const int p = p0 + m * kConvBM + quarter * 32 + lane;
+                bool interior = false;
                 if (p < a.P) {
-                    float* o = a.out + (size_t)p * a.Cout + n0 + c0;
+                    const int rem = p % (a.Hp * a.Wp);
+                    const int hp = rem / a.Wp, wp = rem - hp * a.Wp;
+                    interior = hp >= 1 && hp <= a.Hp - 2 && wp >= 1 && wp <= a.Wp - 2;
+                }
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (MT * BN) + m * BN + (uint32_t)c0;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (m == MT - 1 && c0 + 32 >= BN) {  // accumulator fully read: hand it back to the MMA warp before the stores
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                    }
+                    if (p < a.P) {
+                        float* o = a.out + (size_t)p * a.Cout + n0 + c0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 v;
-                        float* vv = reinterpret_cast<float*>(&v);
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 v;
+                            float* vv = reinterpret_cast<float*>(&v);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float x = __int_as_float((int)r[j + q]);
-                            const int n = n0 + c0 + j + q;
-                            if (a.scale) x *= __ldg(a.scale + n);
-                            if (a.shift) x += __ldg(a.shift + n);
-                            if (a.relu) x = fmaxf(x, 0.0f);
-                            vv[q] = interior ? x : 0.0f;
+                            for (int q = 0; q < 4; ++q) {
+                                float x = __int_as_float((int)r[j + q]);
+                                const int n = n0 + c0 + j + q;
+                                if (a.scale) x *= __ldg(a.scale + n);
+                                if (a.shift) x += __ldg(a.shift + n);
+                                if (a.relu) x = fmaxf(x, 0.0f);
+                                vv[q] = interior ? x : 0.0f;
+                            }
+                            *reinterpret_cast<float4*>(o + j) = v;
                         }
-                        *reinterpret_cast<float4*>(o + j) = v;
                     }
                 }
             }
@@ -247,7 +264,7 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAcc * BN));
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAcc * MT * BN));
 }
 
 // ---- small helper kernels around the tensor-core convolution ----
@@ -410,24 +427,27 @@ inline int conv3x3_forward(const float* x_padded, const float* w9, const float* 
     e = make_map_2d(&mb, w9, (uint64_t)9 * Cout, (uint64_t)Cin, (uint32_t)BN);
     if (e) return e;
     ConvArgs a{(int)P, Hp, Wp, Cin, Cout, scale, shift, relu, y_padded};
-    const long long num_tiles = ((P + kConvBM - 1) / kConvBM) * (Cout / BN);
     int sms = 148;
     {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    // two pixel sub-tiles per CTA tile when that still leaves at least two waves of tiles
+    const long long tiles1 = ((P + kConvBM - 1) / kConvBM) * (Cout / BN);
+    const int MT = (tiles1 >= 4LL * sms) ? 2 : 1;
+    const long long num_tiles = ((P + MT * kConvBM - 1) / (MT * kConvBM)) * (Cout / BN);
     const dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));  // persistent: one CTA per SM
-    const size_t smem = (size_t)(BN == 128 ? 3 : 4) * (kConvARows * kConvBK * 4 + 3 * BN * kConvBK * 4) + 1024;
-    if (BN == 128) {
-        e = (int)cudaFuncSetAttribute(conv3x3_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e) return e;
-        conv3x3_tf32_kernel<128><<<grid, kConvThreads, smem, stream>>>(ma, mb, a);
-    } else {
-        e = (int)cudaFuncSetAttribute(conv3x3_tf32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e) return e;
-        conv3x3_tf32_kernel<64><<<grid, kConvThreads, smem, stream>>>(ma, mb, a);
-    }
+    auto launch = [&](auto kern, int bn, int mt) -> int {
+        const size_t smem = (size_t)conv_stages(bn, mt) * conv_stage_bytes(bn, mt) + 1024;
+        int err = (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err) return err;
+        kern<<<grid, kConvThreads, smem, stream>>>(ma, mb, a);
+        return 0;
+    };
+    if (BN == 128) e = (MT == 2) ? launch(conv3x3_tf32_kernel<128, 2>, 128, 2) : launch(conv3x3_tf32_kernel<128, 1>, 128, 1);
+    else e = (MT == 2) ? launch(conv3x3_tf32_kernel<64, 2>, 64, 2) : launch(conv3x3_tf32_kernel<64, 1>, 64, 1);
+    if (e) return e;
     return (int)cudaGetLastError();
 }
 

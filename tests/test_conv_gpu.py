@@ -129,8 +129,10 @@ def test_conv3x3_function_gradients_single_layer():
 def test_cnn14_backward_small():
     from diffmst_b200 import Cnn14
     g = torch.Generator().manual_seed(3)
-    ref = OracleCnn14(num_classes=32).cuda().train()
-    ours = Cnn14(num_classes=32).cuda().train()
+    # running-statistics BatchNorm: the last blocks see 1x2 / 1x1 maps, where batch statistics over two items are
+    # ill-conditioned (batch-statistics BatchNorm is covered per block in test_conv_block_backward)
+    ref = OracleCnn14(num_classes=32).cuda().eval()
+    ours = Cnn14(num_classes=32).cuda().eval()
     ours.load_state_dict(ref.state_dict(), strict=True)
     x = (torch.rand(2, 1, 1024, 128, generator=g) ** 2).cuda()   # smallest input that survives the six poolings
     want, got = ref(x), ours(x)
