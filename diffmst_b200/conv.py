@@ -39,12 +39,23 @@ def _to_padded_nhwc(x):
     return y
 
 
+_REPACK_CACHE = {}   # id(parameter) -> (data_ptr, version, [9][Cout][Cin] tensor); refreshed when the weight changes
+
+
 def _repack(w):
+    """[Cout][Cin][3][3] -> [9][Cout][Cin], cached until the parameter is modified (inference repacks once)."""
+    key = id(w)
+    hit = _REPACK_CACHE.get(key)
+    if hit is not None and hit[0] == w.data_ptr() and hit[1] == w._version and hit[2].device == w.device:
+        return hit[2]
     lib = _lib.lib()
     Cout, Cin = w.shape[0], w.shape[1]
     w9 = torch.empty(9, Cout, Cin, dtype=torch.float32, device=w.device)
     _lib.check(lib.dmst_conv_repack_weights(_ptr(w.detach().contiguous()), _ptr(w9), Cout, Cin, _stream(w.device)),
                "dmst_conv_repack_weights")
+    if len(_REPACK_CACHE) > 256:
+        _REPACK_CACHE.clear()
+    _REPACK_CACHE[key] = (w.data_ptr(), w._version, w9)
     return w9
 
 

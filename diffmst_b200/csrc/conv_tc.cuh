@@ -309,11 +309,85 @@ __global__ void conv3x3_direct_kernel(const float* x, const float* w9 /*[9][Cout
     }
 }
 
+// First layer (Cin = 1 spectrogram channel; any Cin <= 4 with Cout % 4 == 0): the output write is the whole
+// cost, so this is a streaming kernel: weights and the affine in shared memory, each thread produces 4
+// consecutive output channels of one pixel (a warp writes whole 128-byte lines), inputs are warp-broadcast.
+constexpr int kSmallCinMax = 4;
+__global__ void conv3x3_small_cin_kernel(const float* x, const float* w9 /*[9][Cout][Cin]*/, const float* scale,
+                                         const float* shift, float* y, int P, int Hp, int Wp, int Cin, int Cout, int relu) {
+    extern __shared__ float sm_w[];   // [9][Cin][Cout] (channel fastest), then scale[Cout], shift[Cout]
+    float* sm_scale = sm_w + 9 * Cin * Cout;
+    float* sm_shift = sm_scale + Cout;
+    for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) {
+        const int n = i % Cout, c = (i / Cout) % Cin, tap = i / (Cout * Cin);
+        sm_w[i] = __ldg(w9 + ((long long)tap * Cout + n) * Cin + c);
+    }
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) {
+        sm_scale[i] = scale ? __ldg(scale + i) : 1.0f;
+        sm_shift[i] = shift ? __ldg(shift + i) : 0.0f;
+    }
+    __syncthreads();
+    const int groups = Cout >> 2;                          // float4 channel groups per pixel
+    const int pix_per_block = blockDim.x / groups;
+    const int g = threadIdx.x % groups, lp = threadIdx.x / groups;
+    if (lp >= pix_per_block) return;
+    for (long long p = (long long)blockIdx.x * pix_per_block + lp; p < P; p += (long long)gridDim.x * pix_per_block) {
+        const int rem = (int)(p % ((long long)Hp * Wp));
+        const int hp = rem / Wp, wp = rem - hp * Wp;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const long long q = p + (tap / 3 - 1) * Wp + (tap % 3 - 1);
+                for (int c = 0; c < Cin; ++c) {
+                    const float xv = __ldg(x + q * Cin + c);
+                    const float4 w = *reinterpret_cast<const float4*>(sm_w + (tap * Cin + c) * Cout + 4 * g);
+                    acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y);
+                    acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
+                }
+            }
+            const float4 sc = *reinterpret_cast<const float4*>(sm_scale + 4 * g);
+            const float4 sh = *reinterpret_cast<const float4*>(sm_shift + 4 * g);
+            acc.x = fmaf(acc.x, sc.x, sh.x); acc.y = fmaf(acc.y, sc.y, sh.y);
+            acc.z = fmaf(acc.z, sc.z, sh.z); acc.w = fmaf(acc.w, sc.w, sh.w);
+            if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        }
+        *reinterpret_cast<float4*>(y + p * Cout + 4 * g) = acc;
+    }
+}
+
 // average pool (kh x kw, stride = kernel, floor) of padded NHWC -> NCHW (B, C, H/kh, W/kw) or padded NHWC
 __global__ void avgpool_kernel(const float* x, float* y, int B, int C, int H, int W, int kh, int kw, int out_nhwc_padded) {
     const int Ho = H / kh, Wo = W / kw, Hp = H + 2, Wp = W + 2;
-    const long long total = (long long)B * Ho * Wo * C;
     const float inv = 1.0f / (float)(kh * kw);
+    if ((C & 3) == 0) {
+        // one thread per (output pixel, 4 channels): 128-bit loads over the window, channel-fastest => coalesced
+        const int C4 = C >> 2;
+        const long long total = (long long)B * Ho * Wo * C4;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int c = (int)(i % C4) << 2;
+            long long r = i / C4;
+            const int wo = (int)(r % Wo); r /= Wo;
+            const int ho = (int)(r % Ho);
+            const int b = (int)(r / Ho);
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* base = x + (((long long)b * Hp + (ho * kh + 1)) * Wp + (wo * kw + 1)) * C + c;
+            for (int dy = 0; dy < kh; ++dy)
+                for (int dx = 0; dx < kw; ++dx) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((long long)dy * Wp + dx) * C));
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                }
+            s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+            if (out_nhwc_padded) {
+                *reinterpret_cast<float4*>(y + (((long long)b * (Ho + 2) + ho + 1) * (Wo + 2) + wo + 1) * C + c) = s;
+            } else {
+                const long long o = (((long long)b * C + c) * Ho + ho) * Wo + wo, cs = (long long)Ho * Wo;
+                y[o] = s.x; y[o + cs] = s.y; y[o + 2 * cs] = s.z; y[o + 3 * cs] = s.w;
+            }
+        }
+        return;
+    }
+    const long long total = (long long)B * Ho * Wo * C;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         long long r = i / C;
@@ -414,6 +488,14 @@ inline int conv3x3_forward(const float* x_padded, const float* w9, const float* 
     const int Hp = H + 2, Wp = W + 2;
     const long long P = (long long)B * Hp * Wp;
     if (P > 0x7fffffffLL) return DMST_EINVAL;
+    if (Cin <= kSmallCinMax && Cout % 4 == 0 && Cout <= 256 && 256 % (Cout / 4) == 0) {   // first layer: streaming kernel
+        const int pix_per_block = 256 / (Cout / 4);
+        const long long blocks_needed = (P + pix_per_block - 1) / pix_per_block;
+        const int blocks = (int)(blocks_needed > 148LL * 16 ? 148 * 16 : blocks_needed);
+        const size_t smem = (size_t)(9 * Cin * Cout + 2 * Cout) * sizeof(float);
+        conv3x3_small_cin_kernel<<<blocks, 256, smem, stream>>>(x_padded, w9, scale, shift, y_padded, (int)P, Hp, Wp, Cin, Cout, relu);
+        return (int)cudaGetLastError();
+    }
     if (Cin % kConvBK != 0 || Cout % 64 != 0) {   // small / odd channel counts: CUDA-core path
         const long long total = P * Cout;
         const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);

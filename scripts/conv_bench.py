@@ -49,3 +49,26 @@ for cin, cout, H, W in layers:
     tot_ref = globals().get("tot_ref", 0.0) + best; globals()["tot_ref"] = tot_ref
     print(f"conv {cin:5d}->{cout:5d} @ {H:4d}x{W:3d} x{B}: ours {ms*1e3:8.1f} us {flop/ms/1e9:7.1f} TFLOP/s ({flop/ms/1e9/tf32_peak*100:5.1f}% of {tf32_peak:.0f} TF32 = measured bf16/2) | cuDNN(tf32) {best*1e3:8.1f} us {flop/best/1e9:7.1f} TFLOP/s", flush=True)
 print(f"total ours {tot_ms:.3f} ms ({tot_flop/tot_ms/1e9:.1f} TFLOP/s) | cuDNN conv only {tot_ref:.3f} ms ({tot_flop/tot_ref/1e9:.1f} TFLOP/s) for {tot_flop/1e12:.2f} TFLOP (ours includes the BN+ReLU epilogue)")
+
+# ---- whole trunk, apples to apples: the reference's path is conv2d (cuDNN, TF32 allowed) + BatchNorm2d + ReLU +
+# avg_pool2d as separate kernels (mst/panns.py:49-85); ours fuses BN + ReLU into the convolution epilogue ----
+from diffmst_b200 import Cnn14
+from oracle.panns import OracleCnn14
+torch.backends.cudnn.allow_tf32 = True; torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.benchmark = True
+ref = OracleCnn14(num_classes=512).to(dev).eval()
+ours = Cnn14(num_classes=512).to(dev).eval()
+ours.load_state_dict(ref.state_dict())
+xs = (torch.rand(B, 1, 1025, 257, device=dev) ** 3)
+def timeit(fn, n=5):
+    with torch.no_grad():
+        for _ in range(2): fn()
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(n): fn()
+        ev[1].record(); torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / n
+t_ours = timeit(lambda: ours(xs))
+t_ref = timeit(lambda: ref(xs))
+t_ref_cl = timeit(lambda: ref.to(memory_format=torch.channels_last)(xs.contiguous(memory_format=torch.channels_last)))
+print(f"Cnn14 forward (eval), batch {B} x 1025 x 257: ours {t_ours:.3f} ms | reference modules (cuDNN TF32 + separate BN/ReLU/pool) "
+      f"{t_ref:.3f} ms NCHW, {t_ref_cl:.3f} ms channels_last", flush=True)
