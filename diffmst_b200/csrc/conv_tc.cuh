@@ -331,16 +331,17 @@ __global__ void conv3x3_small_cin_kernel(const float* x, const float* w9 /*[9][C
     const int pix_per_block = blockDim.x / groups;
     const int g = threadIdx.x % groups, lp = threadIdx.x / groups;
     if (lp >= pix_per_block) return;
-    for (long long p = (long long)blockIdx.x * pix_per_block + lp; p < P; p += (long long)gridDim.x * pix_per_block) {
-        const int rem = (int)(p % ((long long)Hp * Wp));
+    const int plane = Hp * Wp;
+    for (int p = blockIdx.x * pix_per_block + lp; p < P; p += gridDim.x * pix_per_block) {   // P < 2^31 (checked on the host)
+        const int rem = p % plane;
         const int hp = rem / Wp, wp = rem - hp * Wp;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                const long long q = p + (tap / 3 - 1) * Wp + (tap % 3 - 1);
+                const int q = p + (tap / 3 - 1) * Wp + (tap % 3 - 1);
                 for (int c = 0; c < Cin; ++c) {
-                    const float xv = __ldg(x + q * Cin + c);
+                    const float xv = __ldg(x + (long long)q * Cin + c);
                     const float4 w = *reinterpret_cast<const float4*>(sm_w + (tap * Cin + c) * Cout + 4 * g);
                     acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y);
                     acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
@@ -352,7 +353,44 @@ __global__ void conv3x3_small_cin_kernel(const float* x, const float* w9 /*[9][C
             acc.z = fmaf(acc.z, sc.z, sh.z); acc.w = fmaf(acc.w, sc.w, sh.w);
             if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
         }
-        *reinterpret_cast<float4*>(y + p * Cout + 4 * g) = acc;
+        *reinterpret_cast<float4*>(y + (long long)p * Cout + 4 * g) = acc;
+    }
+}
+
+// Cin == 1 specialisation of the streaming first-layer kernel: the 9 x 4 weights and the affine of a thread's
+// channel group live in registers for its whole life; per pixel that leaves 9 loads, 36 FMAs and one 16-byte store.
+__global__ void __launch_bounds__(256) conv3x3_cin1_kernel(const float* __restrict__ x, const float* __restrict__ w9 /*[9][Cout]*/,
+                                                           const float* scale, const float* shift, float* __restrict__ y,
+                                                           int P, int Hp, int Wp, int Cout, int relu) {
+    const int groups = Cout >> 2;
+    const int pix_per_block = blockDim.x / groups;
+    const int g = threadIdx.x % groups, lp = threadIdx.x / groups;
+    if (lp >= pix_per_block) return;
+    float4 w[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) w[tap] = __ldg(reinterpret_cast<const float4*>(w9 + tap * Cout + 4 * g));
+    const float4 sc = scale ? __ldg(reinterpret_cast<const float4*>(scale + 4 * g)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 sh = shift ? __ldg(reinterpret_cast<const float4*>(shift + 4 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int plane = Hp * Wp;
+    for (int p = blockIdx.x * pix_per_block + lp; p < P; p += gridDim.x * pix_per_block) {   // P < 2^31 (checked on the host)
+        const int rem = p % plane;
+        const int hp = rem / Wp, wp = rem - hp * Wp;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2) {
+            const float* xp = x + p;
+            float xv[9];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) xv[tap] = __ldg(xp + (tap / 3 - 1) * Wp + (tap % 3 - 1));
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                acc.x = fmaf(xv[tap], w[tap].x, acc.x); acc.y = fmaf(xv[tap], w[tap].y, acc.y);
+                acc.z = fmaf(xv[tap], w[tap].z, acc.z); acc.w = fmaf(xv[tap], w[tap].w, acc.w);
+            }
+            acc.x = fmaf(acc.x, sc.x, sh.x); acc.y = fmaf(acc.y, sc.y, sh.y);
+            acc.z = fmaf(acc.z, sc.z, sh.z); acc.w = fmaf(acc.w, sc.w, sh.w);
+            if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        }
+        *reinterpret_cast<float4*>(y + (long long)p * Cout + 4 * g) = acc;
     }
 }
 
@@ -365,11 +403,12 @@ __global__ void avgpool_kernel(const float* x, float* y, int B, int C, int H, in
         const int C4 = C >> 2;
         const long long total = (long long)B * Ho * Wo * C4;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-            const int c = (int)(i % C4) << 2;
-            long long r = i / C4;
-            const int wo = (int)(r % Wo); r /= Wo;
-            const int ho = (int)(r % Ho);
-            const int b = (int)(r / Ho);
+            const unsigned pix = (unsigned)(i / (unsigned)C4);          // output pixel index < 2^31
+            const int c = (int)(i - (long long)pix * C4) << 2;
+            const unsigned row = pix / (unsigned)Wo;
+            const int wo = (int)(pix - row * Wo);
+            const int b = (int)(row / (unsigned)Ho);
+            const int ho = (int)(row - (unsigned)b * Ho);
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
             const float* base = x + (((long long)b * Hp + (ho * kh + 1)) * Wp + (wo * kw + 1)) * C + c;
             for (int dy = 0; dy < kh; ++dy)
@@ -492,6 +531,10 @@ inline int conv3x3_forward(const float* x_padded, const float* w9, const float* 
         const int pix_per_block = 256 / (Cout / 4);
         const long long blocks_needed = (P + pix_per_block - 1) / pix_per_block;
         const int blocks = (int)(blocks_needed > 148LL * 16 ? 148 * 16 : blocks_needed);
+        if (Cin == 1) {
+            conv3x3_cin1_kernel<<<blocks, 256, 0, stream>>>(x_padded, w9, scale, shift, y_padded, (int)P, Hp, Wp, Cout, relu);
+            return (int)cudaGetLastError();
+        }
         const size_t smem = (size_t)(9 * Cin * Cout + 2 * Cout) * sizeof(float);
         conv3x3_small_cin_kernel<<<blocks, 256, smem, stream>>>(x_padded, w9, scale, shift, y_padded, (int)P, Hp, Wp, Cin, Cout, relu);
         return (int)cudaGetLastError();
