@@ -75,6 +75,10 @@ def lib():
     l.dmst_conv_repack_weights.argtypes = [vp, vp, i, i, vp]
     l.dmst_conv3x3_forward.restype = i
     l.dmst_conv3x3_forward.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    l.dmst_conv3x3_workspace_bytes.restype = sz
+    l.dmst_conv3x3_workspace_bytes.argtypes = [i, i, i, i, i]
+    l.dmst_conv3x3_forward_ws.restype = i
+    l.dmst_conv3x3_forward_ws.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz, vp]
     l.dmst_conv_stats_workspace_bytes.restype = sz
     l.dmst_conv_stats_workspace_bytes.argtypes = [i, i, i, i]
     l.dmst_conv_channel_stats.restype = i

@@ -59,6 +59,15 @@ def _repack(w):
     return w9
 
 
+def _conv3x3(x_pad, w9, scale, shift, y, B, H, W, Cin, Cout, relu, what="dmst_conv3x3_forward"):
+    """One tensor-core convolution call (split-K workspace allocated on demand for the small deep layers)."""
+    lib = _lib.lib()
+    nbytes = lib.dmst_conv3x3_workspace_bytes(B, H, W, Cin, Cout)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x_pad.device) if nbytes else None
+    _lib.check(lib.dmst_conv3x3_forward_ws(_ptr(x_pad), _ptr(w9), _ptr(scale), _ptr(shift), _ptr(y), B, H, W, Cin, Cout,
+                                           relu, _ptr(ws), nbytes, _stream(x_pad.device)), what)
+
+
 def _conv_bn_relu(x_pad, conv: nn.Conv2d, bn, training: bool):
     """x_pad (B, H+2, W+2, Cin) -> relu(bn(conv(x))) as (B, H+2, W+2, Cout)."""
     lib = _lib.lib()
@@ -73,16 +82,13 @@ def _conv_bn_relu(x_pad, conv: nn.Conv2d, bn, training: bool):
     if is_bn and not use_batch_stats:
         scale = (bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)).float().contiguous()
         shift = (bn.bias.detach() - bn.running_mean * scale).float().contiguous()
-        _lib.check(lib.dmst_conv3x3_forward(_ptr(x_pad), _ptr(w9), _ptr(scale), _ptr(shift), _ptr(y), B, H, W, Cin,
-                                            Cout, 1, _stream(dev)), "dmst_conv3x3_forward")
+        _conv3x3(x_pad, w9, scale, shift, y, B, H, W, Cin, Cout, 1)
         return y
     if not is_bn:
-        _lib.check(lib.dmst_conv3x3_forward(_ptr(x_pad), _ptr(w9), None, None, _ptr(y), B, H, W, Cin, Cout, 1,
-                                            _stream(dev)), "dmst_conv3x3_forward")
+        _conv3x3(x_pad, w9, None, None, y, B, H, W, Cin, Cout, 1)
         return y
     # training-mode BatchNorm: raw conv -> batch statistics -> affine + ReLU in place
-    _lib.check(lib.dmst_conv3x3_forward(_ptr(x_pad), _ptr(w9), None, None, _ptr(y), B, H, W, Cin, Cout, 0,
-                                        _stream(dev)), "dmst_conv3x3_forward")
+    _conv3x3(x_pad, w9, None, None, y, B, H, W, Cin, Cout, 0)
     nbytes = lib.dmst_conv_stats_workspace_bytes(B, H, W, Cout)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     mean = torch.empty(Cout, dtype=torch.float32, device=dev)
@@ -114,8 +120,7 @@ class _Conv3x3Function(torch.autograd.Function):
         x_pad = x_pad.contiguous()
         w9 = _repack(weight)
         z = torch.empty(B, Hp, Wp, Cout, dtype=torch.float32, device=x_pad.device)
-        _lib.check(lib.dmst_conv3x3_forward(_ptr(x_pad), _ptr(w9), None, None, _ptr(z), B, Hp - 2, Wp - 2, Cin, Cout, 0,
-                                            _stream(x_pad.device)), "dmst_conv3x3_forward")
+        _conv3x3(x_pad, w9, None, None, z, B, Hp - 2, Wp - 2, Cin, Cout, 0)
         ctx.save_for_backward(x_pad, w9)
         return z
 
@@ -133,8 +138,7 @@ class _Conv3x3Function(torch.autograd.Function):
             # dgrad: correlation with the flipped taps, channel roles swapped -> the same kernel
             w9t = w9.flip(0).transpose(1, 2).contiguous()          # [tap][Cin][Cout]
             gx = torch.empty_like(x_pad)
-            _lib.check(lib.dmst_conv3x3_forward(_ptr(gz), _ptr(w9t), None, None, _ptr(gx), B, Hp - 2, Wp - 2, Cout, Cin, 0,
-                                                _stream(gz.device)), "dmst_conv3x3_forward (dgrad)")
+            _conv3x3(gz, w9t, None, None, gx, B, Hp - 2, Wp - 2, Cout, Cin, 0, "dmst_conv3x3_forward (dgrad)")
         if ctx.needs_input_grad[1]:
             # wgrad: dW[tap] = dz^T @ x shifted by the tap (a constant row offset in the flattened layout;
             # dz is zero on the border, so rows that would cross an image edge contribute nothing)

@@ -164,6 +164,16 @@ int dmst_conv3x3_forward(const float* x_padded, const float* w9, const float* sc
     return dmst::conv3x3_forward(x_padded, w9, scale, shift, y_padded, B, H, W, Cin, Cout, relu,
                                  reinterpret_cast<cudaStream_t>(stream));
 }
+size_t dmst_conv3x3_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return 0;
+    return dmst::conv3x3_workspace_bytes(B, H, W, Cin, Cout);
+}
+int dmst_conv3x3_forward_ws(const float* x_padded, const float* w9, const float* scale, const float* shift, float* y_padded,
+                            int B, int H, int W, int Cin, int Cout, int relu, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    return dmst::conv3x3_forward(x_padded, w9, scale, shift, y_padded, B, H, W, Cin, Cout, relu,
+                                 reinterpret_cast<cudaStream_t>(stream), workspace, workspace_bytes);
+}
 size_t dmst_conv_stats_workspace_bytes(int B, int H, int W, int C) {
     const long long P = (long long)B * (H + 2) * (W + 2);
     return (size_t)((P + dmst::kStatRows - 1) / dmst::kStatRows) * 2 * C * sizeof(float);
@@ -200,6 +210,8 @@ int dmst_conv_avgpool(const float* x_padded, float* y, int B, int C, int H, int 
 int dmst_conv_nchw_to_padded_nhwc(const float*, float*, int, int, int, int, void*) { return DMST_EINVAL; }
 int dmst_conv_repack_weights(const float*, float*, int, int, void*) { return DMST_EINVAL; }
 int dmst_conv3x3_forward(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, void*) { return DMST_EINVAL; }
+size_t dmst_conv3x3_workspace_bytes(int, int, int, int, int) { return 0; }
+int dmst_conv3x3_forward_ws(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, void*, size_t, void*) { return DMST_EINVAL; }
 size_t dmst_conv_stats_workspace_bytes(int, int, int, int) { return 0; }
 int dmst_conv_channel_stats(const float*, int, int, int, int, float*, float*, void*, size_t, void*) { return DMST_EINVAL; }
 int dmst_conv_affine_relu(float*, const float*, const float*, int, int, int, int, int, void*) { return DMST_EINVAL; }

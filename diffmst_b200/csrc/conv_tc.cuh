@@ -98,6 +98,8 @@ struct ConvArgs {
     const float* shift;   // [Cout] or null (= 0)
     int relu;
     float* out;       // [P][Cout], zero border written
+    int ksplit;       // > 1: the (kernel row, k-chunk) stages of a tile are split over `ksplit` work items, each
+    float* partial;   //      writing its raw accumulator to partial[split][P][Cout] (summed by conv_splitk_reduce_kernel)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -134,7 +136,8 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int kchunks = a.Cin / kConvBK, iters = 3 * kchunks;   // (kernel row, k-chunk) stages per tile
     const int tiles_n = a.Cout / BN;
     const int tiles_m = (a.P + kTileM - 1) / kTileM;
-    const int num_tiles = tiles_m * tiles_n;
+    const int ksplit = a.ksplit > 1 ? a.ksplit : 1;
+    const int num_tiles = tiles_m * tiles_n * ksplit;   // work items: (tile, k-split), splits of a tile adjacent
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kConvStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -154,8 +157,10 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             uint32_t g = 0;  // ring position, continuous across tiles
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int p0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
-                for (int it = 0; it < iters; ++it, ++g) {
+                const int split = tile % ksplit, t2 = tile / ksplit;
+                const int p0 = (t2 / tiles_n) * kTileM, n0 = (t2 % tiles_n) * BN;
+                const int it0 = split * iters / ksplit, it1 = (split + 1) * iters / ksplit;
+                for (int it = it0; it < it1; ++it, ++g) {
                     const uint32_t s = g % kConvStages, round = g / kConvStages;
                     mbar_wait(&empty_bar[s], (round & 1) ^ 1);   // passes immediately on the first round
                     const int ky = it / kchunks, kc = it - ky * kchunks;
@@ -180,7 +185,9 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 mbar_wait(&tmem_empty_bar[acc], ((t / kAcc) & 1) ^ 1);   // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + acc * (MT * BN);
-                for (int it = 0; it < iters; ++it, ++g) {
+                const int split = tile % ksplit;
+                const int it0 = split * iters / ksplit, it1 = (split + 1) * iters / ksplit;
+                for (int it = it0; it < it1; ++it, ++g) {
                     const uint32_t s = g % kConvStages, round = g / kConvStages;
                     mbar_wait(&full_bar[s], round & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -195,7 +202,7 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                             for (int k = 0; k < kConvBK / 8; ++k)   // UMMA K = 8 tf32 = 32 bytes: advance the start address
                                 umma_tf32(tmem_d + m * BN, adesc + (uint64_t)((k * 32) >> 4), bdesc + (uint64_t)((k * 32) >> 4),
-                                          idesc, (it | kx | k) != 0);
+                                          idesc, ((it - it0) | kx | k) != 0);
                         }
                     }
                     umma_commit(&empty_bar[s]);           // stage free once these MMAs have read it
@@ -208,7 +215,8 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int quarter = warp & 3;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-            const int p0 = (tile / tiles_n) * kTileM, n0 = (tile % tiles_n) * BN;
+            const int split = tile % ksplit, t2 = tile / ksplit;
+            const int p0 = (t2 / tiles_n) * kTileM, n0 = (t2 % tiles_n) * BN;
             const uint32_t acc = t % kAcc;
             mbar_wait(&tmem_full_bar[acc], (t / kAcc) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -240,7 +248,13 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                     }
-                    if (p < a.P) {
+                    if (p < a.P && ksplit > 1) {   // raw partial sums; the reduction kernel applies the epilogue
+                        float* o = a.partial + ((size_t)split * a.P + p) * a.Cout + n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(__int_as_float((int)r[j]), __int_as_float((int)r[j + 1]),
+                                                                            __int_as_float((int)r[j + 2]), __int_as_float((int)r[j + 3]));
+                    } else if (p < a.P) {
                         float* o = a.out + (size_t)p * a.Cout + n0 + c0;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -521,8 +535,52 @@ inline int make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_
     return r == CUDA_SUCCESS ? 0 : 2001 + (int)r;
 }
 
+// Sum of the split-K partial accumulators (fixed order => deterministic) + affine + ReLU + zero border
+__global__ void conv_splitk_reduce_kernel(const float* partial, int ksplit, float* y, int P, int Hp, int Wp, int C,
+                                          const float* scale, const float* shift, int relu) {
+    const int C4 = C >> 2;
+    const long long total = (long long)P * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i / C4), c = (int)(i - (long long)p * C4) << 2;
+        const int rem = p % (Hp * Wp);
+        const int hp = rem / Wp, wp = rem - hp * Wp;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2) {
+            for (int k = 0; k < ksplit; ++k) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)k * P + p) * C + c));
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            if (scale) { const float4 q = __ldg(reinterpret_cast<const float4*>(scale + c)); s.x *= q.x; s.y *= q.y; s.z *= q.z; s.w *= q.w; }
+            if (shift) { const float4 q = __ldg(reinterpret_cast<const float4*>(shift + c)); s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w; }
+            if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+        }
+        *reinterpret_cast<float4*>(y + (size_t)p * C + c) = s;
+    }
+}
+
+// k-splits for a layer: only when one wave of tiles would leave SMs idle (the small deep layers)
+inline int conv_ksplit(long long P, int Cin, int Cout, int sms) {
+    if (Cin % kConvBK != 0 || Cout % 64 != 0) return 1;
+    const int BN = (Cout % 128 == 0) ? 128 : 64;
+    const long long tiles1 = ((P + kConvBM - 1) / kConvBM) * (Cout / BN);
+    if (tiles1 > sms) return 1;
+    const int iters = 3 * (Cin / kConvBK);
+    long long s = (2LL * sms) / tiles1;
+    if (s > 8) s = 8;
+    if (s > iters / 2) s = iters / 2;
+    return s < 1 ? 1 : (int)s;
+}
+inline size_t conv3x3_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
+    const long long P = (long long)B * (H + 2) * (W + 2);
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int s = conv_ksplit(P, Cin, Cout, sms);
+    return s > 1 ? (size_t)s * P * Cout * sizeof(float) : 0;
+}
+
 inline int conv3x3_forward(const float* x_padded, const float* w9, const float* scale, const float* shift, float* y_padded,
-                           int B, int H, int W, int Cin, int Cout, int relu, cudaStream_t stream) {
+                           int B, int H, int W, int Cin, int Cout, int relu, cudaStream_t stream,
+                           void* workspace = nullptr, size_t workspace_bytes = 0) {
     if (!x_padded || !w9 || !y_padded || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return DMST_EINVAL;
     const int Hp = H + 2, Wp = W + 2;
     const long long P = (long long)B * Hp * Wp;
@@ -551,17 +609,19 @@ inline int conv3x3_forward(const float* x_padded, const float* w9, const float* 
     if (e) return e;
     e = make_map_2d(&mb, w9, (uint64_t)9 * Cout, (uint64_t)Cin, (uint32_t)BN);
     if (e) return e;
-    ConvArgs a{(int)P, Hp, Wp, Cin, Cout, scale, shift, relu, y_padded};
     int sms = 148;
     {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    int ksplit = conv_ksplit(P, Cin, Cout, sms);
+    if (ksplit > 1 && (!workspace || workspace_bytes < (size_t)ksplit * P * Cout * sizeof(float))) ksplit = 1;  // no workspace: unsplit
+    ConvArgs a{(int)P, Hp, Wp, Cin, Cout, scale, shift, relu, y_padded, ksplit, reinterpret_cast<float*>(workspace)};
     // two pixel sub-tiles per CTA tile when that still leaves at least two waves of tiles
     const long long tiles1 = ((P + kConvBM - 1) / kConvBM) * (Cout / BN);
     const int MT = (tiles1 >= 4LL * sms) ? 2 : 1;
-    const long long num_tiles = ((P + MT * kConvBM - 1) / (MT * kConvBM)) * (Cout / BN);
+    const long long num_tiles = ((P + MT * kConvBM - 1) / (MT * kConvBM)) * (Cout / BN) * ksplit;
     const dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));  // persistent: one CTA per SM
     auto launch = [&](auto kern, int bn, int mt) -> int {
         const size_t smem = (size_t)conv_stages(bn, mt) * conv_stage_bytes(bn, mt) + 1024;
@@ -573,6 +633,9 @@ inline int conv3x3_forward(const float* x_padded, const float* w9, const float* 
     if (BN == 128) e = (MT == 2) ? launch(conv3x3_tf32_kernel<128, 2>, 128, 2) : launch(conv3x3_tf32_kernel<128, 1>, 128, 1);
     else e = (MT == 2) ? launch(conv3x3_tf32_kernel<64, 2>, 64, 2) : launch(conv3x3_tf32_kernel<64, 1>, 64, 1);
     if (e) return e;
+    if (ksplit > 1)
+        conv_splitk_reduce_kernel<<<grid_for(P * (Cout / 4)), 256, 0, stream>>>(a.partial, ksplit, y_padded, (int)P, Hp, Wp, Cout,
+                                                                             scale, shift, relu);
     return (int)cudaGetLastError();
 }
 

@@ -173,6 +173,13 @@ int dmst_conv_repack_weights(const float* w, float* w9, int Cout, int Cin, void*
 int dmst_conv3x3_forward(const float* x_padded, const float* w9, const float* scale, const float* shift,
                          float* y_padded, int B, int H, int W, int Cin, int Cout, int relu, void* stream);
 /* training-mode BatchNorm: batch mean and biased variance per channel of a raw conv output */
+/* Same, with a caller-provided workspace (dmst_conv3x3_workspace_bytes, may be 0): layers with fewer
+ * output tiles than SMs (the deep 8x8 / 2x4 layers) split their K loop over several CTAs and reduce the
+ * partial sums in a fixed order. */
+size_t dmst_conv3x3_workspace_bytes(int B, int H, int W, int Cin, int Cout);
+int dmst_conv3x3_forward_ws(const float* x_padded, const float* w9, const float* scale, const float* shift,
+                            float* y_padded, int B, int H, int W, int Cin, int Cout, int relu, void* workspace,
+                            size_t workspace_bytes, void* stream);
 size_t dmst_conv_stats_workspace_bytes(int B, int H, int W, int C);
 int dmst_conv_channel_stats(const float* y_padded, int B, int H, int W, int C, float* mean, float* var_biased,
                             void* workspace, size_t workspace_bytes, void* stream);
