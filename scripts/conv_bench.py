@@ -20,8 +20,11 @@ for cin, cout, H, W in layers:
     w9 = torch.randn(9, cout, cin, device=dev) * 0.05
     sc = torch.rand(cout, device=dev); sh = torch.rand(cout, device=dev)
     y = torch.empty(B, H + 2, W + 2, cout, device=dev)
+    nws = lib.dmst_conv3x3_workspace_bytes(B, H, W, cin, cout)
+    ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
     def run():
-        rc = lib.dmst_conv3x3_forward(_ptr(x), _ptr(w9), _ptr(sc), _ptr(sh), _ptr(y), B, H, W, cin, cout, 1, _stream(dev))
+        rc = lib.dmst_conv3x3_forward_ws(_ptr(x), _ptr(w9), _ptr(sc), _ptr(sh), _ptr(y), B, H, W, cin, cout, 1, _ptr(ws), nws,
+                                         _stream(dev))
         assert rc == 0, rc
     for _ in range(3): run()
     torch.cuda.synchronize()
