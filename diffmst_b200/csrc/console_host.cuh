@@ -89,7 +89,7 @@ struct Carver {
 struct ConsoleWs {
     int* header;          // [0..3] tickets (fwd track, fwd master, bwd master, bwd track)
     RowTab *track_tab, *track_tab_b, *master_tab, *master_tab_b;  // *_b: tables for the backward chunk length
-    float *y, *bus_pre, *dbus, *esave, *ssave;
+    float *y, *bus_pre, *dbus, *esave, *ssave, *m_esave, *m_ssave;
     // forward chain (kept for backward)
     int *t_flag, *m_flag, *t_done;
     Mail *t_state, *m_state;
@@ -121,6 +121,8 @@ inline ConsoleWs carve_console(void* base, int B, int N, int T, int la_t, int la
     w.dbus = c.take<float>((size_t)B * 2 * w.Tp);
     w.esave = c.take<float>(rows * w.Tp);
     w.ssave = c.take<float>(rows * w.nt_track * (size_t)(kNumSections * 2) * (kTrackTile / kBwdChunk));
+    w.m_esave = c.take<float>((size_t)B * 2 * w.Tp);
+    w.m_ssave = c.take<float>((size_t)B * w.nt_master * (size_t)(kNumSections * 2 * 2) * (kMasterTile / kBwdChunk));
     w.flags_begin = (c.off + 255) & ~size_t(255);   // zeroed before every forward
     w.t_flag = c.take<int>(rt);
     w.m_flag = c.take<int>(rm);
@@ -254,6 +256,7 @@ inline void fill_chain(ChainArgs& a, const ConsoleCall& k, bool master, ConsoleW
         a.nrows = k.B; a.ntiles = w.nt_master; a.flags = master_chain_flags(k.flags) | debug_flags();
         a.lookahead = k.la_m;
         a.src = w.y; a.tab = w.master_tab; a.track_tab = w.track_tab; a.bus_pre = w.bus_pre;
+        if ((a.flags & kChainEq) && kMasterBwdL == kBwdChunk) { a.esave = w.m_esave; a.ssave = w.m_ssave; }  // checkpoints: backward skips the EQ recompute
         a.ticket = w.header + 1; a.flag = w.m_flag; a.state = w.m_state; a.tail2 = w.m_tail2; a.etail = w.m_etail;
         a.partial = w.m_partial; a.bflag = w.m_bflag; a.bstate = w.m_bstate; a.dhead = w.m_dhead;
     }
