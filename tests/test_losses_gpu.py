@@ -66,6 +66,25 @@ def test_mrstft_vs_oracle_strided_and_scaled():
     assert abs(a - b) <= 1e-4 * abs(b)
 
 
+def test_mrstft_gradient_general_layouts():
+    """Gradient parity where the fast paths do not apply: window shorter than the FFT and hops that are not
+    half the FFT (auraloss defaults 1024/2048/512, hops 120/240/50, windows 600/1200/240), an odd length, and
+    views that are only 4-byte aligned."""
+    from diffmst_b200 import MRSTFTLoss
+    g = torch.Generator().manual_seed(23)
+    full_x = torch.randn(2, 2, 30003, generator=g) * 0.1
+    full_y = torch.randn(2, 2, 30003, generator=g) * 0.1 + 0.5 * full_x
+    for res in (dict(), RES):
+        f, o = MRSTFTLoss(**res), OracleMRSTFT(**res)
+        xc = full_x.cuda()[..., 10001:].requires_grad_(True)      # odd offset, odd length (20002 samples)
+        loss = f(xc, full_y.cuda()[..., 10001:])
+        x64 = full_x[..., 10001:].double().requires_grad_(True)
+        ref = o(x64, full_y[..., 10001:].double())
+        assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+        loss.backward(); ref.backward()
+        assert rell2(xc.grad.cpu().numpy(), x64.grad.numpy()) <= 3e-3
+
+
 def test_mrstft_closed_forms_and_errors():
     from diffmst_b200 import MRSTFTLoss
     g = torch.Generator().manual_seed(22)
