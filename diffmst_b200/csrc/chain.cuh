@@ -3,10 +3,10 @@
 // A "row" is one mono track (NCH = 1, the per-track chain gain -> EQ -> compressor of
 // mst/modules.py:230-251) or one stereo master bus (NCH = 2, mst/modules.py:286-312, both
 // channels share coefficients and the compressor side-chain is their sum).  Time is cut
-// into tiles of NT*L samples; one CTA owns one (row, tile); thread t owns samples
-// [t*L, t*L+L) of the tile in registers.  Linear recurrences are solved exactly across
+// into tiles of NT*L samples; a (row, tile) is one work item of a persistent CTA; thread t owns
+// samples [t*L, t*L+L) of the tile in registers.  Linear recurrences are solved exactly across
 // threads by a scan whose combine operator is a constant matrix power (tables in RowTab),
-// and across tiles by chaining CTAs through global memory (per-section wavefront).
+// and across tiles by chaining work items through global memory (per-section wavefront).
 #pragma once
 #include "common.cuh"
 
@@ -70,21 +70,7 @@ __device__ __forceinline__ void mat2T_apply_acc(const float* m, float t1, float 
     s2 = fmaf(m[1], t1, fmaf(m[3], t2, s2));
 }
 
-// Load L consecutive floats starting at p[0] (global), zero beyond `valid` elements.
-template <int L>
-__device__ __forceinline__ void load_chunk(const float* p, int valid, bool vec_ok, float (&v)[L]) {
-    if (vec_ok && valid >= L) {
-        const float4* p4 = reinterpret_cast<const float4*>(p);
-#pragma unroll
-        for (int i = 0; i < L / 4; ++i) {
-            float4 q = __ldg(p4 + i);
-            v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < L; ++i) v[i] = (i < valid) ? __ldg(p + i) : 0.0f;
-    }
-}
+// Store L consecutive floats starting at p[0] (global), first `valid` elements only.
 template <int L>
 __device__ __forceinline__ void store_chunk(float* p, int valid, bool vec_ok, const float (&v)[L]) {
     if (vec_ok && valid >= L) {
@@ -187,36 +173,6 @@ __device__ __forceinline__ float4 load4(const float* p, int valid, bool vec_ok) 
     r.z = valid > 2 ? __ldg(p + 2) : 0.0f;
     r.w = valid > 3 ? __ldg(p + 3) : 0.0f;
     return r;
-}
-
-// Coalesced tile I/O through the padded shared-memory layout: the CTA moves TILE consecutive
-// floats with fully coalesced 128-bit global accesses, threads then read/write their own
-// L-sample chunk from shared memory (conflict-free thanks to the i + i/32 padding).
-template <int NT, int TILE>
-__device__ __forceinline__ void stage_in(float* stage, const float* g, int valid, bool vec_ok, int tid) {
-#pragma unroll
-    for (int q = tid; q < TILE / 4; q += NT) {
-        const int idx = 4 * q;
-        const float4 val = load4(g + idx, valid - idx, vec_ok);
-        const int p = pidx(idx);
-        stage[p] = val.x; stage[p + 1] = val.y; stage[p + 2] = val.z; stage[p + 3] = val.w;
-    }
-}
-template <int NT, int TILE>
-__device__ __forceinline__ void stage_out(float* g, const float* stage, int valid, bool vec_ok, int tid, float scale = 1.0f) {
-#pragma unroll
-    for (int q = tid; q < TILE / 4; q += NT) {
-        const int idx = 4 * q, p = pidx(idx), left = valid - idx;
-        const float4 val = make_float4(stage[p] * scale, stage[p + 1] * scale, stage[p + 2] * scale, stage[p + 3] * scale);
-        if (vec_ok && left >= 4) {
-            *reinterpret_cast<float4*>(g + idx) = val;
-        } else {
-            if (left > 0) g[idx] = val.x;
-            if (left > 1) g[idx + 1] = val.y;
-            if (left > 2) g[idx + 2] = val.z;
-            if (left > 3) g[idx + 3] = val.w;
-        }
-    }
 }
 
 // Static-curve gain computer of the dasp compressor, branch-free:

@@ -152,9 +152,6 @@ __device__ __forceinline__ float mail_wait(const Mail* p, bool skip = false) {
     return v;
 }
 
-// padded shared-memory index: conflict-free when lane l touches element l*L + i
-__host__ __device__ __forceinline__ int pidx(int i) { return i + (i >> 5); }
-
 // padded shared-memory index for 128-bit accesses: 4 floats of padding per 32, so that lane l reading
 // float4 #j of its own L-sample chunk (L = 16 or 32), or thread q moving float4 #q of a tile, is
 // conflict-free, and every float4 stays 16-byte aligned (targets of cp.async)

@@ -72,7 +72,7 @@ __device__ __forceinline__ float4 load4_cg(const float* p, int valid) {
     r.w = valid > 3 ? __ldcg(p + 3) : 0.0f;
     return r;
 }
-// Coalesced tile output from the pidx4 layout (see stage_out in chain.cuh)
+// Coalesced tile output from the pidx4 layout: the CTA moves TILE consecutive floats with 128-bit accesses
 template <int NT, int TILE>
 __device__ __forceinline__ void stage_out4(float* g, const float* stage, int valid, bool vec_ok, int tid, float scale = 1.0f) {
 #pragma unroll
