@@ -110,7 +110,8 @@ def test_conv3x3_function_gradients_single_layer():
     import torch.nn.functional as F
     from diffmst_b200.conv import _Conv3x3Function
     g = torch.Generator().manual_seed(9)
-    for (B, cin, cout, H, W) in [(2, 64, 64, 9, 7), (2, 64, 128, 21, 18), (1, 8, 8, 5, 5), (2, 1, 64, 12, 10)]:
+    for (B, cin, cout, H, W) in [(2, 64, 64, 9, 7), (2, 64, 128, 21, 18), (1, 8, 8, 5, 5), (2, 1, 64, 12, 10),
+                                 (3, 128, 256, 30, 17), (2, 256, 96, 12, 9)]:
         x = torch.randn(B, cin, H, W, generator=g).cuda()
         w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.1).cuda()
         xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
@@ -123,7 +124,8 @@ def test_conv3x3_function_gradients_single_layer():
         (yo * probe).sum().backward()
         assert relmax(yo.detach(), yr.detach()) <= TOL
         assert relmax(xo.grad, xr.grad) <= TOL, relmax(xo.grad, xr.grad)
-        assert relmax(wo.grad, wr.grad) <= 1e-5, relmax(wo.grad, wr.grad)
+        # tensor-core wgrad (TF32) where the channel counts allow it, FP32 library GEMMs otherwise
+        assert relmax(wo.grad, wr.grad) <= (TOL if cin % 64 == 0 else 1e-5), relmax(wo.grad, wr.grad)
 
 
 def test_cnn14_backward_small():
