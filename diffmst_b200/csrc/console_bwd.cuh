@@ -197,7 +197,7 @@ __device__ __forceinline__ int bwd_tile(const BwdArgs& f, const int row, const i
     // With checkpoints from forward (EQ output + section states every kBwdChunk samples) the
     // forward EQ recompute below is skipped.
     const bool saved = (a.esave != nullptr) && (a.flags & kChainEq);
-    static_assert(MASTER || L == kBwdChunk, "state checkpoints are spaced by the backward chunk length");
+    static_assert(MASTER || L == kBwdChunk, "state checkpoints are spaced by the backward chunk length");  // (master: forward is built with CHK = this L)
     const float* ssave = a.ssave ? a.ssave + rt * (kNumSections * NCH * 2) * NT : nullptr;
     (void)uvec;
     float v[NCH][L];

@@ -146,7 +146,8 @@ struct FwdShared {
 };
 
 // One (row, tile) of a chain.  Returns the next ticket of this CTA (claimed on the way, inputs prefetched).
-template <int NCH, int L, int NT, bool MASTER, int TILE_T>
+// CHK: spacing of the section-state checkpoints left for backward = thread chunk of the backward kernel of this role
+template <int NCH, int L, int NT, bool MASTER, int TILE_T, int CHK>
 __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, const int row, const int tile,
                                         float* ebuf, float* inbuf, const RowTab& tb, float* tab_next,
                                         FwdShared<NT>& sh) {
@@ -260,7 +261,8 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
             const SectionTab& st = tb.sec[k];
             const float b0 = st.b0, b1 = st.b1, b2 = st.b2, na1 = -st.a1, na2 = -st.a2;
             float s1[NCH], s2[NCH];
-            constexpr int NSUB = (L + kBwdChunk - 1) / kBwdChunk;  // state checkpoints per thread chunk
+            static_assert(L % CHK == 0, "checkpoint spacing divides the forward chunk");
+            constexpr int NSUB = L / CHK;  // state checkpoints per thread chunk
             float zm1[NCH][NSUB], zm2[NCH][NSUB];                  // zero-state states at the checkpoints
             if (tid == 0) {
                 if (!MASTER && k == 1) claimed = atomicAdd(f.ticket, 1);
@@ -272,7 +274,7 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
                 float z1 = 0.0f, z2 = 0.0f;
 #pragma unroll
                 for (int i = 0; i < L; ++i) {
-                    if (i % kBwdChunk == 0) { zm1[c][i / kBwdChunk] = z1; zm2[c][i / kBwdChunk] = z2; }
+                    if (i % CHK == 0) { zm1[c][i / CHK] = z1; zm2[c][i / CHK] = z2; }
                     const float x = v[c][i];
                     const float yv = fmaf(b0, x, z1);
                     z1 = fmaf(b1, x, fmaf(na1, yv, z2));
@@ -323,17 +325,17 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
             }
             // add the homogeneous response to the carried-in state
             float* ssave = a.ssave
-                               ? a.ssave + ((long long)row * a.ntiles + tile) * (kNumSections * NCH * 2) * (TILE / kBwdChunk)
+                               ? a.ssave + ((long long)row * a.ntiles + tile) * (kNumSections * NCH * 2) * (TILE / CHK)
                                : nullptr;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 float h1 = e1[c], h2 = e2[c];
 #pragma unroll
                 for (int i = 0; i < L; ++i) {
-                    if (i % kBwdChunk == 0 && ssave) {  // true state at this checkpoint
-                        const int tbx = tid * NSUB + i / kBwdChunk;
-                        ssave[((k * NCH + c) * 2 + 0) * (TILE / kBwdChunk) + tbx] = zm1[c][i / kBwdChunk] + h1;
-                        ssave[((k * NCH + c) * 2 + 1) * (TILE / kBwdChunk) + tbx] = zm2[c][i / kBwdChunk] + h2;
+                    if (i % CHK == 0 && ssave) {  // true state at this checkpoint
+                        const int tbx = tid * NSUB + i / CHK;
+                        ssave[((k * NCH + c) * 2 + 0) * (TILE / CHK) + tbx] = zm1[c][i / CHK] + h1;
+                        ssave[((k * NCH + c) * 2 + 1) * (TILE / CHK) + tbx] = zm2[c][i / CHK] + h2;
                     }
                     const float t = h1;
                     v[c][i] += t;
@@ -484,7 +486,7 @@ __host__ __device__ inline int fwd_ebuf_floats(int tile_t, int la_t, int tile_m,
     return t > m ? t : m;
 }
 
-template <int L_T, int L_M, int NT>
+template <int L_T, int L_M, int NT, int CHK_T, int CHK_M>
 __global__ void __launch_bounds__(NT, 2) console_fwd_kernel(FwdArgs f) {
     constexpr int TILE_T = NT * L_T;
     DMST_DYN_SMEM(smem_raw);
@@ -513,10 +515,10 @@ __global__ void __launch_bounds__(NT, 2) console_fwd_kernel(FwdArgs f) {
         float* tab_next = s_tabf + (par ^ 1) * (sizeof(RowTab) / 4);
         int nxt;
         if (w.role == 1) {
-            nxt = fwd_tile<1, L_T, NT, false, TILE_T>(f, f.t, w.row, w.tile, ebuf, inbuf, tb, tab_next, sh);
+            nxt = fwd_tile<1, L_T, NT, false, TILE_T, CHK_T>(f, f.t, w.row, w.tile, ebuf, inbuf, tb, tab_next, sh);
             signal = f.done + (long long)(w.row / f.t.N) * f.t.ntiles + w.tile;
         } else if (w.role == 2) {
-            nxt = fwd_tile<2, L_M, NT, true, TILE_T>(f, f.m, w.row, w.tile, ebuf, inbuf, tb, tab_next, sh);
+            nxt = fwd_tile<2, L_M, NT, true, TILE_T, CHK_M>(f, f.m, w.row, w.tile, ebuf, inbuf, tb, tab_next, sh);
         } else {
             if (tid == 0) sh.next = atomicAdd(f.ticket, 1);
             __syncthreads();

@@ -122,7 +122,7 @@ inline ConsoleWs carve_console(void* base, int B, int N, int T, int la_t, int la
     w.esave = c.take<float>(rows * w.Tp);
     w.ssave = c.take<float>(rows * w.nt_track * (size_t)(kNumSections * 2) * (kTrackTile / kBwdChunk));
     w.m_esave = c.take<float>((size_t)B * 2 * w.Tp);
-    w.m_ssave = c.take<float>((size_t)B * w.nt_master * (size_t)(kNumSections * 2 * 2) * (kMasterTile / kBwdChunk));
+    w.m_ssave = c.take<float>((size_t)B * w.nt_master * (size_t)(kNumSections * 2 * 2) * (kMasterTile / kMasterBwdL));
     w.flags_begin = (c.off + 255) & ~size_t(255);   // zeroed before every forward
     w.t_flag = c.take<int>(rt);
     w.m_flag = c.take<int>(rm);
@@ -256,7 +256,7 @@ inline void fill_chain(ChainArgs& a, const ConsoleCall& k, bool master, ConsoleW
         a.nrows = k.B; a.ntiles = w.nt_master; a.flags = master_chain_flags(k.flags) | debug_flags();
         a.lookahead = k.la_m;
         a.src = w.y; a.tab = w.master_tab; a.track_tab = w.track_tab; a.bus_pre = w.bus_pre;
-        if ((a.flags & kChainEq) && kMasterBwdL == kBwdChunk) { a.esave = w.m_esave; a.ssave = w.m_ssave; }  // checkpoints: backward skips the EQ recompute
+        if (a.flags & kChainEq) { a.esave = w.m_esave; a.ssave = w.m_ssave; }  // checkpoints: backward skips the EQ recompute
         a.ticket = w.header + 1; a.flag = w.m_flag; a.state = w.m_state; a.tail2 = w.m_tail2; a.etail = w.m_etail;
         a.partial = w.m_partial; a.bflag = w.m_bflag; a.bstate = w.m_bstate; a.dhead = w.m_dhead;
     }
@@ -300,7 +300,7 @@ inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* 
     f.group = k.B * f.R + k.B * k.N;
     f.ticket = w.header + 0; f.done = w.t_done;
     {
-        auto kern = console_fwd_kernel<kTrackFwdL, kMasterL, kTrackFwdNT>;
+        auto kern = console_fwd_kernel<kTrackFwdL, kMasterL, kTrackFwdNT, kBwdChunk, kMasterBwdL>;
         const size_t smem = fwd_smem_bytes(k.la_t, k.la_m);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
         int ctas = persistent_ctas(kern, kTrackFwdNT, smem);
