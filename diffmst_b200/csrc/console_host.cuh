@@ -205,7 +205,8 @@ inline int check_call(const ConsoleCall& k) {
     if (k.flags & DMST_USE_FX_BUS) return DMST_EINVAL;              // out of scope
     if (!(k.flags & DMST_USE_TRACK_PANNER)) return DMST_EINVAL;     // broken upstream (modules.py:269)
     if (!(k.flags & DMST_BASIC_CONSOLE) && !k.master_params) return DMST_EINVAL;
-    if (k.la_t < 0 || k.la_t > kTrackTile || k.la_m < 0 || k.la_m > kMasterTile) return DMST_EINVAL;
+    // (limits: the backward kernels keep two look-ahead + tile lines and the prefetched gradient in shared memory)
+    if (k.la_t < 0 || k.la_t > kTrackTile / 2 || k.la_m < 0 || k.la_m > kMasterTile) return DMST_EINVAL;
     if ((k.la_t & 31) || (k.la_m & 31)) return DMST_EINVAL;  // look-ahead must be a multiple of 32 samples
     return 0;
 }

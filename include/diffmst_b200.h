@@ -73,7 +73,7 @@ size_t dmst_console_workspace_bytes(int B, int N, int T, unsigned flags);
  * out-of-range parameter (track index space first, then 1000 + master index), which the
  * host turns into the reference's ValueError (mst/modules.py:86-89).
  * track_lookahead / master_lookahead: compressor look-ahead in samples (2048 / 1024 upstream,
- * mst/modules.py:250,304); multiples of 32, at most one tile (8192 / 4096).
+ * mst/modules.py:250,304); multiples of 32, at most 4096 samples each.
  * The workspace keeps what backward needs; it must stay untouched until
  * dmst_console_backward for the same call has run.
  */
