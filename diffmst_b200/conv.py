@@ -16,6 +16,7 @@ torch.matmul - a hand-written split-K tcgen05 wgrad is the next step); BatchNorm
 of the differentiable path are PyTorch ops on NHWC views.
 """
 import ctypes
+import weakref
 from typing import List
 
 import torch
@@ -39,23 +40,21 @@ def _to_padded_nhwc(x):
     return y
 
 
-_REPACK_CACHE = {}   # id(parameter) -> (data_ptr, version, [9][Cout][Cin] tensor); refreshed when the weight changes
+_REPACK_CACHE = {}   # id(parameter) -> (weak reference to it, data_ptr, version, [9][Cout][Cin] tensor)
 
 
 def _repack(w):
     """[Cout][Cin][3][3] -> [9][Cout][Cin], cached until the parameter is modified (inference repacks once)."""
     key = id(w)
     hit = _REPACK_CACHE.get(key)
-    if hit is not None and hit[0] == w.data_ptr() and hit[1] == w._version and hit[2].device == w.device:
-        return hit[2]
+    if hit is not None and hit[0]() is w and hit[1] == w.data_ptr() and hit[2] == w._version and hit[3].device == w.device:
+        return hit[3]
     lib = _lib.lib()
     Cout, Cin = w.shape[0], w.shape[1]
     w9 = torch.empty(9, Cout, Cin, dtype=torch.float32, device=w.device)
     _lib.check(lib.dmst_conv_repack_weights(_ptr(w.detach().contiguous()), _ptr(w9), Cout, Cin, _stream(w.device)),
                "dmst_conv_repack_weights")
-    if len(_REPACK_CACHE) > 256:
-        _REPACK_CACHE.clear()
-    _REPACK_CACHE[key] = (w.data_ptr(), w._version, w9)
+    _REPACK_CACHE[key] = (weakref.ref(w, lambda _r, k=key: _REPACK_CACHE.pop(k, None)), w.data_ptr(), w._version, w9)
     return w9
 
 
