@@ -322,3 +322,44 @@ def test_random_mix_helpers_on_device():
     assert torch.equal(params[0], tp) and not bool(has_nan)
     assert torch.equal(ref_mix, batch_stereo_peak_normalize(mix))
     assert abs(float(ref_mix.abs().amax(dim=(1, 2)).min()) - 1.0) < 1e-6
+
+
+def test_graphed_step_replays_the_eager_step_bit_for_bit():
+    """GraphedStep (one CUDA graph of console forward + MRSTFT + backward): every
+    replay gives the eager loss and gradients exactly (the kernels are deterministic), follows in-place
+    refills of the static inputs, and leaves the range check working outside the graph."""
+    from diffmst_b200 import AdvancedMixConsole, GraphedStep, MRSTFTLoss
+    B, N, T = 2, 3, 50000
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(B, N, T, generator=g) * 0.1).cuda()
+    x2 = (torch.randn(B, N, T, generator=g) * 0.1).cuda()
+    tp = torch.rand(B, N, 27, generator=g).cuda().requires_grad_(True)
+    fp = torch.rand(B, 25, generator=g).cuda()
+    mp = torch.rand(B, 26, generator=g).cuda().requires_grad_(True)
+    target = (torch.randn(B, 2, T, generator=g) * 0.1).cuda()
+    con = AdvancedMixConsole(SR).cuda()
+    con.materialize_tracks = False
+    loss_fn = MRSTFTLoss(fft_sizes=[512, 2048, 8192], hop_sizes=[256, 1024, 4096], win_lengths=[512, 2048, 8192])
+
+    def eager(inp):
+        tp.grad = None; mp.grad = None
+        loss = loss_fn(con(inp, tp, fp, mp, use_fx_bus=False)[1], target)
+        loss.backward()
+        return loss.detach().clone(), tp.grad.clone(), mp.grad.clone()
+
+    e1 = eager(x)
+    e2 = eager(x2)
+    static_x = x.clone()
+    step = GraphedStep(lambda: loss_fn(con(static_x, tp, fp, mp, use_fx_bus=False)[1], target), params=[tp, mp],
+                       consoles=[con])
+    assert con.check_ranges is True  # restored after the capture
+    for _ in range(3):
+        loss = step()
+        assert torch.equal(loss.detach(), e1[0]) and torch.equal(tp.grad, e1[1]) and torch.equal(mp.grad, e1[2])
+    static_x.copy_(x2)
+    loss = step()
+    assert torch.equal(loss.detach(), e2[0]) and torch.equal(tp.grad, e2[1]) and torch.equal(mp.grad, e2[2])
+    with pytest.raises(ValueError, match="out of range"):
+        con(x, tp.detach() + 1.0, fp, mp.detach(), use_fx_bus=False)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        GraphedStep(lambda: None, params=[torch.zeros(1, requires_grad=True)])
