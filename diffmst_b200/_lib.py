@@ -87,6 +87,10 @@ def lib():
     l.dmst_conv_affine_relu.argtypes = [vp, vp, vp, i, i, i, i, i, vp]
     l.dmst_conv_avgpool.restype = i
     l.dmst_conv_avgpool.argtypes = [vp, vp, i, i, i, i, i, i, i, vp]
+    l.dmst_spectrogram_workspace_bytes.restype = sz
+    l.dmst_spectrogram_workspace_bytes.argtypes = [i, i, i, i, i]
+    l.dmst_spectrogram_frontend.restype = i
+    l.dmst_spectrogram_frontend.argtypes = [vp, ll, vp, i, i, i, i, i, f, f, vp, vp, sz, vp]
     l.dmst_profile_enable.restype = i
     l.dmst_profile_enable.argtypes = [i]
     l.dmst_profile_read.restype = i

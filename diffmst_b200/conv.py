@@ -251,7 +251,10 @@ class Cnn14(nn.Module):
 
     def forward(self, x: torch.Tensor):
         _require_cuda(x, "x")
-        h = _to_padded_nhwc_any(x, _needs_grad(x, self))
+        return self.forward_padded_nhwc(_to_padded_nhwc_any(x, _needs_grad(x, self)))
+
+    def forward_padded_nhwc(self, h: torch.Tensor):
+        """Same as forward for an input already in the zero-bordered NHWC layout (B, H+2, W+2, n_inputs)."""
         for i, pool in enumerate(self.POOLS):
             h = getattr(self, f"conv_block{i + 1}").forward_nhwc(h, pool, out_padded_nhwc=(i < 5))
         h = torch.mean(h, dim=2)            # mean across stft bins
@@ -265,9 +268,11 @@ class SpectrogramEncoder(nn.Module):
 
     Same constructor arguments, buffer (``window``) and sub-module names (``model``, ``bn``) as the
     reference, so its checkpoints load with ``load_state_dict``.  The convolution trunk is the
-    tensor-core ``Cnn14`` above; the spectrogram front-end is cuFFT through ``torch.stft`` followed
-    by one fused magnitude-compression kernel from PyTorch (plumbing; fusing it into conv_block1's
-    loader is the next step)."""
+    tensor-core ``Cnn14`` above.  The spectrogram front-end is
+    ``dmst_spectrogram_frontend``: 128-bit framing, one batched cuFFT R2C and one kernel that takes the
+    magnitude, compresses it and writes the zero-bordered NHWC tensor the first convolution reads
+    (three launches instead of pad / stft / abs / add / pow / layout conversion).  Only a waveform that
+    itself needs a gradient, or ``input_batchnorm=True``, goes through the PyTorch composition."""
 
     def __init__(self, embed_dim: int = 128, n_inputs: int = 1, n_fft: int = 2048, hop_length: int = 512,
                  input_batchnorm: bool = False, encoder_batchnorm: bool = True) -> None:
@@ -281,8 +286,33 @@ class SpectrogramEncoder(nn.Module):
         self.model = Cnn14(n_inputs=n_inputs, num_classes=embed_dim, use_batchnorm=encoder_batchnorm)
         self.bn = nn.BatchNorm2d(3) if input_batchnorm else nn.Identity()
 
+    def _frontend(self, x: torch.Tensor) -> torch.Tensor:
+        """(bs, chs, T) waveform -> (bs, n_fft/2+1 + 2, frames + 2, chs) compressed magnitudes, zero border."""
+        lib = _lib.lib()
+        _require_cuda(x, "x")
+        bs, chs, T = x.shape
+        if T <= self.n_fft // 2:
+            raise RuntimeError(f"Argument #4: Padding size should be less than the corresponding input dimension, "
+                               f"but got: padding ({self.n_fft // 2}, {self.n_fft // 2}) at dimension 2 of input "
+                               f"{[1, bs * chs, T]}")  # torch.stft's reflect-padding error
+        x = x.contiguous()
+        dev = x.device
+        bins, frames = self.n_fft // 2 + 1, 1 + T // self.hop_length
+        with torch.cuda.device(dev):
+            nbytes = lib.dmst_spectrogram_workspace_bytes(bs, chs, T, self.n_fft, self.hop_length)
+            if nbytes == 0:
+                raise ValueError("dmst_spectrogram_frontend: unsupported STFT geometry (n_fft must be a power of two)")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            out = torch.empty(bs, bins + 2, frames + 2, chs, dtype=torch.float32, device=dev)
+            _lib.check(lib.dmst_spectrogram_frontend(_ptr(x), T, _ptr(self.window.float().contiguous()), bs, chs, T,
+                                                     self.n_fft, self.hop_length, 1e-8, 0.3, _ptr(out), _ptr(ws), nbytes,
+                                                     _stream(dev)), "dmst_spectrogram_frontend")
+        return out
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         bs, chs, seq_len = x.size()
+        if not self.input_batchnorm and not (torch.is_grad_enabled() and x.requires_grad):
+            return self.model.forward_padded_nhwc(self._frontend(x))
         X = torch.stft(x.reshape(-1, seq_len), n_fft=self.n_fft, hop_length=self.hop_length, window=self.window,
                        return_complex=True)
         X = X.view(bs, chs, X.shape[-2], X.shape[-1])

@@ -4,6 +4,7 @@
 #include "conv_tc.cuh"
 #include "mrstft.cuh"
 #include "peaknorm.cuh"
+#include "specfront.cuh"
 
 extern "C" {
 
@@ -206,7 +207,21 @@ int dmst_conv_avgpool(const float* x_padded, float* y, int B, int C, int H, int 
                                                                                                    out_padded_nhwc);
     return (int)cudaGetLastError();
 }
+size_t dmst_spectrogram_workspace_bytes(int B, int C, int T, int n_fft, int hop) {
+    dmst::SpecWs w;
+    if (B <= 0 || C <= 0 || dmst::spec_carve(nullptr, B * C, T, n_fft, hop, &w) != 0) return 0;
+    return w.total;
+}
+int dmst_spectrogram_frontend(const float* x, long long row_stride, const float* window, int B, int C, int T, int n_fft,
+                              int hop, float eps, float power, float* out_padded, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    return dmst::spectrogram_frontend(x, row_stride, window, B, C, T, n_fft, hop, eps, power, out_padded, workspace,
+                                      workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
 #else
+size_t dmst_spectrogram_workspace_bytes(int, int, int, int, int) { return 0; }
+int dmst_spectrogram_frontend(const float*, long long, const float*, int, int, int, int, int, float, float, float*, void*,
+                              size_t, void*) { return DMST_EINVAL; }
 int dmst_conv_nchw_to_padded_nhwc(const float*, float*, int, int, int, int, void*) { return DMST_EINVAL; }
 int dmst_conv_repack_weights(const float*, float*, int, int, void*) { return DMST_EINVAL; }
 int dmst_conv3x3_forward(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, void*) { return DMST_EINVAL; }

@@ -189,6 +189,17 @@ int dmst_conv_affine_relu(float* y_padded, const float* scale, const float* shif
 int dmst_conv_avgpool(const float* x_padded, float* y, int B, int C, int H, int W, int kh, int kw,
                       int out_padded_nhwc, void* stream);
 
+/* Spectrogram front-end of the encoder, replaces the torch.stft / abs / pow lines of
+ * SpectrogramEncoder.forward (mst/modules.py:787-800): x holds B*C waveforms of T samples (row r = b*C + c at
+ * x + r*row_stride); window = n_fft Hann coefficients; the result (|STFT| + eps)^power is written as the
+ * zero-bordered NHWC tensor (B, n_fft/2+1 + 2, 1 + T/hop + 2, C) that dmst_conv3x3_forward consumes (bins are
+ * rows, frames are columns).  STFT semantics are torch.stft's defaults (centred, reflect padding, onesided,
+ * unnormalised); requires T > n_fft/2 and n_fft a power of two. */
+size_t dmst_spectrogram_workspace_bytes(int B, int C, int T, int n_fft, int hop);
+int dmst_spectrogram_frontend(const float* x, long long row_stride, const float* window, int B, int C, int T,
+                              int n_fft, int hop, float eps, float power, float* out_padded, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

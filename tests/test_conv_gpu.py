@@ -185,3 +185,30 @@ def test_spectrogram_encoder_matches_reference_composition():
         want = ref(torch.pow(X.abs() + 1e-8, 0.3))
     assert got.shape == (2, 64)
     assert relmax(got, want) <= 1e-2, relmax(got, want)
+
+
+def test_spectrogram_frontend_matches_torch_stft_composition():
+    """dmst_spectrogram_frontend against the reference's lines (mst/modules.py:787-800): torch.stft(n_fft, hop,
+    Hann) -> (|X| + 1e-8)^0.3, as the zero-bordered NHWC tensor conv_block1 reads.  float32 FFTs: 1e-4 relative
+    to the largest value; the border is exactly zero; odd lengths, several channels and ragged tiles covered."""
+    from diffmst_b200 import SpectrogramEncoder
+    g = torch.Generator().manual_seed(5)
+    for bs, chs, T, n_fft, hop in ((2, 1, 131072, 2048, 512), (1, 2, 50001, 2048, 512), (3, 1, 9000, 512, 128)):
+        enc = SpectrogramEncoder(embed_dim=8, n_inputs=chs, n_fft=n_fft, hop_length=hop).cuda().eval()
+        x = (torch.randn(bs, chs, T, generator=g) * 0.1).cuda()
+        got = enc._frontend(x)
+        X = torch.stft(x.view(-1, T), n_fft=n_fft, hop_length=hop, window=torch.hann_window(n_fft).cuda(),
+                       return_complex=True).view(bs, chs, n_fft // 2 + 1, -1)
+        want = torch.pow(X.abs() + 1e-8, 0.3)
+        assert got.shape == (bs, want.shape[2] + 2, want.shape[3] + 2, chs)
+        inner = got[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)
+        assert relmax(inner, want) <= 1e-4, relmax(inner, want)
+        assert float(got[:, 0].abs().max()) == 0.0 and float(got[:, -1].abs().max()) == 0.0
+        assert float(got[:, :, 0].abs().max()) == 0.0 and float(got[:, :, -1].abs().max()) == 0.0
+    # a waveform that needs a gradient takes the differentiable composition; too-short input is torch.stft's error
+    enc = SpectrogramEncoder(embed_dim=8).cuda().eval()
+    xg = (torch.randn(1, 1, 65536, generator=g) * 0.1).cuda().requires_grad_(True)
+    enc(xg).sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all()
+    with pytest.raises(RuntimeError, match="Padding size"):
+        enc._frontend(torch.zeros(1, 1, 1000).cuda())
