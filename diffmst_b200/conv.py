@@ -12,8 +12,9 @@ Training: with autograd enabled the 3x3 convolution is a ``torch.autograd.Functi
 and input gradient (dgrad = the same shifted-GEMM kernel run on the output gradient with the taps
 flipped and the channel roles swapped) run on tcgen05; the weight gradient is nine plain GEMMs
 ``dz^T @ x_shifted`` over the flattened zero-bordered NHWC tensors (library GEMM, cuBLAS through
-torch.matmul - a hand-written split-K tcgen05 wgrad is the next step); BatchNorm / ReLU / pooling
-of the differentiable path are PyTorch ops on NHWC views.
+torch.matmul - a hand-written split-K tcgen05 wgrad is the next step); BatchNorm + ReLU and the
+average pooling of the differentiable path are CUDA autograd Functions too (batch statistics,
+normalisation, their backward and the pooling backward in csrc/conv_tc.cuh).
 """
 import ctypes
 import weakref
@@ -39,6 +40,10 @@ def _to_padded_nhwc(x):
                "dmst_conv_nchw_to_padded_nhwc")
     return y
 
+
+# measurement aid (scripts/cnn14_train_bench.py): False routes BatchNorm / ReLU / pooling of the differentiable path
+# through PyTorch ops on NHWC views, as before the CUDA Functions existed
+_CUDA_BN_POOL = True
 
 _REPACK_CACHE = {}   # id(parameter) -> (weak reference to it, data_ptr, version, [9][Cout][Cin] tensor)
 
@@ -77,7 +82,7 @@ def _conv_bn_relu(x_pad, conv: nn.Conv2d, bn, training: bool):
     w9 = _repack(conv.weight)
     y = torch.empty(B, Hp, Wp, Cout, dtype=torch.float32, device=dev)
     is_bn = isinstance(bn, nn.BatchNorm2d)
-    use_batch_stats = is_bn and (training or bn.running_mean is None)
+    use_batch_stats = is_bn and (bn.training or bn.running_mean is None)   # nn.BatchNorm2d.forward's rule
     if is_bn and not use_batch_stats:
         scale = (bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)).float().contiguous()
         shift = (bn.bias.detach() - bn.running_mean * scale).float().contiguous()
@@ -88,19 +93,9 @@ def _conv_bn_relu(x_pad, conv: nn.Conv2d, bn, training: bool):
         return y
     # training-mode BatchNorm: raw conv -> batch statistics -> affine + ReLU in place
     _conv3x3(x_pad, w9, None, None, y, B, H, W, Cin, Cout, 0)
-    nbytes = lib.dmst_conv_stats_workspace_bytes(B, H, W, Cout)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    mean = torch.empty(Cout, dtype=torch.float32, device=dev)
-    var = torch.empty(Cout, dtype=torch.float32, device=dev)
-    _lib.check(lib.dmst_conv_channel_stats(_ptr(y), B, H, W, Cout, _ptr(mean), _ptr(var), _ptr(ws), nbytes,
-                                           _stream(dev)), "dmst_conv_channel_stats")
-    if bn.track_running_stats and bn.running_mean is not None:
-        with torch.no_grad():
-            n = B * H * W
-            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
-            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-            bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
-            bn.num_batches_tracked += 1
+    mean, var = _channel_stats(y)
+    if bn.training:
+        _update_running_stats(bn, mean, var, B * H * W)
     scale = (bn.weight.detach() * torch.rsqrt(var + bn.eps)).contiguous()
     shift = (bn.bias.detach() - mean * scale).contiguous()
     _lib.check(lib.dmst_conv_affine_relu(_ptr(y), _ptr(scale), _ptr(shift), B, H, W, Cout, 1, _stream(dev)),
@@ -139,15 +134,34 @@ class _Conv3x3Function(torch.autograd.Function):
             gx = torch.empty_like(x_pad)
             _conv3x3(gz, w9t, None, None, gx, B, Hp - 2, Wp - 2, Cout, Cin, 0, "dmst_conv3x3_forward (dgrad)")
         if ctx.needs_input_grad[1]:
-            # wgrad: dW[tap] = dz^T @ x shifted by the tap (a constant row offset in the flattened layout;
-            # dz is zero on the border, so rows that would cross an image edge contribute nothing)
+            # wgrad: dW[tap] = dz^T @ x shifted by the tap (a constant row offset in the flattened layout; dz is zero
+            # on the border, so rows that would cross an image edge contribute nothing).  K = all pixels is huge and
+            # the output tiny, so K is split into S chunks run as one batched GEMM per tap and summed afterwards.
+            # TF32 follows torch.backends.cudnn.allow_tf32, the switch that governs the reference's convolutions.
             P = B * Hp * Wp
             gzf, xf = gz.view(P, Cout), x_pad.view(P, Cin)
-            g9 = torch.empty(9, Cout, Cin, dtype=torch.float32, device=gz.device)
-            for t in range(9):
-                off = (t // 3 - 1) * Wp + (t % 3 - 1)
-                lo, hi = max(0, -off), min(P, P - off)
-                torch.matmul(gzf[lo:hi].t(), xf[lo + off:hi + off], out=g9[t])
+            first = Wp + 1                                   # rows before it / after P - first are border rows: dz = 0
+            Pc = P - 2 * first
+            tiles = -(-Cout // 128) * -(-Cin // 128)
+            S = max(1, min(256, -(-296 // tiles), Pc // 512))
+            Kc = Pc // S
+            main = S * Kc
+            tf32 = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = bool(torch.backends.cudnn.allow_tf32)
+            try:
+                a = gzf[first:first + main].view(S, Kc, Cout).transpose(1, 2)              # (S, Cout, Kc)
+                part = torch.empty(9, S, Cout, Cin, dtype=torch.float32, device=gz.device)
+                for t in range(9):
+                    off = (t // 3 - 1) * Wp + (t % 3 - 1)
+                    torch.bmm(a, xf[first + off:first + off + main].view(S, Kc, Cin), out=part[t])
+                g9 = part.sum(dim=1)
+                if main < Pc:                                                               # the last Pc - main < S rows
+                    ar = gzf[first + main:first + Pc].t()
+                    for t in range(9):
+                        off = (t // 3 - 1) * Wp + (t % 3 - 1)
+                        g9[t].addmm_(ar, xf[first + main + off:first + Pc + off])
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = tf32
             gw = g9.permute(1, 2, 0).reshape(Cout, Cin, 3, 3)
         return gx, gw
 
@@ -158,21 +172,125 @@ def _needs_grad(x, *modules):
     return x.requires_grad or any(p.requires_grad for m in modules if isinstance(m, nn.Module) for p in m.parameters())
 
 
+def _channel_stats(z_pad):
+    """Per-channel batch mean and biased variance of a zero-bordered NHWC convolution output."""
+    lib = _lib.lib()
+    B, Hp, Wp, C = z_pad.shape
+    dev = z_pad.device
+    if C % 4:   # odd channel counts (never in Cnn14): the vectorised reduction does not apply
+        zi = z_pad[:, 1:-1, 1:-1, :]
+        return zi.mean(dim=(0, 1, 2)), zi.var(dim=(0, 1, 2), unbiased=False)
+    nbytes = lib.dmst_conv_stats_workspace_bytes(B, Hp - 2, Wp - 2, C)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    mean = torch.empty(C, dtype=torch.float32, device=dev)
+    var = torch.empty(C, dtype=torch.float32, device=dev)
+    _lib.check(lib.dmst_conv_channel_stats(_ptr(z_pad), B, Hp - 2, Wp - 2, C, _ptr(mean), _ptr(var), _ptr(ws), nbytes,
+                                           _stream(dev)), "dmst_conv_channel_stats")
+    return mean, var
+
+
+def _update_running_stats(bn, mean, var, n):
+    """nn.BatchNorm2d's bookkeeping in training mode (unbiased variance into the running estimate)."""
+    if bn.track_running_stats and bn.running_mean is not None:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
+
+
+class _BnReluFunction(torch.autograd.Function):
+    """y = relu(BatchNorm(z)) on zero-bordered NHWC (mst/panns.py:79-80), forward and backward in CUDA.  `mean` / `var`
+    are the statistics the normalisation uses: the batch's (batch_stats=True; the backward then carries the mean and
+    variance terms) or the running estimates."""
+
+    @staticmethod
+    def forward(ctx, z_pad, gamma, beta, mean, var, eps, batch_stats):
+        lib = _lib.lib()
+        B, Hp, Wp, C = z_pad.shape
+        z_pad = z_pad.contiguous()
+        rstd = torch.rsqrt(var.detach().float() + eps)
+        scale = (gamma.detach().float() * rstd).contiguous()
+        shift = (beta.detach().float() - mean.detach().float() * scale).contiguous()
+        y = torch.empty_like(z_pad)
+        _lib.check(lib.dmst_conv_affine_relu_to(_ptr(z_pad), _ptr(y), _ptr(scale), _ptr(shift), B, Hp - 2, Wp - 2, C,
+                                                _stream(z_pad.device)), "dmst_conv_affine_relu_to")
+        ctx.save_for_backward(z_pad, scale, shift, mean.detach().float().contiguous(), rstd.contiguous())
+        ctx.batch_stats = bool(batch_stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.lib()
+        z_pad, scale, shift, mean, rstd = ctx.saved_tensors
+        B, Hp, Wp, C = z_pad.shape
+        dev = z_pad.device
+        gy = gy.contiguous()
+        dz = torch.empty_like(z_pad)
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        nbytes = lib.dmst_conv_stats_workspace_bytes(B, Hp - 2, Wp - 2, C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.dmst_conv_bn_relu_backward(_ptr(z_pad), _ptr(gy), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
+                                                  1 if ctx.batch_stats else 0, B, Hp - 2, Wp - 2, C, _ptr(dz), _ptr(dgamma),
+                                                  _ptr(dbeta), _ptr(ws), nbytes, _stream(dev)), "dmst_conv_bn_relu_backward")
+        return (dz, dgamma if ctx.needs_input_grad[1] else None, dbeta if ctx.needs_input_grad[2] else None,
+                None, None, None, None)
+
+
+class _AvgPoolFunction(torch.autograd.Function):
+    """F.avg_pool2d(x, (kh, kw)) of a zero-bordered NHWC tensor -> NCHW or zero-bordered NHWC (mst/panns.py:81-85)."""
+
+    @staticmethod
+    def forward(ctx, x_pad, kh, kw, out_padded_nhwc):
+        ctx.cfg = (tuple(x_pad.shape), kh, kw, bool(out_padded_nhwc))
+        return _avgpool_forward(x_pad.contiguous(), kh, kw, out_padded_nhwc)
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.lib()
+        (B, Hp, Wp, C), kh, kw, padded = ctx.cfg
+        gy = gy.contiguous()
+        gx = torch.empty(B, Hp, Wp, C, dtype=torch.float32, device=gy.device)
+        _lib.check(lib.dmst_conv_avgpool_backward(_ptr(gy), _ptr(gx), B, C, Hp - 2, Wp - 2, kh, kw, 1 if padded else 0,
+                                                  _stream(gy.device)), "dmst_conv_avgpool_backward")
+        return gx, None, None, None
+
+
 def _conv_bn_relu_autograd(x_pad, conv: nn.Conv2d, bn, training: bool):
-    """Differentiable twin of _conv_bn_relu: tensor-core conv Function + PyTorch BatchNorm/ReLU on NHWC views."""
+    """Differentiable twin of _conv_bn_relu: tensor-core conv Function, then BatchNorm + ReLU as one CUDA Function
+    (statistics, normalisation and their backward in csrc/conv_tc.cuh)."""
     z = _Conv3x3Function.apply(x_pad, conv.weight)
+    C = z.shape[-1]
+    if isinstance(bn, nn.BatchNorm2d) and C % 4 == 0 and _CUDA_BN_POOL:
+        batch_stats = bn.training or bn.running_mean is None   # nn.BatchNorm2d.forward's rule
+        if batch_stats:
+            mean, var = _channel_stats(z.detach())
+            if bn.training:
+                _update_running_stats(bn, mean, var, z.shape[0] * (z.shape[1] - 2) * (z.shape[2] - 2))
+        else:
+            mean, var = bn.running_mean, bn.running_var
+        gamma = bn.weight if bn.weight is not None else torch.ones(C, device=z.device)
+        beta = bn.bias if bn.bias is not None else torch.zeros(C, device=z.device)
+        return _BnReluFunction.apply(z, gamma, beta, mean, var, bn.eps, batch_stats)
+    # no BatchNorm (use_batchnorm=False) or an odd channel count: PyTorch ops on NHWC views
     zi = z[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)                     # NCHW view of the interior (channels-last memory)
     if isinstance(bn, nn.BatchNorm2d):
-        zi = bn(zi) if bn.training == training else F.batch_norm(
-            zi, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, bn.momentum or 0.0, bn.eps)
+        zi = bn(zi)
     y = F.relu(zi).permute(0, 2, 3, 1)
     return F.pad(y, (0, 0, 1, 1, 1, 1))                              # back to zero-bordered NHWC
 
 
 def _avgpool(x_pad, kh, kw, out_padded_nhwc):
     if torch.is_grad_enabled() and x_pad.requires_grad:
-        y = F.avg_pool2d(x_pad[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2), kernel_size=(kh, kw))
-        return F.pad(y.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)) if out_padded_nhwc else y.contiguous()
+        if not _CUDA_BN_POOL or x_pad.shape[-1] % 4:
+            y = F.avg_pool2d(x_pad[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2), kernel_size=(kh, kw))
+            return F.pad(y.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)) if out_padded_nhwc else y.contiguous()
+        return _AvgPoolFunction.apply(x_pad, kh, kw, out_padded_nhwc)
+    return _avgpool_forward(x_pad, kh, kw, out_padded_nhwc)
+
+
+def _avgpool_forward(x_pad, kh, kw, out_padded_nhwc):
     lib = _lib.lib()
     B, Hp, Wp, C = x_pad.shape
     H, W = Hp - 2, Wp - 2

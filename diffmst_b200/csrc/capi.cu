@@ -181,13 +181,13 @@ size_t dmst_conv_stats_workspace_bytes(int B, int H, int W, int C) {
 }
 int dmst_conv_channel_stats(const float* y_padded, int B, int H, int W, int C, float* mean, float* var_biased,
                             void* workspace, size_t workspace_bytes, void* stream) {
-    if (!y_padded || !mean || !var_biased || !workspace) return DMST_EINVAL;
+    if (!y_padded || !mean || !var_biased || !workspace || (C & 3)) return DMST_EINVAL;
     if (workspace_bytes < dmst_conv_stats_workspace_bytes(B, H, W, C)) return DMST_EINVAL;
     const int P = B * (H + 2) * (W + 2);
     const int chunks = (P + dmst::kStatRows - 1) / dmst::kStatRows;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     dmst::channel_partial_kernel<<<chunks, 256, 0, s>>>(y_padded, P, C, reinterpret_cast<float*>(workspace));
-    dmst::channel_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(reinterpret_cast<float*>(workspace), chunks, C,
+    dmst::channel_final_kernel<<<(C + 7) / 8, 256, 0, s>>>(reinterpret_cast<float*>(workspace), chunks, C,
                                                                (double)B * H * W, mean, var_biased);
     return (int)cudaGetLastError();
 }
@@ -207,6 +207,40 @@ int dmst_conv_avgpool(const float* x_padded, float* y, int B, int C, int H, int 
                                                                                                    out_padded_nhwc);
     return (int)cudaGetLastError();
 }
+int dmst_conv_affine_relu_to(const float* z_padded, float* y_padded, const float* scale, const float* shift, int B, int H,
+                             int W, int C, void* stream) {
+    if (!z_padded || !y_padded || !scale || !shift || (C & 3)) return DMST_EINVAL;
+    const int P = B * (H + 2) * (W + 2);
+    dmst::affine_relu_to_kernel<<<dmst::grid_for((long long)P * (C / 4)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        z_padded, y_padded, P, H + 2, W + 2, C, scale, shift);
+    return (int)cudaGetLastError();
+}
+int dmst_conv_bn_relu_backward(const float* z_padded, const float* dy_padded, const float* scale, const float* shift,
+                               const float* mean, const float* rstd, int batch_stats, int B, int H, int W, int C,
+                               float* dz_padded, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    if (!z_padded || !dy_padded || !scale || !shift || !mean || !rstd || !dz_padded || !dgamma || !dbeta || !workspace || (C & 3))
+        return DMST_EINVAL;
+    if (workspace_bytes < dmst_conv_stats_workspace_bytes(B, H, W, C)) return DMST_EINVAL;
+    const int P = B * (H + 2) * (W + 2);
+    const int chunks = (P + dmst::kStatRows - 1) / dmst::kStatRows;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    float* partial = reinterpret_cast<float*>(workspace);
+    dmst::bn_relu_bwd_partial_kernel<<<chunks, 256, 0, s>>>(z_padded, dy_padded, P, H + 2, W + 2, C, scale, shift, mean, rstd, partial);
+    dmst::bn_relu_bwd_final_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, chunks, C, dgamma, dbeta);
+    const float inv_count = batch_stats ? (float)(1.0 / ((double)B * H * W)) : 0.0f;
+    dmst::bn_relu_bwd_apply_kernel<<<dmst::grid_for((long long)P * (C / 4)), 256, 0, s>>>(
+        z_padded, dy_padded, dz_padded, P, H + 2, W + 2, C, scale, shift, mean, rstd, dgamma, dbeta, inv_count);
+    return (int)cudaGetLastError();
+}
+int dmst_conv_avgpool_backward(const float* dy, float* dx_padded, int B, int C, int H, int W, int kh, int kw,
+                               int dy_padded_nhwc, void* stream) {
+    if (!dy || !dx_padded || kh <= 0 || kw <= 0 || H / kh <= 0 || W / kw <= 0 || (C & 3)) return DMST_EINVAL;
+    const long long total = (long long)B * (H + 2) * (W + 2) * (C / 4);
+    dmst::avgpool_bwd_kernel<<<dmst::grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, dx_padded, B, C, H, W, kh, kw,
+                                                                                                       dy_padded_nhwc);
+    return (int)cudaGetLastError();
+}
 size_t dmst_spectrogram_workspace_bytes(int B, int C, int T, int n_fft, int hop) {
     dmst::SpecWs w;
     if (B <= 0 || C <= 0 || dmst::spec_carve(nullptr, B * C, T, n_fft, hop, &w) != 0) return 0;
@@ -219,6 +253,10 @@ int dmst_spectrogram_frontend(const float* x, long long row_stride, const float*
                                       workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 #else
+int dmst_conv_affine_relu_to(const float*, float*, const float*, const float*, int, int, int, int, void*) { return DMST_EINVAL; }
+int dmst_conv_bn_relu_backward(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
+                               int, int, float*, float*, float*, void*, size_t, void*) { return DMST_EINVAL; }
+int dmst_conv_avgpool_backward(const float*, float*, int, int, int, int, int, int, int, void*) { return DMST_EINVAL; }
 size_t dmst_spectrogram_workspace_bytes(int, int, int, int, int) { return 0; }
 int dmst_spectrogram_frontend(const float*, long long, const float*, int, int, int, int, int, float, float, float*, void*,
                               size_t, void*) { return DMST_EINVAL; }

@@ -470,27 +470,72 @@ __global__ void repack_weights_kernel(const float* w, float* w9, int Cout, int C
 // ---- training-mode BatchNorm support: per-channel batch statistics of a raw conv output ----
 // The zero border contributes nothing, so sums over all P rows are sums over the B*H*W pixels.
 constexpr int kStatRows = 512;
-__global__ void channel_partial_kernel(const float* y, int P, int C, float* partial /*[chunks][2][C]*/) {
+// Thread layout of the per-channel reductions over a chunk of kStatRows rows of a [P][C] tensor: a block of 256
+// threads covers min(C/4, 256) float4 columns x (256 / columns) rows at a time (all threads load 128 bits,
+// consecutive threads consecutive addresses); the row lanes are then added in a fixed order through shared memory.
+struct StatLayout {
+    int cols, lanes, cq, rl;
+    __device__ __forceinline__ StatLayout(int C) {
+        const int C4 = C >> 2;
+        cols = C4 < 256 ? C4 : 256;
+        lanes = 256 / cols;
+        cq = threadIdx.x % cols;
+        rl = threadIdx.x / cols;
+    }
+};
+// sums the per-lane float4 pairs of one column group over the row lanes and stores them: partial[chunk][0/1][c..c+3]
+__device__ __forceinline__ void stat_lane_reduce(const StatLayout& L, float4 a, float4 b, float4* sh /*[2][256]*/,
+                                                 float* partial, int chunk, int C, int c) {
+    sh[threadIdx.x] = a;
+    sh[256 + threadIdx.x] = b;
+    __syncthreads();
+    if (L.rl == 0 && c < C) {
+        for (int l = 1; l < L.lanes; ++l) {
+            const float4 u = sh[l * L.cols + L.cq], v = sh[256 + l * L.cols + L.cq];
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+            b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+        }
+        *reinterpret_cast<float4*>(partial + ((size_t)chunk * 2 + 0) * C + c) = a;
+        *reinterpret_cast<float4*>(partial + ((size_t)chunk * 2 + 1) * C + c) = b;
+    }
+    __syncthreads();
+}
+// C % 4 == 0 (every Cnn14 layer); blockDim.x == 256
+__global__ void __launch_bounds__(256) channel_partial_kernel(const float* y, int P, int C, float* partial /*[chunks][2][C]*/) {
+    __shared__ float4 sh[512];
+    const StatLayout L(C);
     const int chunk = blockIdx.x;
     const int r0 = chunk * kStatRows, r1 = min(r0 + kStatRows, P);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = 0.0f, s2 = 0.0f;
-        for (int r = r0; r < r1; ++r) {
-            const float v = __ldg(y + (size_t)r * C + c);
-            s += v; s2 = fmaf(v, v, s2);
-        }
-        partial[((size_t)chunk * 2 + 0) * C + c] = s;
-        partial[((size_t)chunk * 2 + 1) * C + c] = s2;
+    for (int g = 0; g * L.cols < (C >> 2); ++g) {
+        const int c = (g * L.cols + L.cq) << 2;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s;
+        if (c < C && L.rl < L.lanes)
+            for (int r = r0 + L.rl; r < r1; r += L.lanes) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(y + (size_t)r * C + c));
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+            }
+        stat_lane_reduce(L, s, s2, sh, partial, chunk, C, c);
     }
 }
+// one warp per channel: lanes stride over the chunks in float64, fixed-order butterfly at the end
+__device__ __forceinline__ void stat_chunk_sums(const float* partial, int chunks, int C, int c, double& s, double& s2) {
+    const int lane = threadIdx.x & 31;
+    s = 0.0; s2 = 0.0;
+    for (int k = lane; k < chunks; k += 32) { s += partial[((size_t)k * 2 + 0) * C + c]; s2 += partial[((size_t)k * 2 + 1) * C + c]; }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+}
+// grid: ceil(C / 8) blocks of 256 threads
 __global__ void channel_final_kernel(const float* partial, int chunks, int C, double count, float* mean, float* var_biased) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
-    double s = 0.0, s2 = 0.0;
-    for (int k = 0; k < chunks; ++k) { s += partial[((size_t)k * 2 + 0) * C + c]; s2 += partial[((size_t)k * 2 + 1) * C + c]; }
-    const double m = s / count;
-    mean[c] = (float)m;
-    var_biased[c] = (float)fmax(s2 / count - m * m, 0.0);
+    double s, s2;
+    stat_chunk_sums(partial, chunks, C, c, s, s2);
+    if ((threadIdx.x & 31) == 0) {
+        const double m = s / count;
+        mean[c] = (float)m;
+        var_biased[c] = (float)fmax(s2 / count - m * m, 0.0);
+    }
 }
 // in-place y = relu(y * scale[c] + shift[c]) on interior pixels (border stays zero)
 __global__ void affine_relu_kernel(float* y, int P, int Hp, int Wp, int C, const float* scale, const float* shift, int relu) {
@@ -504,6 +549,126 @@ __global__ void affine_relu_kernel(float* y, int P, int Hp, int Wp, int C, const
             float v = fmaf(y[i], __ldg(scale + c), __ldg(shift + c));
             y[i] = relu ? fmaxf(v, 0.0f) : v;
         }
+    }
+}
+// out-of-place twin of affine_relu_kernel (the differentiable path keeps the raw convolution output):
+// y = relu(z * scale[c] + shift[c]) on interior pixels, zero on the border
+__global__ void affine_relu_to_kernel(const float* z, float* y, int P, int Hp, int Wp, int C, const float* scale,
+                                      const float* shift) {
+    const int C4 = C >> 2;
+    const long long total = (long long)P * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i / C4), c = (int)(i - (long long)p * C4) << 2;
+        const int rem = p % (Hp * Wp);
+        const int hp = rem / Wp, wp = rem - hp * Wp;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(z + (size_t)p * C + c));
+            const float4 a = __ldg(reinterpret_cast<const float4*>(scale + c)), b = __ldg(reinterpret_cast<const float4*>(shift + c));
+            o.x = fmaxf(fmaf(v.x, a.x, b.x), 0.f); o.y = fmaxf(fmaf(v.y, a.y, b.y), 0.f);
+            o.z = fmaxf(fmaf(v.z, a.z, b.z), 0.f); o.w = fmaxf(fmaf(v.w, a.w, b.w), 0.f);
+        }
+        *reinterpret_cast<float4*>(y + (size_t)p * C + c) = o;
+    }
+}
+
+// ---- backward of y = relu(BatchNorm(z)) (mst/panns.py:79-80 under autograd) on zero-bordered NHWC ----
+// With zhat = (z - mean) * rstd, dyr = dy * [scale * z + shift > 0]:
+//   dbeta = sum dyr, dgamma = sum dyr * zhat,
+//   batch statistics:   dz = gamma * rstd * (dyr - dbeta / n - zhat * dgamma / n)
+//   running statistics: dz = gamma * rstd * dyr
+// Pass 1 accumulates the two sums per channel over chunks of rows (fixed order => deterministic), pass 2 adds the
+// chunks in float64, pass 3 writes dz (zero on the border).
+__global__ void __launch_bounds__(256) bn_relu_bwd_partial_kernel(const float* z, const float* dy, int P, int Hp, int Wp, int C,
+                                                                  const float* scale, const float* shift, const float* mean,
+                                                                  const float* rstd, float* partial /*[chunks][2][C]*/) {
+    __shared__ float4 sh[512];
+    const StatLayout L(C);
+    const int chunk = blockIdx.x;
+    const int r0 = chunk * kStatRows, r1 = min(r0 + kStatRows, P);
+    for (int g = 0; g * L.cols < (C >> 2); ++g) {
+        const int c = (g * L.cols + L.cq) << 2;
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+        if (c < C && L.rl < L.lanes) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(scale + c)), b = __ldg(reinterpret_cast<const float4*>(shift + c));
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mean + c)), rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
+            for (int r = r0 + L.rl; r < r1; r += L.lanes) {
+                const int rem = r % (Hp * Wp);
+                const int hp = rem / Wp, wp = rem - hp * Wp;
+                if (hp < 1 || hp > Hp - 2 || wp < 1 || wp > Wp - 2) continue;  // border rows are padding
+                const float4 v = __ldg(reinterpret_cast<const float4*>(z + (size_t)r * C + c));
+                const float4 d = __ldg(reinterpret_cast<const float4*>(dy + (size_t)r * C + c));
+                const float gx = fmaf(v.x, a.x, b.x) > 0.0f ? d.x : 0.0f, gy = fmaf(v.y, a.y, b.y) > 0.0f ? d.y : 0.0f;
+                const float gz = fmaf(v.z, a.z, b.z) > 0.0f ? d.z : 0.0f, gw = fmaf(v.w, a.w, b.w) > 0.0f ? d.w : 0.0f;
+                s1.x += gx; s1.y += gy; s1.z += gz; s1.w += gw;
+                s2.x = fmaf(gx, (v.x - m.x) * rs.x, s2.x); s2.y = fmaf(gy, (v.y - m.y) * rs.y, s2.y);
+                s2.z = fmaf(gz, (v.z - m.z) * rs.z, s2.z); s2.w = fmaf(gw, (v.w - m.w) * rs.w, s2.w);
+            }
+        }
+        stat_lane_reduce(L, s1, s2, sh, partial, chunk, C, c);
+    }
+}
+// grid: ceil(C / 8) blocks of 256 threads
+__global__ void bn_relu_bwd_final_kernel(const float* partial, int chunks, int C, float* dgamma, float* dbeta) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    double s1, s2;
+    stat_chunk_sums(partial, chunks, C, c, s1, s2);
+    if ((threadIdx.x & 31) == 0) { dbeta[c] = (float)s1; dgamma[c] = (float)s2; }
+}
+__global__ void bn_relu_bwd_apply_kernel(const float* z, const float* dy, float* dz, int P, int Hp, int Wp, int C,
+                                         const float* scale, const float* shift, const float* mean, const float* rstd,
+                                         const float* dgamma, const float* dbeta, float inv_count /* 0: running statistics */) {
+    const int C4 = C >> 2;
+    const long long total = (long long)P * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i / C4), c = (int)(i - (long long)p * C4) << 2;
+        const int rem = p % (Hp * Wp);
+        const int hp = rem / Wp, wp = rem - hp * Wp;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2) {
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(z + (size_t)p * C + c));
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + (size_t)p * C + c));
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+            float r[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a = __ldg(scale + c + e), b = __ldg(shift + c + e);
+                const float gr = fmaf(v[e], a, b) > 0.0f ? g[e] : 0.0f;
+                const float zh = (v[e] - __ldg(mean + c + e)) * __ldg(rstd + c + e);
+                r[e] = a * (gr - inv_count * (__ldg(dbeta + c + e) + zh * __ldg(dgamma + c + e)));
+            }
+            o = make_float4(r[0], r[1], r[2], r[3]);
+        }
+        *reinterpret_cast<float4*>(dz + (size_t)p * C + c) = o;
+    }
+}
+
+// backward of avgpool_kernel: dx (zero-bordered NHWC) from dy (NCHW (B, C, Ho, Wo) or zero-bordered NHWC)
+__global__ void avgpool_bwd_kernel(const float* dy, float* dx, int B, int C, int H, int W, int kh, int kw, int dy_nhwc_padded) {
+    const int Ho = H / kh, Wo = W / kw, Hp = H + 2, Wp = W + 2;
+    const float inv = 1.0f / (float)(kh * kw);
+    const int C4 = C >> 2;   // C % 4 == 0 checked by the caller
+    const long long total = (long long)B * Hp * Wp * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned pix = (unsigned)(i / (unsigned)C4);
+        const int c = (int)(i - (long long)pix * C4) << 2;
+        const unsigned row = pix / (unsigned)Wp;
+        const int wp = (int)(pix - row * Wp);
+        const int b = (int)(row / (unsigned)Hp);
+        const int hp = (int)(row - (unsigned)b * Hp);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int ho = (hp - 1) / kh, wo = (wp - 1) / kw;
+        if (hp >= 1 && wp >= 1 && ho < Ho && wo < Wo) {
+            if (dy_nhwc_padded) {
+                v = __ldg(reinterpret_cast<const float4*>(dy + (((long long)b * (Ho + 2) + ho + 1) * (Wo + 2) + wo + 1) * C + c));
+            } else {
+                const long long o = (((long long)b * C + c) * Ho + ho) * Wo + wo, cs = (long long)Ho * Wo;
+                v = make_float4(__ldg(dy + o), __ldg(dy + o + cs), __ldg(dy + o + 2 * cs), __ldg(dy + o + 3 * cs));
+            }
+            v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+        }
+        *reinterpret_cast<float4*>(dx + (size_t)pix * C + c) = v;
     }
 }
 inline int grid_for(long long total) { long long b = (total + 255) / 256; return (int)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b)); }

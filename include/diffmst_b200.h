@@ -189,6 +189,20 @@ int dmst_conv_affine_relu(float* y_padded, const float* scale, const float* shif
 int dmst_conv_avgpool(const float* x_padded, float* y, int B, int C, int H, int W, int kh, int kw,
                       int out_padded_nhwc, void* stream);
 
+/* Differentiable path of the same units (autograd of mst/panns.py:79-85).  y = relu(z * scale + shift) out of place
+ * (the raw convolution output z is kept for backward); backward of y = relu(BatchNorm(z)): given dL/dy it writes
+ * dL/dz (zero border), dL/dgamma and dL/dbeta, with scale = gamma * rstd, shift = beta - mean * scale;
+ * batch_stats = 1 for training-mode statistics (the mean / variance terms of the BatchNorm gradient), 0 for running
+ * statistics.  Workspace: dmst_conv_stats_workspace_bytes.  C % 4 == 0.  Backward of dmst_conv_avgpool. */
+int dmst_conv_affine_relu_to(const float* z_padded, float* y_padded, const float* scale, const float* shift, int B,
+                             int H, int W, int C, void* stream);
+int dmst_conv_bn_relu_backward(const float* z_padded, const float* dy_padded, const float* scale, const float* shift,
+                               const float* mean, const float* rstd, int batch_stats, int B, int H, int W, int C,
+                               float* dz_padded, float* dgamma, float* dbeta, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int dmst_conv_avgpool_backward(const float* dy, float* dx_padded, int B, int C, int H, int W, int kh, int kw,
+                               int dy_padded_nhwc, void* stream);
+
 /* Spectrogram front-end of the encoder, replaces the torch.stft / abs / pow lines of
  * SpectrogramEncoder.forward (mst/modules.py:787-800): x holds B*C waveforms of T samples (row r = b*C + c at
  * x + r*row_stride); window = n_fft Hann coefficients; the result (|STFT| + eps)^power is written as the
