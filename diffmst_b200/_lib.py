@@ -73,6 +73,8 @@ def lib():
     l.dmst_conv_nchw_to_padded_nhwc.argtypes = [vp, vp, i, i, i, i, vp]
     l.dmst_conv_repack_weights.restype = i
     l.dmst_conv_repack_weights.argtypes = [vp, vp, i, i, vp]
+    l.dmst_conv_repack_weights_dgrad.restype = i
+    l.dmst_conv_repack_weights_dgrad.argtypes = [vp, vp, i, i, vp]
     l.dmst_conv3x3_forward.restype = i
     l.dmst_conv3x3_forward.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     l.dmst_conv3x3_workspace_bytes.restype = sz

@@ -107,7 +107,10 @@ class _Conv3x3Function(torch.autograd.Function):
     """z = conv3x3(x) on zero-bordered NHWC tensors (no bias, stride 1, padding 1; mst/panns.py:33-47)."""
 
     @staticmethod
-    def forward(ctx, x_pad, weight):
+    def forward(ctx, x_pad, weight, clean_border=False):
+        # clean_border: the gradient that will arrive for z is known to be zero on the border (it comes from
+        # _BnReluFunction), so backward need not clear it
+        ctx.clean_border = bool(clean_border)
         lib = _lib.lib()
         B, Hp, Wp, Cin = x_pad.shape
         Cout = weight.shape[0]
@@ -115,22 +118,25 @@ class _Conv3x3Function(torch.autograd.Function):
         w9 = _repack(weight)
         z = torch.empty(B, Hp, Wp, Cout, dtype=torch.float32, device=x_pad.device)
         _conv3x3(x_pad, w9, None, None, z, B, Hp - 2, Wp - 2, Cin, Cout, 0)
-        ctx.save_for_backward(x_pad, w9)
+        ctx.save_for_backward(x_pad, w9, weight)
         return z
 
     @staticmethod
     def backward(ctx, gz):
         lib = _lib.lib()
-        x_pad, w9 = ctx.saved_tensors
+        x_pad, w9, weight = ctx.saved_tensors
         B, Hp, Wp, Cin = x_pad.shape
         Cout = w9.shape[1]
         gz = gz.contiguous()
-        # the border of the output is padding: whatever gradient arrives there does not exist upstream
-        gz[:, 0, :, :] = 0; gz[:, -1, :, :] = 0; gz[:, :, 0, :] = 0; gz[:, :, -1, :] = 0
+        if not ctx.clean_border:
+            # the border of the output is padding: whatever gradient arrives there does not exist upstream
+            gz[:, 0, :, :] = 0; gz[:, -1, :, :] = 0; gz[:, :, 0, :] = 0; gz[:, :, -1, :] = 0
         gx = gw = None
         if ctx.needs_input_grad[0]:
             # dgrad: correlation with the flipped taps, channel roles swapped -> the same kernel
-            w9t = w9.flip(0).transpose(1, 2).contiguous()          # [tap][Cin][Cout]
+            w9t = torch.empty(9, Cin, Cout, dtype=torch.float32, device=gz.device)   # [flipped tap][Cin][Cout]
+            _lib.check(lib.dmst_conv_repack_weights_dgrad(_ptr(weight.detach().contiguous()), _ptr(w9t), Cout, Cin,
+                                                          _stream(gz.device)), "dmst_conv_repack_weights_dgrad")
             gx = torch.empty_like(x_pad)
             _conv3x3(gz, w9t, None, None, gx, B, Hp - 2, Wp - 2, Cout, Cin, 0, "dmst_conv3x3_forward (dgrad)")
         if ctx.needs_input_grad[1]:
@@ -163,7 +169,7 @@ class _Conv3x3Function(torch.autograd.Function):
             finally:
                 torch.backends.cuda.matmul.allow_tf32 = tf32
             gw = g9.permute(1, 2, 0).reshape(Cout, Cin, 3, 3)
-        return gx, gw
+        return gx, gw, None
 
 
 def _needs_grad(x, *modules):
@@ -260,9 +266,10 @@ class _AvgPoolFunction(torch.autograd.Function):
 def _conv_bn_relu_autograd(x_pad, conv: nn.Conv2d, bn, training: bool):
     """Differentiable twin of _conv_bn_relu: tensor-core conv Function, then BatchNorm + ReLU as one CUDA Function
     (statistics, normalisation and their backward in csrc/conv_tc.cuh)."""
-    z = _Conv3x3Function.apply(x_pad, conv.weight)
-    C = z.shape[-1]
-    if isinstance(bn, nn.BatchNorm2d) and C % 4 == 0 and _CUDA_BN_POOL:
+    C = conv.weight.shape[0]
+    cuda_bn = isinstance(bn, nn.BatchNorm2d) and C % 4 == 0 and _CUDA_BN_POOL
+    z = _Conv3x3Function.apply(x_pad, conv.weight, cuda_bn)
+    if cuda_bn:
         batch_stats = bn.training or bn.running_mean is None   # nn.BatchNorm2d.forward's rule
         if batch_stats:
             mean, var = _channel_stats(z.detach())

@@ -160,6 +160,12 @@ int dmst_conv_repack_weights(const float* w, float* w9, int Cout, int Cin, void*
     dmst::repack_weights_kernel<<<dmst::grid_for(9LL * Cout * Cin), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, w9, Cout, Cin);
     return (int)cudaGetLastError();
 }
+int dmst_conv_repack_weights_dgrad(const float* w, float* w9t, int Cout, int Cin, void* stream) {
+    if (!w || !w9t || Cout <= 0 || Cin <= 0) return DMST_EINVAL;
+    dmst::repack_weights_dgrad_kernel<<<dim3((Cin + 31) / 32, (Cout + 31) / 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        w, w9t, Cout, Cin);
+    return (int)cudaGetLastError();
+}
 int dmst_conv3x3_forward(const float* x_padded, const float* w9, const float* scale, const float* shift, float* y_padded,
                          int B, int H, int W, int Cin, int Cout, int relu, void* stream) {
     return dmst::conv3x3_forward(x_padded, w9, scale, shift, y_padded, B, H, W, Cin, Cout, relu,
@@ -177,14 +183,15 @@ int dmst_conv3x3_forward_ws(const float* x_padded, const float* w9, const float*
 }
 size_t dmst_conv_stats_workspace_bytes(int B, int H, int W, int C) {
     const long long P = (long long)B * (H + 2) * (W + 2);
-    return (size_t)((P + dmst::kStatRows - 1) / dmst::kStatRows) * 2 * C * sizeof(float);
+    const int rows = dmst::stat_rows(P);
+    return (size_t)((P + rows - 1) / rows) * 2 * C * sizeof(float);
 }
 int dmst_conv_channel_stats(const float* y_padded, int B, int H, int W, int C, float* mean, float* var_biased,
                             void* workspace, size_t workspace_bytes, void* stream) {
     if (!y_padded || !mean || !var_biased || !workspace || (C & 3)) return DMST_EINVAL;
     if (workspace_bytes < dmst_conv_stats_workspace_bytes(B, H, W, C)) return DMST_EINVAL;
     const int P = B * (H + 2) * (W + 2);
-    const int chunks = (P + dmst::kStatRows - 1) / dmst::kStatRows;
+    const int chunks = (P + dmst::stat_rows(P) - 1) / dmst::stat_rows(P);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     dmst::channel_partial_kernel<<<chunks, 256, 0, s>>>(y_padded, P, C, reinterpret_cast<float*>(workspace));
     dmst::channel_final_kernel<<<(C + 7) / 8, 256, 0, s>>>(reinterpret_cast<float*>(workspace), chunks, C,
@@ -223,7 +230,7 @@ int dmst_conv_bn_relu_backward(const float* z_padded, const float* dy_padded, co
         return DMST_EINVAL;
     if (workspace_bytes < dmst_conv_stats_workspace_bytes(B, H, W, C)) return DMST_EINVAL;
     const int P = B * (H + 2) * (W + 2);
-    const int chunks = (P + dmst::kStatRows - 1) / dmst::kStatRows;
+    const int chunks = (P + dmst::stat_rows(P) - 1) / dmst::stat_rows(P);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     float* partial = reinterpret_cast<float*>(workspace);
     dmst::bn_relu_bwd_partial_kernel<<<chunks, 256, 0, s>>>(z_padded, dy_padded, P, H + 2, W + 2, C, scale, shift, mean, rstd, partial);
@@ -262,6 +269,7 @@ int dmst_spectrogram_frontend(const float*, long long, const float*, int, int, i
                               size_t, void*) { return DMST_EINVAL; }
 int dmst_conv_nchw_to_padded_nhwc(const float*, float*, int, int, int, int, void*) { return DMST_EINVAL; }
 int dmst_conv_repack_weights(const float*, float*, int, int, void*) { return DMST_EINVAL; }
+int dmst_conv_repack_weights_dgrad(const float*, float*, int, int, void*) { return DMST_EINVAL; }
 int dmst_conv3x3_forward(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, void*) { return DMST_EINVAL; }
 size_t dmst_conv3x3_workspace_bytes(int, int, int, int, int) { return 0; }
 int dmst_conv3x3_forward_ws(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, void*, size_t, void*) { return DMST_EINVAL; }

@@ -467,10 +467,35 @@ __global__ void repack_weights_kernel(const float* w, float* w9, int Cout, int C
 }
 
 
+// [Cout][Cin][3][3] -> [9][Cin][Cout] with the taps flipped: the weights of the input-gradient convolution (dgrad =
+// the same shifted GEMM with the channel roles swapped).  One block per 32 x 32 (Cout, Cin) tile: 288 contiguous
+// floats are read per output channel, 32 contiguous output channels written per (tap, input channel).
+// grid: (ceil(Cin/32), ceil(Cout/32)), block 256
+__global__ void repack_weights_dgrad_kernel(const float* w, float* w9t, int Cout, int Cin) {
+    __shared__ float tile[32][289];
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    const int nci = min(32, Cin - ci0);
+    for (int i = threadIdx.x; i < 32 * 288; i += blockDim.x) {
+        const int r = i / 288, q = i - r * 288;
+        if (co0 + r < Cout && q < nci * 9) tile[r][q] = __ldg(w + ((size_t)(co0 + r) * Cin + ci0) * 9 + q);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * 32 * 32; i += blockDim.x) {
+        const int co = i & 31, ci = (i >> 5) & 31, tap = i >> 10;
+        if (co0 + co < Cout && ci < nci)
+            w9t[((size_t)(8 - tap) * Cin + ci0 + ci) * Cout + co0 + co] = tile[co][ci * 9 + tap];
+    }
+}
+
 // ---- training-mode BatchNorm support: per-channel batch statistics of a raw conv output ----
 // The zero border contributes nothing, so sums over all P rows are sums over the B*H*W pixels.
-constexpr int kStatRows = 512;
-// Thread layout of the per-channel reductions over a chunk of kStatRows rows of a [P][C] tensor: a block of 256
+// rows of a [P][C] tensor per reduction chunk (= per CTA): at most 512, fewer on the small deep layers so that the
+// grid still covers the device a few times
+__host__ __device__ inline int stat_rows(long long P) {
+    long long r = P / (4 * 148);
+    return (int)(r < 32 ? 32 : (r > 512 ? 512 : r));
+}
+// Thread layout of the per-channel reductions over a chunk of stat_rows(P) rows of a [P][C] tensor: a block of 256
 // threads covers min(C/4, 256) float4 columns x (256 / columns) rows at a time (all threads load 128 bits,
 // consecutive threads consecutive addresses); the row lanes are then added in a fixed order through shared memory.
 struct StatLayout {
@@ -505,11 +530,13 @@ __global__ void __launch_bounds__(256) channel_partial_kernel(const float* y, in
     __shared__ float4 sh[512];
     const StatLayout L(C);
     const int chunk = blockIdx.x;
-    const int r0 = chunk * kStatRows, r1 = min(r0 + kStatRows, P);
+    const int rows = stat_rows(P);
+    const int r0 = chunk * rows, r1 = min(r0 + rows, P);
     for (int g = 0; g * L.cols < (C >> 2); ++g) {
         const int c = (g * L.cols + L.cq) << 2;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s;
         if (c < C && L.rl < L.lanes)
+#pragma unroll 8
             for (int r = r0 + L.rl; r < r1; r += L.lanes) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(y + (size_t)r * C + c));
                 s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -585,21 +612,26 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_partial_kernel(const float* z
     __shared__ float4 sh[512];
     const StatLayout L(C);
     const int chunk = blockIdx.x;
-    const int r0 = chunk * kStatRows, r1 = min(r0 + kStatRows, P);
+    const int rows = stat_rows(P);
+    const int r0 = chunk * rows, r1 = min(r0 + rows, P);
     for (int g = 0; g * L.cols < (C >> 2); ++g) {
         const int c = (g * L.cols + L.cq) << 2;
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
         if (c < C && L.rl < L.lanes) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(scale + c)), b = __ldg(reinterpret_cast<const float4*>(shift + c));
             const float4 m = __ldg(reinterpret_cast<const float4*>(mean + c)), rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
+            // (hp, wp) of the row, advanced incrementally: no division in the loop
+            int rem = (r0 + L.rl) % (Hp * Wp);
+            int hp = rem / Wp, wp = rem - hp * Wp;
+#pragma unroll 2
             for (int r = r0 + L.rl; r < r1; r += L.lanes) {
-                const int rem = r % (Hp * Wp);
-                const int hp = rem / Wp, wp = rem - hp * Wp;
-                if (hp < 1 || hp > Hp - 2 || wp < 1 || wp > Wp - 2) continue;  // border rows are padding
                 const float4 v = __ldg(reinterpret_cast<const float4*>(z + (size_t)r * C + c));
                 const float4 d = __ldg(reinterpret_cast<const float4*>(dy + (size_t)r * C + c));
-                const float gx = fmaf(v.x, a.x, b.x) > 0.0f ? d.x : 0.0f, gy = fmaf(v.y, a.y, b.y) > 0.0f ? d.y : 0.0f;
-                const float gz = fmaf(v.z, a.z, b.z) > 0.0f ? d.z : 0.0f, gw = fmaf(v.w, a.w, b.w) > 0.0f ? d.w : 0.0f;
+                const bool in = hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2;   // border rows are padding
+                wp += L.lanes;
+                while (wp >= Wp) { wp -= Wp; if (++hp == Hp) hp = 0; }
+                const float gx = (in && fmaf(v.x, a.x, b.x) > 0.0f) ? d.x : 0.0f, gy = (in && fmaf(v.y, a.y, b.y) > 0.0f) ? d.y : 0.0f;
+                const float gz = (in && fmaf(v.z, a.z, b.z) > 0.0f) ? d.z : 0.0f, gw = (in && fmaf(v.w, a.w, b.w) > 0.0f) ? d.w : 0.0f;
                 s1.x += gx; s1.y += gy; s1.z += gz; s1.w += gw;
                 s2.x = fmaf(gx, (v.x - m.x) * rs.x, s2.x); s2.y = fmaf(gy, (v.y - m.y) * rs.y, s2.y);
                 s2.z = fmaf(gz, (v.z - m.z) * rs.z, s2.z); s2.w = fmaf(gw, (v.w - m.w) * rs.w, s2.w);
@@ -630,13 +662,17 @@ __global__ void bn_relu_bwd_apply_kernel(const float* z, const float* dy, float*
             const float4 v4 = __ldg(reinterpret_cast<const float4*>(z + (size_t)p * C + c));
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + (size_t)p * C + c));
             const float v[4] = {v4.x, v4.y, v4.z, v4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(scale + c)), b4 = __ldg(reinterpret_cast<const float4*>(shift + c));
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + c)), r4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
+            const float4 dg4 = __ldg(reinterpret_cast<const float4*>(dgamma + c)), db4 = __ldg(reinterpret_cast<const float4*>(dbeta + c));
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
+            const float rs[4] = {r4.x, r4.y, r4.z, r4.w}, dg[4] = {dg4.x, dg4.y, dg4.z, dg4.w}, db[4] = {db4.x, db4.y, db4.z, db4.w};
             float r[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float a = __ldg(scale + c + e), b = __ldg(shift + c + e);
-                const float gr = fmaf(v[e], a, b) > 0.0f ? g[e] : 0.0f;
-                const float zh = (v[e] - __ldg(mean + c + e)) * __ldg(rstd + c + e);
-                r[e] = a * (gr - inv_count * (__ldg(dbeta + c + e) + zh * __ldg(dgamma + c + e)));
+                const float gr = fmaf(v[e], a[e], b[e]) > 0.0f ? g[e] : 0.0f;
+                const float zh = (v[e] - m[e]) * rs[e];
+                r[e] = a[e] * (gr - inv_count * (db[e] + zh * dg[e]));
             }
             o = make_float4(r[0], r[1], r[2], r[3]);
         }

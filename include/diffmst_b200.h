@@ -168,6 +168,9 @@ int dmst_peak_normalize(const float* x, long long batch_stride, long long ch_str
 int dmst_conv_nchw_to_padded_nhwc(const float* x, float* y, int B, int C, int H, int W, void* stream);
 /* nn.Conv2d weight (Cout, Cin, 3, 3) -> (9, Cout, Cin) */
 int dmst_conv_repack_weights(const float* w, float* w9, int Cout, int Cin, void* stream);
+/* the same weight as the operand of the input-gradient convolution: (9, Cin, Cout), taps flipped, so that
+ * dL/dx = dmst_conv3x3_forward(dL/dz, w9t) with the channel counts swapped */
+int dmst_conv_repack_weights_dgrad(const float* w, float* w9t, int Cout, int Cin, void* stream);
 /* y = [relu](conv3x3(x) * scale[c] + shift[c]); scale/shift may be NULL (1 / 0).  TF32 tensor-core
  * path (tcgen05 + TMA) when Cin % 32 == 0 and Cout % 64 == 0, CUDA-core path otherwise (first layer). */
 int dmst_conv3x3_forward(const float* x_padded, const float* w9, const float* scale, const float* shift,
