@@ -41,7 +41,7 @@ def _to_padded_nhwc(x):
     return y
 
 
-# measurement aid (scripts/cnn14_train_bench.py): False routes BatchNorm / ReLU / pooling of the differentiable path
+# measurement aid (tests/tools/cnn14_train_bench.py): False routes BatchNorm / ReLU / pooling of the differentiable path
 # through PyTorch ops on NHWC views, as before the CUDA Functions existed
 _CUDA_BN_POOL = True
 

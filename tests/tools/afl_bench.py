@@ -1,7 +1,7 @@
-"""AudioFeatureLoss forward+backward: ours vs the oracle's PyTorch composition run on the same GPU
+"""TEST INFRASTRUCTURE (uses the oracle as the comparison arm): AudioFeatureLoss forward+backward: ours vs the oracle's PyTorch composition run on the same GPU
 (the reference's own GPU path is that composition of torch ops, mst/loss.py:62-260)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from diffmst_b200 import AudioFeatureLoss
 from oracle.loss import OracleAudioFeatureLoss

@@ -1,7 +1,7 @@
-"""Cnn14 forward + backward (training mode, batch statistics) at the encoder's real input size: ours with the CUDA
+"""TEST INFRASTRUCTURE (uses the oracle as the comparison arm): Cnn14 forward + backward (training mode, batch statistics) at the encoder's real input size: ours with the CUDA
 BatchNorm/ReLU/pooling Functions, ours with those on PyTorch ops, and the reference modules on cuDNN."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from diffmst_b200 import Cnn14, conv
 from oracle.panns import OracleCnn14

@@ -1,7 +1,7 @@
-"""Per-layer timing of the Cnn14 conv trunk (tensor-core row): TFLOP/s per 3x3 convolution at the
+"""TEST INFRASTRUCTURE (uses the oracle as the comparison arm): Per-layer timing of the Cnn14 conv trunk (tensor-core row): TFLOP/s per 3x3 convolution at the
 encoder's real shapes (mst/modules.py:786-806: 1025 bins x 257 frames), batch of items = argv[1]."""
 import ctypes, json, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from diffmst_b200 import _lib
 from diffmst_b200.conv import _ptr, _stream
@@ -9,8 +9,8 @@ from diffmst_b200.conv import _ptr, _stream
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 lib = _lib.lib()
 dev = torch.device("cuda", 0)
-peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) if os.path.exists(
-    os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
+peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "..", "MEASURED_PEAKS.json"))) if os.path.exists(
+    os.path.join(os.path.dirname(__file__), "..", "..", "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
 tf32_peak = peaks["bf16_tflops"] / 2.0   # dense TF32 is half the BF16 rate on this part
 layers = [(64, 64, 1025, 257), (64, 128, 512, 128), (128, 128, 512, 128), (128, 256, 128, 32), (256, 256, 128, 32),
           (256, 512, 32, 16), (512, 512, 32, 16), (512, 1024, 8, 8), (1024, 1024, 8, 8), (1024, 2048, 2, 4), (2048, 2048, 2, 4)]

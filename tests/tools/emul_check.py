@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE: runs the host-emulated kernels (tests/emul) against the float64 oracle on a
 small case; for debugging kernel logic in the GPU-less container."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
 import numpy as np, torch
 import harness

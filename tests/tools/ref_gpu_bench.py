@@ -1,8 +1,8 @@
-"""Context number (not a bench contract line): the reference ALGORITHM (oracle port of dasp-pytorch's
+"""TEST INFRASTRUCTURE (uses the oracle as the comparison arm): Context number (not a bench contract line): the reference ALGORITHM (oracle port of dasp-pytorch's
 frequency-sampling path + auraloss MRSTFT, float32) run as PyTorch ops on the same GPU, i.e. what the
 reference itself would execute on a B200, next to our step.  Same workload as bench.py."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import bench
 from oracle.auraloss.freq import MultiResolutionSTFTLoss as OracleMR
