@@ -89,6 +89,10 @@ def lib():
     l.dmst_conv_affine_relu.argtypes = [vp, vp, vp, i, i, i, i, i, vp]
     l.dmst_conv_avgpool.restype = i
     l.dmst_conv_avgpool.argtypes = [vp, vp, i, i, i, i, i, i, i, vp]
+    l.dmst_conv3x3_wgrad_workspace_bytes.restype = sz
+    l.dmst_conv3x3_wgrad_workspace_bytes.argtypes = [i, i, i, i, i]
+    l.dmst_conv3x3_wgrad.restype = i
+    l.dmst_conv3x3_wgrad.argtypes = [vp, vp, vp, i, i, i, i, i, vp, sz, vp]
     l.dmst_conv_affine_relu_to.restype = i
     l.dmst_conv_affine_relu_to.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
     l.dmst_conv_bn_relu_backward.restype = i

@@ -45,6 +45,8 @@ def _to_padded_nhwc(x):
 # through PyTorch ops on NHWC views, as before the CUDA Functions existed
 _CUDA_BN_POOL = True
 
+_TC_WGRAD = True       # False: weight gradient through the split-K batched library GEMMs (comparison / fallback arm)
+
 _REPACK_CACHE = {}   # id(parameter) -> (weak reference to it, data_ptr, version, [9][Cout][Cin] tensor)
 
 
@@ -140,10 +142,18 @@ class _Conv3x3Function(torch.autograd.Function):
             gx = torch.empty_like(x_pad)
             _conv3x3(gz, w9t, None, None, gx, B, Hp - 2, Wp - 2, Cout, Cin, 0, "dmst_conv3x3_forward (dgrad)")
         if ctx.needs_input_grad[1]:
-            # wgrad: dW[tap] = dz^T @ x shifted by the tap (a constant row offset in the flattened layout; dz is zero
-            # on the border, so rows that would cross an image edge contribute nothing).  K = all pixels is huge and
-            # the output tiny, so K is split into S chunks run as one batched GEMM per tap and summed afterwards.
-            # TF32 follows torch.backends.cudnn.allow_tf32, the switch that governs the reference's convolutions.
+            # wgrad on the tensor cores: dmst_conv3x3_wgrad (tcgen05, MN-major operands straight from the NHWC tensors)
+            nbytes = lib.dmst_conv3x3_wgrad_workspace_bytes(B, Hp - 2, Wp - 2, Cin, Cout) if _TC_WGRAD else 0
+            if nbytes:
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=gz.device)
+                g9 = torch.empty(9, Cout, Cin, dtype=torch.float32, device=gz.device)
+                _lib.check(lib.dmst_conv3x3_wgrad(_ptr(x_pad), _ptr(gz), _ptr(g9), B, Hp - 2, Wp - 2, Cin, Cout, _ptr(ws), nbytes,
+                                                  _stream(gz.device)), "dmst_conv3x3_wgrad")
+                return gx, g9.permute(1, 2, 0).reshape(Cout, Cin, 3, 3), None
+            # the 1-channel first layer (and channel counts that are not multiples of 32): library GEMMs.
+            # dW[tap] = dz^T @ x shifted by the tap (a constant row offset in the flattened layout; dz is zero on the
+            # border, so rows that would cross an image edge contribute nothing); K = all pixels is split into S chunks
+            # run as one batched GEMM per tap.  TF32 follows torch.backends.cudnn.allow_tf32 (the reference's switch).
             P = B * Hp * Wp
             gzf, xf = gz.view(P, Cout), x_pad.view(P, Cin)
             first = Wp + 1                                   # rows before it / after P - first are border rows: dz = 0

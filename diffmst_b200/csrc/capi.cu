@@ -214,6 +214,15 @@ int dmst_conv_avgpool(const float* x_padded, float* y, int B, int C, int H, int 
                                                                                                    out_padded_nhwc);
     return (int)cudaGetLastError();
 }
+size_t dmst_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return 0;
+    return dmst::conv3x3_wgrad_workspace_bytes(B, H, W, Cin, Cout);
+}
+int dmst_conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* g9, int B, int H, int W, int Cin, int Cout,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    return dmst::conv3x3_wgrad(x_padded, dz_padded, g9, B, H, W, Cin, Cout, workspace, workspace_bytes,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
 int dmst_conv_affine_relu_to(const float* z_padded, float* y_padded, const float* scale, const float* shift, int B, int H,
                              int W, int C, void* stream) {
     if (!z_padded || !y_padded || !scale || !shift || (C & 3)) return DMST_EINVAL;
@@ -260,6 +269,8 @@ int dmst_spectrogram_frontend(const float* x, long long row_stride, const float*
                                       workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 #else
+size_t dmst_conv3x3_wgrad_workspace_bytes(int, int, int, int, int) { return 0; }
+int dmst_conv3x3_wgrad(const float*, const float*, float*, int, int, int, int, int, void*, size_t, void*) { return DMST_EINVAL; }
 int dmst_conv_affine_relu_to(const float*, float*, const float*, const float*, int, int, int, int, void*) { return DMST_EINVAL; }
 int dmst_conv_bn_relu_backward(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
                                int, int, float*, float*, float*, void*, size_t, void*) { return DMST_EINVAL; }

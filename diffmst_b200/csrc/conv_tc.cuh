@@ -723,7 +723,8 @@ inline EncodeTiledFn encode_tiled() {
     return fn;
 }
 // 2-D float32 row-major matrix [rows][cols], box = [box_rows][32 cols] with 128-byte swizzle
-inline int make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+inline int make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn f = encode_tiled();
     if (!f) return 2000;
     cuuint64_t dims[2] = {cols, rows};
@@ -731,7 +732,7 @@ inline int make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_
     cuuint32_t box[2] = {(cuuint32_t)kConvBK, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 2001 + (int)r;
 }
@@ -757,6 +758,231 @@ __global__ void conv_splitk_reduce_kernel(const float* partial, int ksplit, floa
         }
         *reinterpret_cast<float4*>(y + (size_t)p * C + c) = s;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores.  dW[tap][co][ci] = sum_p dz[p][co] * x[p + off(tap)][ci] over all padded
+// pixels p (dz is zero on the border, so products that would cross an image edge vanish): per tap a GEMM with
+// M = Cout, N = Cin and K = pixels.  Both operands are stored with their M / N dimension contiguous
+// ([pixels][channels]), so they are fed as MN-MAJOR UMMA operands: a TMA box of 32 pixel rows x 32 channels
+// (128-byte rows, 32-byte-chunk swizzle) is one "slab", K = 8 pixel rows are 1024 bytes, and the tap shift is
+// a shift of the box's ROW coordinate, which TMA does not constrain (with pixels as the innermost, K-major,
+// coordinate it would have to be a multiple of 16 bytes - why this kernel does not transpose anything).
+// One CTA = (128 output channels) x (32 input channels) x (a contiguous chunk of the pixels): the dz tile of a
+// stage feeds the nine taps' accumulators (9 x 32 TMEM columns); raw sums go to partial[split][9][Cout][Cin],
+// wgrad_reduce_kernel adds the splits in a fixed order.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWgRows = 32;                 // pixel rows (K) per pipeline stage
+constexpr int kWgBM = 128, kWgBN = 32;      // output-channel x input-channel tile
+constexpr int kWgStages = 4;
+constexpr uint32_t kWgSlabBytes = kWgRows * 128;                           // 32 rows x 32 channels
+constexpr uint32_t kWgABytes = (kWgBM / 32) * kWgSlabBytes;                // 4 slabs of dz
+constexpr uint32_t kWgStageBytes = kWgABytes + 9 * kWgSlabBytes;           // + one slab of x per tap
+
+// MN-major TF32 operand.  32-bit MN-major operands exist in one shared-memory layout only: 128-byte rows whose
+// 32-byte chunks are XOR-ed with the row index mod 4 (UMMA layout type "128B swizzle, 32-byte base" = TMA swizzle
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  32-channel slabs `lbo` bytes apart, 4-row K groups 512 bytes apart.
+__device__ __forceinline__ uint64_t umma_smem_desc_mn(uint32_t smem_addr, uint32_t lbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;     // leading byte offset: between slabs along M / N
+    d |= (uint64_t)(512 >> 4) << 32;                // stride byte offset: between 4-row groups along K
+    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+    d |= (uint64_t)1 << 61;                         // SWIZZLE_128B_BASE32B
+    return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N) {
+    return umma_idesc_tf32(M, N) | (1u << 15) | (1u << 16);   // A and B MN-major
+}
+
+struct WgradArgs {
+    int P, Wp, Cin, Cout;
+    int rows_per_split;   // multiple of kWgRows
+    int tiles_m, tiles_n, splits;
+    float* partial;       // [splits][9][Cout][Cin]
+    unsigned debug;       // DMST_WG_DEBUG: bit 0 K-major flags, bit 1 swap LBO/SBO, bit 2 dump (development aid)
+    float* dump;
+};
+
+// grid: tiles_m * tiles_n * splits CTAs of 192 threads (warp 0 TMA, warp 1 MMA, warps 2-5 epilogue)
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x, WgradArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[kWgStages], empty_bar[kWgStages], acc_bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x % a.splits, t2 = blockIdx.x / a.splits;
+    const int n0 = (t2 % a.tiles_n) * kWgBN, m0 = (t2 / a.tiles_n) * kWgBM;
+    const int r0 = split * a.rows_per_split;
+    const int r1 = min(r0 + a.rows_per_split, a.P);
+    const int iters = r1 > r0 ? (r1 - r0 + kWgRows - 1) / kWgRows : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWgStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // 9 taps x 32 FP32 accumulator columns -> 512 (power of two)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const uint32_t s = it % kWgStages, round = it / kWgStages;
+                mbar_wait(&empty_bar[s], (round & 1) ^ 1);
+                unsigned char* sa = tiles + (size_t)s * kWgStageBytes;
+                // (slabs beyond Cout, when Cout < 128, are not loaded: their accumulator rows are never stored)
+                const int slabs = min(kWgBM / 32, (a.Cout - m0) / 32);
+                mbar_expect_tx(&full_bar[s], (slabs + 9) * kWgSlabBytes);
+                const int p = r0 + it * kWgRows;
+                for (int j = 0; j < slabs; ++j)
+                    tma_load_2d(sa + j * kWgSlabBytes, &map_dz, &full_bar[s], m0 + j * 32, p);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap)
+                    tma_load_2d(sa + kWgABytes + tap * kWgSlabBytes, &map_x, &full_bar[s], n0,
+                                p + (tap / 3 - 1) * a.Wp + (tap % 3 - 1));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (a.debug & 1u) ? umma_idesc_tf32(kWgBM, kWgBN) : umma_idesc_tf32_mn(kWgBM, kWgBN);
+            for (int it = 0; it < iters; ++it) {
+                const uint32_t s = it % kWgStages, round = it / kWgStages;
+                mbar_wait(&full_bar[s], round & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(tiles + (size_t)s * kWgStageBytes);
+                uint64_t adesc = umma_smem_desc_mn(sa, kWgSlabBytes);
+                if (a.debug & 2u) adesc = (adesc & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(kWgSlabBytes >> 4) << 32);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    uint64_t bdesc = umma_smem_desc_mn(sa + kWgABytes + tap * kWgSlabBytes, kWgSlabBytes);
+                    if (a.debug & 2u) bdesc = (bdesc & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(kWgSlabBytes >> 4) << 32);
+#pragma unroll
+                    for (int k = 0; k < kWgRows / 8; ++k)   // UMMA K = 8 pixel rows = one 1024-byte atom
+                        umma_tf32(tmem_base + tap * kWgBN, adesc + (uint64_t)((k * 1024) >> 4), bdesc + (uint64_t)((k * 1024) >> 4),
+                                  idesc, (it | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&acc_bar);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int co = m0 + quarter * 32 + lane;
+        if (iters > 0) {
+            mbar_wait(&acc_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+            uint32_t r[32];
+            if (iters > 0) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tap * kWgBN);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            if ((a.debug & 4u) && blockIdx.x == 0 && tap == 4) {
+                for (int j = 0; j < 32; ++j) a.dump[2048 + (quarter * 32 + lane) * 32 + j] = __int_as_float((int)r[j]);
+                const float* sm = reinterpret_cast<const float*>(tiles);
+                for (int j = (quarter * 32 + lane); j < 1024; j += 128) {
+                    a.dump[j] = sm[j];                                                  // stage 0, dz slab 0
+                    a.dump[1024 + j] = sm[(kWgABytes + 4 * kWgSlabBytes) / 4 + j];      // stage 0, x tap 4
+                }
+            }
+            if (co < a.Cout) {
+                float* o = a.partial + (((size_t)split * 9 + tap) * a.Cout + co) * a.Cin + n0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(o + j) = make_float4(__int_as_float((int)r[j]), __int_as_float((int)r[j + 1]),
+                                                                    __int_as_float((int)r[j + 2]), __int_as_float((int)r[j + 3]));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+// g9[i] = sum over splits of partial[split][i], fixed order; n = 9 * Cout * Cin (multiple of 4)
+__global__ void wgrad_reduce_kernel(const float* partial, int splits, long long n, float* g9) {
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < splits; ++k) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (size_t)k * n + i));
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        *reinterpret_cast<float4*>(g9 + i) = s;
+    }
+}
+
+struct WgradPlan { int tiles_m, tiles_n, splits, rows_per_split; };
+inline bool wgrad_supported(int Cin, int Cout) { return Cin % kWgBN == 0 && Cout % 32 == 0; }
+inline WgradPlan wgrad_plan(long long P, int Cin, int Cout) {
+    WgradPlan w;
+    w.tiles_m = (Cout + kWgBM - 1) / kWgBM;
+    w.tiles_n = Cin / kWgBN;
+    const int tiles = w.tiles_m * w.tiles_n;
+    long long s = (2LL * 148 + tiles - 1) / tiles;                      // about two CTAs per SM in total
+    const long long max_s = (P + 8 * kWgRows - 1) / (8 * kWgRows);      // at least 8 stages per CTA
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    long long rows = (P + s - 1) / s;
+    rows = (rows + kWgRows - 1) / kWgRows * kWgRows;
+    w.rows_per_split = (int)rows;
+    w.splits = (int)((P + rows - 1) / rows);
+    return w;
+}
+inline size_t conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
+    if (!wgrad_supported(Cin, Cout)) return 0;
+    const WgradPlan w = wgrad_plan((long long)B * (H + 2) * (W + 2), Cin, Cout);
+    return (size_t)w.splits * 9 * Cout * Cin * sizeof(float);
+}
+// x_padded (B, H+2, W+2, Cin), dz_padded (B, H+2, W+2, Cout) with a zero border -> g9 [9][Cout][Cin]
+inline int conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* g9, int B, int H, int W, int Cin, int Cout,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!x_padded || !dz_padded || !g9 || !workspace || B <= 0 || H <= 0 || W <= 0) return DMST_EINVAL;
+    if (!wgrad_supported(Cin, Cout)) return DMST_EINVAL;
+    const long long P = (long long)B * (H + 2) * (W + 2);
+    if (P > 0x7fffffffLL) return DMST_EINVAL;
+    if (workspace_bytes < conv3x3_wgrad_workspace_bytes(B, H, W, Cin, Cout)) return DMST_EINVAL;
+    const WgradPlan w = wgrad_plan(P, Cin, Cout);
+    // (a runtime call first: in a thread that has made none yet - an autograd worker - the driver call below would
+    // find no current context)
+    const size_t smem = (size_t)kWgStages * kWgStageBytes + 1024;
+    int e = (int)cudaFuncSetAttribute(conv3x3_wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    CUtensorMap mdz, mx;
+    e = make_map_2d(&mdz, dz_padded, (uint64_t)P, (uint64_t)Cout, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (e) return e;
+    e = make_map_2d(&mx, x_padded, (uint64_t)P, (uint64_t)Cin, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (e) return e;
+    WgradArgs a{(int)P, W + 2, Cin, Cout, w.rows_per_split, w.tiles_m, w.tiles_n, w.splits, reinterpret_cast<float*>(workspace), 0u, nullptr};
+    if (const char* dbg = getenv("DMST_WG_DEBUG")) {
+        a.debug = (unsigned)atoi(dbg);
+        a.dump = g9;   // the caller passes a g9 buffer of at least 2048 + 4096 floats when dumping; the reduction is skipped
+    }
+    conv3x3_wgrad_tf32_kernel<<<w.tiles_m * w.tiles_n * w.splits, kConvThreads, smem, stream>>>(mdz, mx, a);
+    const long long n = 9LL * Cout * Cin;
+    if (!(a.debug & 4u)) wgrad_reduce_kernel<<<grid_for(n / 4), 256, 0, stream>>>(a.partial, w.splits, n, g9);
+    return (int)cudaGetLastError();
 }
 
 // k-splits for a layer: only when one wave of tiles would leave SMs idle (the small deep layers)
