@@ -150,7 +150,7 @@ class _Conv3x3Function(torch.autograd.Function):
                 _lib.check(lib.dmst_conv3x3_wgrad(_ptr(x_pad), _ptr(gz), _ptr(g9), B, Hp - 2, Wp - 2, Cin, Cout, _ptr(ws), nbytes,
                                                   _stream(gz.device)), "dmst_conv3x3_wgrad")
                 return gx, g9.permute(1, 2, 0).reshape(Cout, Cin, 3, 3), None
-            # the 1-channel first layer (and channel counts that are not multiples of 32): library GEMMs.
+            # channel counts the kernels do not cover (Cin neither 1 nor a multiple of 32): library GEMMs.
             # dW[tap] = dz^T @ x shifted by the tap (a constant row offset in the flattened layout; dz is zero on the
             # border, so rows that would cross an image edge contribute nothing); K = all pixels is split into S chunks
             # run as one batched GEMM per tap.  TF32 follows torch.backends.cudnn.allow_tf32 (the reference's switch).

@@ -933,8 +933,60 @@ __global__ void wgrad_reduce_kernel(const float* partial, int splits, long long 
     }
 }
 
+// Weight gradient of the 1-channel first layer: dW[tap][co] = sum_p dz[p][co] * x[p + off(tap)], one streaming pass
+// over dz for all nine taps (the layer is memory bound: 4 * Cout bytes per pixel).  Same thread layout and two-stage
+// fixed-order reduction as the BatchNorm statistics; partial[chunk][9][C].
+__global__ void __launch_bounds__(256) wgrad_cin1_partial_kernel(const float* dz, const float* x, int P, int Wp, int C, float* partial) {
+    __shared__ float4 sh[256];
+    const StatLayout L(C);
+    const int chunk = blockIdx.x;
+    const int rows = stat_rows(P);
+    const int r0 = chunk * rows, r1 = min(r0 + rows, P);
+    for (int g = 0; g * L.cols < (C >> 2); ++g) {
+        const int c = (g * L.cols + L.cq) << 2;
+        float4 acc[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < C && L.rl < L.lanes)
+            for (int r = r0 + L.rl; r < r1; r += L.lanes) {
+                const float4 d = __ldg(reinterpret_cast<const float4*>(dz + (size_t)r * C + c));
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int q = r + (t / 3 - 1) * Wp + (t % 3 - 1);
+                    const float xv = (q >= 0 && q < P) ? __ldg(x + q) : 0.0f;
+                    acc[t].x = fmaf(d.x, xv, acc[t].x); acc[t].y = fmaf(d.y, xv, acc[t].y);
+                    acc[t].z = fmaf(d.z, xv, acc[t].z); acc[t].w = fmaf(d.w, xv, acc[t].w);
+                }
+            }
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) {
+            sh[threadIdx.x] = acc[t];
+            __syncthreads();
+            if (L.rl == 0 && c < C) {
+                float4 a = acc[t];
+                for (int l = 1; l < L.lanes; ++l) {
+                    const float4 u = sh[l * L.cols + L.cq];
+                    a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+                }
+                *reinterpret_cast<float4*>(partial + ((size_t)chunk * 9 + t) * C + c) = a;
+            }
+            __syncthreads();
+        }
+    }
+}
+// g9[tap][co] (Cin = 1): one warp per (tap, co), lanes stride over the chunks in float64
+__global__ void wgrad_cin1_final_kernel(const float* partial, int chunks, int C, float* g9) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // tap * C + co
+    if (i >= 9 * C) return;
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int k = lane; k < chunks; k += 32) s += partial[(size_t)k * 9 * C + i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) g9[i] = (float)s;
+}
+
 struct WgradPlan { int tiles_m, tiles_n, splits, rows_per_split; };
-inline bool wgrad_supported(int Cin, int Cout) { return Cin % kWgBN == 0 && Cout % 32 == 0; }
+inline bool wgrad_supported(int Cin, int Cout) { return (Cin % kWgBN == 0 && Cout % 32 == 0) || (Cin == 1 && Cout % 4 == 0); }
 inline WgradPlan wgrad_plan(long long P, int Cin, int Cout) {
     WgradPlan w;
     w.tiles_m = (Cout + kWgBM - 1) / kWgBM;
@@ -952,6 +1004,10 @@ inline WgradPlan wgrad_plan(long long P, int Cin, int Cout) {
 }
 inline size_t conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout) {
     if (!wgrad_supported(Cin, Cout)) return 0;
+    if (Cin == 1) {
+        const long long P = (long long)B * (H + 2) * (W + 2);
+        return (size_t)((P + stat_rows(P) - 1) / stat_rows(P)) * 9 * Cout * sizeof(float);
+    }
     const WgradPlan w = wgrad_plan((long long)B * (H + 2) * (W + 2), Cin, Cout);
     return (size_t)w.splits * 9 * Cout * Cin * sizeof(float);
 }
@@ -963,6 +1019,13 @@ inline int conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* g
     const long long P = (long long)B * (H + 2) * (W + 2);
     if (P > 0x7fffffffLL) return DMST_EINVAL;
     if (workspace_bytes < conv3x3_wgrad_workspace_bytes(B, H, W, Cin, Cout)) return DMST_EINVAL;
+    if (Cin == 1) {
+        const int chunks = (int)((P + stat_rows(P) - 1) / stat_rows(P));
+        float* partial = reinterpret_cast<float*>(workspace);
+        wgrad_cin1_partial_kernel<<<chunks, 256, 0, stream>>>(dz_padded, x_padded, (int)P, W + 2, Cout, partial);
+        wgrad_cin1_final_kernel<<<(9 * Cout + 7) / 8, 256, 0, stream>>>(partial, chunks, Cout, g9);
+        return (int)cudaGetLastError();
+    }
     const WgradPlan w = wgrad_plan(P, Cin, Cout);
     // (a runtime call first: in a thread that has made none yet - an autograd worker - the driver call below would
     // find no current context)

@@ -212,3 +212,34 @@ def test_spectrogram_frontend_matches_torch_stft_composition():
     assert xg.grad is not None and torch.isfinite(xg.grad).all()
     with pytest.raises(RuntimeError, match="Padding size"):
         enc._frontend(torch.zeros(1, 1, 1000).cuda())
+
+
+@pytest.mark.parametrize("shape", [(1, 6, 5, 32, 32), (2, 17, 9, 64, 64), (1, 33, 20, 32, 128), (2, 8, 8, 128, 256),
+                                   (1, 6, 5, 1, 64), (2, 33, 17, 1, 64), (3, 40, 24, 96, 160)])
+def test_wgrad_tensor_core_matches_float64(shape):
+    """dmst_conv3x3_wgrad (tcgen05, MN-major TF32 operands; streaming kernel for the 1-channel first layer) against
+    torch's float64 weight gradient of the same convolution.  TF32 products with FP32 accumulation: 3e-3 of the
+    largest entry (the tolerance of the forward convolution); the first layer runs in FP32: 1e-5.  Also: the result
+    is deterministic and the library-GEMM arm used for uncovered channel counts agrees."""
+    from diffmst_b200 import conv
+    B, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin)
+    x = torch.randn(B, Cin, H, W, generator=g).cuda()
+    gy = torch.randn(B, Cout, H, W, generator=g).cuda()
+    x_pad = F.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()
+    gz = F.pad(gy.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()
+
+    def wgrad(tc):
+        conv._TC_WGRAD = tc
+        try:
+            w = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
+            conv._Conv3x3Function.apply(x_pad.clone(), w, True).backward(gz)
+            return w.grad
+        finally:
+            conv._TC_WGRAD = True
+
+    want = torch.nn.grad.conv2d_weight(x.double(), (Cout, Cin, 3, 3), gy.double(), padding=1)
+    got = wgrad(True)
+    assert relmax(got, want) <= (1e-5 if Cin == 1 else TOL), relmax(got, want)
+    assert torch.equal(got, wgrad(True))
+    assert relmax(wgrad(False), want) <= TOL

@@ -20,7 +20,7 @@ def wgrad_ours(x_pad, gz, Cin, Cout, tc):
     return w.grad
 
 
-for (B, H, W, Cin, Cout) in ((1, 6, 5, 32, 32), (2, 17, 9, 64, 64), (1, 33, 20, 32, 128), (2, 8, 8, 128, 256), (4, 1025, 257, 64, 64),
+for (B, H, W, Cin, Cout) in ((1, 6, 5, 1, 64), (2, 33, 17, 1, 64), (4, 1025, 257, 1, 64), (1, 6, 5, 32, 32), (2, 17, 9, 64, 64), (1, 33, 20, 32, 128), (2, 8, 8, 128, 256), (4, 1025, 257, 64, 64),
                               (4, 512, 128, 128, 128), (4, 8, 8, 1024, 1024)):
     x = torch.randn(B, Cin, H, W, device=dev)
     g = torch.randn(B, Cout, H, W, device=dev)
