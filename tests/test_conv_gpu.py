@@ -5,6 +5,7 @@ output's max magnitude, the same class as cuDNN's default TF32 convolutions."""
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle.panns import OracleCnn14, OracleConvBlock
 
