@@ -10,9 +10,10 @@ inside ``Cnn14``).
 
 Training: with autograd enabled the 3x3 convolution is a ``torch.autograd.Function`` whose forward
 and input gradient (dgrad = the same shifted-GEMM kernel run on the output gradient with the taps
-flipped and the channel roles swapped) run on tcgen05; the weight gradient is nine plain GEMMs
-``dz^T @ x_shifted`` over the flattened zero-bordered NHWC tensors (library GEMM, cuBLAS through
-torch.matmul - a hand-written split-K tcgen05 wgrad is the next step); BatchNorm + ReLU and the
+flipped and the channel roles swapped) run on tcgen05, and so does the weight gradient
+(``dmst_conv3x3_wgrad``: per tap ``dz^T @ x_shifted`` over the flattened zero-bordered NHWC tensors
+with MN-major TF32 operands, split over pixel chunks; split-K batched library GEMMs remain only
+for channel counts that kernel does not cover, none of them in Cnn14); BatchNorm + ReLU and the
 average pooling of the differentiable path are CUDA autograd Functions too (batch statistics,
 normalisation, their backward and the pooling backward in csrc/conv_tc.cuh).
 """

@@ -768,16 +768,20 @@ __global__ void conv_splitk_reduce_kernel(const float* partial, int ksplit, floa
 // (128-byte rows, 32-byte-chunk swizzle) is one "slab", K = 8 pixel rows are 1024 bytes, and the tap shift is
 // a shift of the box's ROW coordinate, which TMA does not constrain (with pixels as the innermost, K-major,
 // coordinate it would have to be a multiple of 16 bytes - why this kernel does not transpose anything).
-// One CTA = (128 output channels) x (32 input channels) x (a contiguous chunk of the pixels): the dz tile of a
-// stage feeds the nine taps' accumulators (9 x 32 TMEM columns); raw sums go to partial[split][9][Cout][Cin],
-// wgrad_reduce_kernel adds the splits in a fixed order.
+// One CTA = (128 output channels) x (64 or 32 input channels) x (a contiguous chunk of the pixels) x (a group of
+// taps): the dz tile of a stage feeds the accumulators of all the CTA's taps (5 or 4 x 64, or 9 x 32 TMEM columns);
+// raw sums go to partial[split][9][Cout][Cin], wgrad_reduce_kernel adds the splits in a fixed order.
 // ---------------------------------------------------------------------------------------------
 constexpr int kWgRows = 32;                 // pixel rows (K) per pipeline stage
-constexpr int kWgBM = 128, kWgBN = 32;      // output-channel x input-channel tile
-constexpr int kWgStages = 4;
+constexpr int kWgBM = 128;                  // output channels per tile (UMMA M)
 constexpr uint32_t kWgSlabBytes = kWgRows * 128;                           // 32 rows x 32 channels
 constexpr uint32_t kWgABytes = (kWgBM / 32) * kWgSlabBytes;                // 4 slabs of dz
-constexpr uint32_t kWgStageBytes = kWgABytes + 9 * kWgSlabBytes;           // + one slab of x per tap
+// BN input channels per tile: 64 where Cin allows it (each dz tile read from shared memory then feeds twice the
+// columns; the nine taps are split over two CTAs, 5 + 4, because 9 x 64 accumulator columns exceed TMEM), else 32.
+__host__ __device__ constexpr int wg_groups(int BN) { return BN == 64 ? 2 : 1; }
+__host__ __device__ constexpr int wg_max_taps(int BN) { return BN == 64 ? 5 : 9; }
+__host__ __device__ constexpr uint32_t wg_stage_bytes(int BN) { return kWgABytes + wg_max_taps(BN) * (BN / 32) * kWgSlabBytes; }
+__host__ __device__ constexpr int wg_stages(int BN) { return BN == 64 ? 3 : 4; }
 
 // MN-major TF32 operand.  32-bit MN-major operands exist in one shared-memory layout only: 128-byte rows whose
 // 32-byte chunks are XOR-ed with the row index mod 4 (UMMA layout type "128B swizzle, 32-byte base" = TMA swizzle
@@ -800,30 +804,34 @@ struct WgradArgs {
     int rows_per_split;   // multiple of kWgRows
     int tiles_m, tiles_n, splits;
     float* partial;       // [splits][9][Cout][Cin]
-    unsigned debug;       // DMST_WG_DEBUG: bit 0 K-major flags, bit 1 swap LBO/SBO, bit 2 dump (development aid)
-    float* dump;
 };
 
-// grid: tiles_m * tiles_n * splits CTAs of 192 threads (warp 0 TMA, warp 1 MMA, warps 2-5 epilogue)
+// grid: tiles_m * tiles_n * splits * wg_groups(BN) CTAs of 192 threads (warp 0 TMA, warp 1 MMA, warps 2-5 epilogue)
+template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x, WgradArgs a) {
+    constexpr int kStages = wg_stages(BN), kGroups = wg_groups(BN);
+    constexpr uint32_t kStageBytes = wg_stage_bytes(BN);
+    constexpr uint32_t kBBytes = (BN / 32) * kWgSlabBytes;   // one tap's x tile: BN / 32 slabs
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
-    __shared__ __align__(8) uint64_t full_bar[kWgStages], empty_bar[kWgStages], acc_bar;
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_bar;
     __shared__ uint32_t tmem_base_smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int split = blockIdx.x % a.splits, t2 = blockIdx.x / a.splits;
-    const int n0 = (t2 % a.tiles_n) * kWgBN, m0 = (t2 / a.tiles_n) * kWgBM;
+    const int group = blockIdx.x % kGroups, b1 = blockIdx.x / kGroups;
+    const int split = b1 % a.splits, t2 = b1 / a.splits;
+    const int n0 = (t2 % a.tiles_n) * BN, m0 = (t2 / a.tiles_n) * kWgBM;
+    const int tap0 = group == 0 ? 0 : wg_max_taps(BN), ntaps = kGroups == 1 ? 9 : (group == 0 ? 5 : 4);
     const int r0 = split * a.rows_per_split;
     const int r1 = min(r0 + a.rows_per_split, a.P);
     const int iters = r1 > r0 ? (r1 - r0 + kWgRows - 1) / kWgRows : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kWgStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // 9 taps x 32 FP32 accumulator columns -> 512 (power of two)
+    if (warp == 1) {  // up to 9 x 32 or 5 x 64 FP32 accumulator columns -> 512 (power of two)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -834,39 +842,39 @@ conv3x3_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dz, const __gr
 
     if (warp == 0) {
         if (lane == 0) {
+            // (slabs beyond Cout, when Cout < 128, are not loaded: their accumulator rows are never stored)
+            const int slabs = min(kWgBM / 32, (a.Cout - m0) / 32);
             for (int it = 0; it < iters; ++it) {
-                const uint32_t s = it % kWgStages, round = it / kWgStages;
+                const uint32_t s = it % kStages, round = it / kStages;
                 mbar_wait(&empty_bar[s], (round & 1) ^ 1);
-                unsigned char* sa = tiles + (size_t)s * kWgStageBytes;
-                // (slabs beyond Cout, when Cout < 128, are not loaded: their accumulator rows are never stored)
-                const int slabs = min(kWgBM / 32, (a.Cout - m0) / 32);
-                mbar_expect_tx(&full_bar[s], (slabs + 9) * kWgSlabBytes);
+                unsigned char* sa = tiles + (size_t)s * kStageBytes;
+                mbar_expect_tx(&full_bar[s], slabs * kWgSlabBytes + ntaps * kBBytes);
                 const int p = r0 + it * kWgRows;
                 for (int j = 0; j < slabs; ++j)
                     tma_load_2d(sa + j * kWgSlabBytes, &map_dz, &full_bar[s], m0 + j * 32, p);
+                for (int t = 0; t < ntaps; ++t) {
+                    const int tap = tap0 + t;
+                    const int row = p + (tap / 3 - 1) * a.Wp + (tap % 3 - 1);
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap)
-                    tma_load_2d(sa + kWgABytes + tap * kWgSlabBytes, &map_x, &full_bar[s], n0,
-                                p + (tap / 3 - 1) * a.Wp + (tap % 3 - 1));
+                    for (int j = 0; j < BN / 32; ++j)
+                        tma_load_2d(sa + kWgABytes + t * kBBytes + j * kWgSlabBytes, &map_x, &full_bar[s], n0 + j * 32, row);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = (a.debug & 1u) ? umma_idesc_tf32(kWgBM, kWgBN) : umma_idesc_tf32_mn(kWgBM, kWgBN);
+            constexpr uint32_t idesc = umma_idesc_tf32_mn(kWgBM, BN);
             for (int it = 0; it < iters; ++it) {
-                const uint32_t s = it % kWgStages, round = it / kWgStages;
+                const uint32_t s = it % kStages, round = it / kStages;
                 mbar_wait(&full_bar[s], round & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(tiles + (size_t)s * kWgStageBytes);
-                uint64_t adesc = umma_smem_desc_mn(sa, kWgSlabBytes);
-                if (a.debug & 2u) adesc = (adesc & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(kWgSlabBytes >> 4) << 32);
+                const uint32_t sa = smem_u32(tiles + (size_t)s * kStageBytes);
+                const uint64_t adesc = umma_smem_desc_mn(sa, kWgSlabBytes);
+                for (int t = 0; t < ntaps; ++t) {
+                    const uint64_t bdesc = umma_smem_desc_mn(sa + kWgABytes + t * kBBytes, kWgSlabBytes);
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    uint64_t bdesc = umma_smem_desc_mn(sa + kWgABytes + tap * kWgSlabBytes, kWgSlabBytes);
-                    if (a.debug & 2u) bdesc = (bdesc & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(kWgSlabBytes >> 4) << 32);
-#pragma unroll
-                    for (int k = 0; k < kWgRows / 8; ++k)   // UMMA K = 8 pixel rows = one 1024-byte atom
-                        umma_tf32(tmem_base + tap * kWgBN, adesc + (uint64_t)((k * 1024) >> 4), bdesc + (uint64_t)((k * 1024) >> 4),
+                    for (int k = 0; k < kWgRows / 8; ++k)   // UMMA K = 8 pixel rows = 1024 bytes of every slab
+                        umma_tf32(tmem_base + t * BN, adesc + (uint64_t)((k * 1024) >> 4), bdesc + (uint64_t)((k * 1024) >> 4),
                                   idesc, (it | k) != 0);
                 }
                 umma_commit(&empty_bar[s]);
@@ -881,10 +889,11 @@ conv3x3_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dz, const __gr
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int t = 0; t < ntaps * (BN / 32); ++t) {
+            const int tl = t / (BN / 32), c0 = (t % (BN / 32)) * 32;
             uint32_t r[32];
             if (iters > 0) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tap * kWgBN);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tl * BN + c0);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -899,16 +908,8 @@ conv3x3_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dz, const __gr
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
-            if ((a.debug & 4u) && blockIdx.x == 0 && tap == 4) {
-                for (int j = 0; j < 32; ++j) a.dump[2048 + (quarter * 32 + lane) * 32 + j] = __int_as_float((int)r[j]);
-                const float* sm = reinterpret_cast<const float*>(tiles);
-                for (int j = (quarter * 32 + lane); j < 1024; j += 128) {
-                    a.dump[j] = sm[j];                                                  // stage 0, dz slab 0
-                    a.dump[1024 + j] = sm[(kWgABytes + 4 * kWgSlabBytes) / 4 + j];      // stage 0, x tap 4
-                }
-            }
             if (co < a.Cout) {
-                float* o = a.partial + (((size_t)split * 9 + tap) * a.Cout + co) * a.Cin + n0;
+                float* o = a.partial + (((size_t)split * 9 + tap0 + tl) * a.Cout + co) * a.Cin + n0 + c0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(o + j) = make_float4(__int_as_float((int)r[j]), __int_as_float((int)r[j + 1]),
@@ -985,14 +986,15 @@ __global__ void wgrad_cin1_final_kernel(const float* partial, int chunks, int C,
     if (lane == 0) g9[i] = (float)s;
 }
 
-struct WgradPlan { int tiles_m, tiles_n, splits, rows_per_split; };
-inline bool wgrad_supported(int Cin, int Cout) { return (Cin % kWgBN == 0 && Cout % 32 == 0) || (Cin == 1 && Cout % 4 == 0); }
+struct WgradPlan { int bn, tiles_m, tiles_n, splits, rows_per_split; };
+inline bool wgrad_supported(int Cin, int Cout) { return (Cin % 32 == 0 && Cout % 32 == 0) || (Cin == 1 && Cout % 4 == 0); }
 inline WgradPlan wgrad_plan(long long P, int Cin, int Cout) {
     WgradPlan w;
+    w.bn = (Cin % 64 == 0) ? 64 : 32;
     w.tiles_m = (Cout + kWgBM - 1) / kWgBM;
-    w.tiles_n = Cin / kWgBN;
-    const int tiles = w.tiles_m * w.tiles_n;
-    long long s = (2LL * 148 + tiles - 1) / tiles;                      // about two CTAs per SM in total
+    w.tiles_n = Cin / w.bn;
+    const int ctas_per_split = w.tiles_m * w.tiles_n * wg_groups(w.bn);
+    long long s = (2LL * 148 + ctas_per_split - 1) / ctas_per_split;    // about two CTAs per SM in total
     const long long max_s = (P + 8 * kWgRows - 1) / (8 * kWgRows);      // at least 8 stages per CTA
     if (s > max_s) s = max_s;
     if (s < 1) s = 1;
@@ -1029,22 +1031,22 @@ inline int conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* g
     const WgradPlan w = wgrad_plan(P, Cin, Cout);
     // (a runtime call first: in a thread that has made none yet - an autograd worker - the driver call below would
     // find no current context)
-    const size_t smem = (size_t)kWgStages * kWgStageBytes + 1024;
-    int e = (int)cudaFuncSetAttribute(conv3x3_wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)wg_stages(w.bn) * wg_stage_bytes(w.bn) + 1024;
+    int e = w.bn == 64
+                ? (int)cudaFuncSetAttribute(conv3x3_wgrad_tf32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                : (int)cudaFuncSetAttribute(conv3x3_wgrad_tf32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
     CUtensorMap mdz, mx;
     e = make_map_2d(&mdz, dz_padded, (uint64_t)P, (uint64_t)Cout, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (e) return e;
     e = make_map_2d(&mx, x_padded, (uint64_t)P, (uint64_t)Cin, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (e) return e;
-    WgradArgs a{(int)P, W + 2, Cin, Cout, w.rows_per_split, w.tiles_m, w.tiles_n, w.splits, reinterpret_cast<float*>(workspace), 0u, nullptr};
-    if (const char* dbg = getenv("DMST_WG_DEBUG")) {
-        a.debug = (unsigned)atoi(dbg);
-        a.dump = g9;   // the caller passes a g9 buffer of at least 2048 + 4096 floats when dumping; the reduction is skipped
-    }
-    conv3x3_wgrad_tf32_kernel<<<w.tiles_m * w.tiles_n * w.splits, kConvThreads, smem, stream>>>(mdz, mx, a);
+    WgradArgs a{(int)P, W + 2, Cin, Cout, w.rows_per_split, w.tiles_m, w.tiles_n, w.splits, reinterpret_cast<float*>(workspace)};
+    const int grid = w.tiles_m * w.tiles_n * w.splits * wg_groups(w.bn);
+    if (w.bn == 64) conv3x3_wgrad_tf32_kernel<64><<<grid, kConvThreads, smem, stream>>>(mdz, mx, a);
+    else conv3x3_wgrad_tf32_kernel<32><<<grid, kConvThreads, smem, stream>>>(mdz, mx, a);
     const long long n = 9LL * Cout * Cin;
-    if (!(a.debug & 4u)) wgrad_reduce_kernel<<<grid_for(n / 4), 256, 0, stream>>>(a.partial, w.splits, n, g9);
+    wgrad_reduce_kernel<<<grid_for(n / 4), 256, 0, stream>>>(a.partial, w.splits, n, g9);
     return (int)cudaGetLastError();
 }
 
