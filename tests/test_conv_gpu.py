@@ -14,7 +14,8 @@ TOL = 3e-3
 
 
 def relmax(a, b):
-    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
 def _randomise_bn(block, g):
