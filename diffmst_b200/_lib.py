@@ -99,6 +99,10 @@ def lib():
     l.dmst_conv_bn_relu_backward.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp, sz, vp]
     l.dmst_conv_avgpool_backward.restype = i
     l.dmst_conv_avgpool_backward.argtypes = [vp, vp, i, i, i, i, i, i, i, vp]
+    l.dmst_conv_bn_relu_avgpool.restype = i
+    l.dmst_conv_bn_relu_avgpool.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    l.dmst_conv_bn_relu_avgpool_backward.restype = i
+    l.dmst_conv_bn_relu_avgpool_backward.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp, sz, vp]
     l.dmst_spectrogram_workspace_bytes.restype = sz
     l.dmst_spectrogram_workspace_bytes.argtypes = [i, i, i, i, i]
     l.dmst_spectrogram_frontend.restype = i

@@ -255,6 +255,51 @@ class _BnReluFunction(torch.autograd.Function):
                 None, None, None, None)
 
 
+class _BnReluPoolFunction(torch.autograd.Function):
+    """avg_pool2d(relu(BatchNorm(z))) as one unit (mst/panns.py:80-85): the BatchNorm+ReLU output and its gradient are
+    never materialised; backward gathers the pooled gradient on the fly.  Pool sizes are powers of two."""
+
+    @staticmethod
+    def forward(ctx, z_pad, gamma, beta, mean, var, eps, batch_stats, kh, kw, out_padded_nhwc):
+        lib = _lib.lib()
+        B, Hp, Wp, C = z_pad.shape
+        H, W = Hp - 2, Wp - 2
+        z_pad = z_pad.contiguous()
+        rstd = torch.rsqrt(var.detach().float() + eps)
+        scale = (gamma.detach().float() * rstd).contiguous()
+        shift = (beta.detach().float() - mean.detach().float() * scale).contiguous()
+        Ho, Wo = H // kh, W // kw
+        if out_padded_nhwc:
+            y = torch.zeros(B, Ho + 2, Wo + 2, C, dtype=torch.float32, device=z_pad.device)
+        else:
+            y = torch.empty(B, C, Ho, Wo, dtype=torch.float32, device=z_pad.device)
+        _lib.check(lib.dmst_conv_bn_relu_avgpool(_ptr(z_pad), _ptr(scale), _ptr(shift), _ptr(y), B, C, H, W, kh, kw,
+                                                 1 if out_padded_nhwc else 0, _stream(z_pad.device)), "dmst_conv_bn_relu_avgpool")
+        ctx.save_for_backward(z_pad, scale, shift, mean.detach().float().contiguous(), rstd.contiguous())
+        ctx.cfg = (bool(batch_stats), kh, kw, bool(out_padded_nhwc))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.lib()
+        z_pad, scale, shift, mean, rstd = ctx.saved_tensors
+        batch_stats, kh, kw, padded = ctx.cfg
+        B, Hp, Wp, C = z_pad.shape
+        dev = z_pad.device
+        gy = gy.contiguous()
+        dz = torch.empty_like(z_pad)
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        nbytes = lib.dmst_conv_stats_workspace_bytes(B, Hp - 2, Wp - 2, C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.dmst_conv_bn_relu_avgpool_backward(
+            _ptr(z_pad), _ptr(gy), kh, kw, 1 if padded else 0, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
+            1 if batch_stats else 0, B, Hp - 2, Wp - 2, C, _ptr(dz), _ptr(dgamma), _ptr(dbeta), _ptr(ws), nbytes, _stream(dev)),
+            "dmst_conv_bn_relu_avgpool_backward")
+        return (dz, dgamma if ctx.needs_input_grad[1] else None, dbeta if ctx.needs_input_grad[2] else None,
+                None, None, None, None, None, None, None)
+
+
 class _AvgPoolFunction(torch.autograd.Function):
     """F.avg_pool2d(x, (kh, kw)) of a zero-bordered NHWC tensor -> NCHW or zero-bordered NHWC (mst/panns.py:81-85)."""
 
@@ -274,9 +319,10 @@ class _AvgPoolFunction(torch.autograd.Function):
         return gx, None, None, None
 
 
-def _conv_bn_relu_autograd(x_pad, conv: nn.Conv2d, bn, training: bool):
+def _conv_bn_relu_autograd(x_pad, conv: nn.Conv2d, bn, training: bool, pool=None):
     """Differentiable twin of _conv_bn_relu: tensor-core conv Function, then BatchNorm + ReLU as one CUDA Function
-    (statistics, normalisation and their backward in csrc/conv_tc.cuh)."""
+    (statistics, normalisation and their backward in csrc/conv_tc.cuh).  pool = (kh, kw, out_padded_nhwc) fuses the
+    block's average pooling into that Function when the pool sizes are powers of two."""
     C = conv.weight.shape[0]
     cuda_bn = isinstance(bn, nn.BatchNorm2d) and C % 4 == 0 and _CUDA_BN_POOL
     z = _Conv3x3Function.apply(x_pad, conv.weight, cuda_bn)
@@ -290,13 +336,18 @@ def _conv_bn_relu_autograd(x_pad, conv: nn.Conv2d, bn, training: bool):
             mean, var = bn.running_mean, bn.running_var
         gamma = bn.weight if bn.weight is not None else torch.ones(C, device=z.device)
         beta = bn.bias if bn.bias is not None else torch.zeros(C, device=z.device)
+        if pool is not None:
+            kh, kw, out_padded = pool
+            if kh & (kh - 1) == 0 and kw & (kw - 1) == 0:
+                return _BnReluPoolFunction.apply(z, gamma, beta, mean, var, bn.eps, batch_stats, kh, kw, out_padded)
+            return _avgpool(_BnReluFunction.apply(z, gamma, beta, mean, var, bn.eps, batch_stats), kh, kw, out_padded)
         return _BnReluFunction.apply(z, gamma, beta, mean, var, bn.eps, batch_stats)
     # no BatchNorm (use_batchnorm=False) or an odd channel count: PyTorch ops on NHWC views
     zi = z[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)                     # NCHW view of the interior (channels-last memory)
     if isinstance(bn, nn.BatchNorm2d):
         zi = bn(zi)
-    y = F.relu(zi).permute(0, 2, 3, 1)
-    return F.pad(y, (0, 0, 1, 1, 1, 1))                              # back to zero-bordered NHWC
+    y = F.pad(F.relu(zi).permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1))    # back to zero-bordered NHWC
+    return y if pool is None else _avgpool(y, *pool)
 
 
 def _avgpool(x_pad, kh, kw, out_padded_nhwc):
@@ -361,10 +412,13 @@ class ConvBlock(nn.Module):
             init_bn(self.bn2)
 
     def forward_nhwc(self, x_pad, pool_size, out_padded_nhwc: bool):
-        unit = _conv_bn_relu_autograd if _needs_grad(x_pad, self) else _conv_bn_relu
-        x = unit(x_pad, self.conv1, self.bn1, self.training)
-        x = unit(x, self.conv2, self.bn2, self.training)
-        return _avgpool(x, int(pool_size[0]), int(pool_size[1]), out_padded_nhwc)
+        kh, kw = int(pool_size[0]), int(pool_size[1])
+        if _needs_grad(x_pad, self):
+            x = _conv_bn_relu_autograd(x_pad, self.conv1, self.bn1, self.training)
+            return _conv_bn_relu_autograd(x, self.conv2, self.bn2, self.training, pool=(kh, kw, out_padded_nhwc))
+        x = _conv_bn_relu(x_pad, self.conv1, self.bn1, self.training)
+        x = _conv_bn_relu(x, self.conv2, self.bn2, self.training)
+        return _avgpool(x, kh, kw, out_padded_nhwc)
 
     def forward(self, input: torch.Tensor, pool_size: List[int]):
         _require_cuda(input, "input")

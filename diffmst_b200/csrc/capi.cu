@@ -231,23 +231,50 @@ int dmst_conv_affine_relu_to(const float* z_padded, float* y_padded, const float
         z_padded, y_padded, P, H + 2, W + 2, C, scale, shift);
     return (int)cudaGetLastError();
 }
-int dmst_conv_bn_relu_backward(const float* z_padded, const float* dy_padded, const float* scale, const float* shift,
-                               const float* mean, const float* rstd, int batch_stats, int B, int H, int W, int C,
-                               float* dz_padded, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
-                               void* stream) {
-    if (!z_padded || !dy_padded || !scale || !shift || !mean || !rstd || !dz_padded || !dgamma || !dbeta || !workspace || (C & 3))
-        return DMST_EINVAL;
+static int bn_relu_backward_impl(const float* z_padded, const float* dy_padded, dmst::PoolGrad pg, const float* scale,
+                                 const float* shift, const float* mean, const float* rstd, int batch_stats, int B, int H, int W,
+                                 int C, float* dz_padded, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    if (!z_padded || !scale || !shift || !mean || !rstd || !dz_padded || !dgamma || !dbeta || !workspace || (C & 3)) return DMST_EINVAL;
     if (workspace_bytes < dmst_conv_stats_workspace_bytes(B, H, W, C)) return DMST_EINVAL;
     const int P = B * (H + 2) * (W + 2);
     const int chunks = (P + dmst::stat_rows(P) - 1) / dmst::stat_rows(P);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     float* partial = reinterpret_cast<float*>(workspace);
-    dmst::bn_relu_bwd_partial_kernel<<<chunks, 256, 0, s>>>(z_padded, dy_padded, P, H + 2, W + 2, C, scale, shift, mean, rstd, partial);
+    dmst::bn_relu_bwd_partial_kernel<<<chunks, 256, 0, s>>>(z_padded, dy_padded, pg, P, H + 2, W + 2, C, scale, shift, mean, rstd, partial);
     dmst::bn_relu_bwd_final_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, chunks, C, dgamma, dbeta);
     const float inv_count = batch_stats ? (float)(1.0 / ((double)B * H * W)) : 0.0f;
     dmst::bn_relu_bwd_apply_kernel<<<dmst::grid_for((long long)P * (C / 4)), 256, 0, s>>>(
-        z_padded, dy_padded, dz_padded, P, H + 2, W + 2, C, scale, shift, mean, rstd, dgamma, dbeta, inv_count);
+        z_padded, dy_padded, pg, dz_padded, P, H + 2, W + 2, C, scale, shift, mean, rstd, dgamma, dbeta, inv_count);
     return (int)cudaGetLastError();
+}
+int dmst_conv_bn_relu_backward(const float* z_padded, const float* dy_padded, const float* scale, const float* shift,
+                               const float* mean, const float* rstd, int batch_stats, int B, int H, int W, int C,
+                               float* dz_padded, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    if (!dy_padded) return DMST_EINVAL;
+    dmst::PoolGrad pg{nullptr, 0, 0, 0, 0, 0, 0.0f};
+    return bn_relu_backward_impl(z_padded, dy_padded, pg, scale, shift, mean, rstd, batch_stats, B, H, W, C, dz_padded, dgamma,
+                                 dbeta, workspace, workspace_bytes, stream);
+}
+static int log2_exact(int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; }
+int dmst_conv_bn_relu_avgpool(const float* z_padded, const float* scale, const float* shift, float* y, int B, int C, int H,
+                              int W, int kh, int kw, int out_padded_nhwc, void* stream) {
+    if (!z_padded || !scale || !shift || !y || kh <= 0 || kw <= 0 || H / kh <= 0 || W / kw <= 0 || (C & 3)) return DMST_EINVAL;
+    const long long total = (long long)B * (H / kh) * (W / kw) * (C / 4);
+    dmst::bn_relu_avgpool_kernel<<<dmst::grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        z_padded, scale, shift, y, B, C, H, W, kh, kw, out_padded_nhwc);
+    return (int)cudaGetLastError();
+}
+int dmst_conv_bn_relu_avgpool_backward(const float* z_padded, const float* dpooled, int kh, int kw, int dpooled_padded_nhwc,
+                                       const float* scale, const float* shift, const float* mean, const float* rstd,
+                                       int batch_stats, int B, int H, int W, int C, float* dz_padded, float* dgamma,
+                                       float* dbeta, void* workspace, size_t workspace_bytes, void* stream) {
+    const int sh = kh > 0 ? log2_exact(kh) : -1, sw = kw > 0 ? log2_exact(kw) : -1;
+    if (!dpooled || sh < 0 || sw < 0 || H / kh <= 0 || W / kw <= 0) return DMST_EINVAL;
+    dmst::PoolGrad pg{dpooled, sh, sw, H / kh, W / kw, dpooled_padded_nhwc, 1.0f / (float)(kh * kw)};
+    return bn_relu_backward_impl(z_padded, nullptr, pg, scale, shift, mean, rstd, batch_stats, B, H, W, C, dz_padded, dgamma,
+                                 dbeta, workspace, workspace_bytes, stream);
 }
 int dmst_conv_avgpool_backward(const float* dy, float* dx_padded, int B, int C, int H, int W, int kh, int kw,
                                int dy_padded_nhwc, void* stream) {
@@ -275,6 +302,9 @@ int dmst_conv_affine_relu_to(const float*, float*, const float*, const float*, i
 int dmst_conv_bn_relu_backward(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
                                int, int, float*, float*, float*, void*, size_t, void*) { return DMST_EINVAL; }
 int dmst_conv_avgpool_backward(const float*, float*, int, int, int, int, int, int, int, void*) { return DMST_EINVAL; }
+int dmst_conv_bn_relu_avgpool(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, void*) { return DMST_EINVAL; }
+int dmst_conv_bn_relu_avgpool_backward(const float*, const float*, int, int, int, const float*, const float*, const float*, const float*,
+                                       int, int, int, int, int, float*, float*, float*, void*, size_t, void*) { return DMST_EINVAL; }
 size_t dmst_spectrogram_workspace_bytes(int, int, int, int, int) { return 0; }
 int dmst_spectrogram_frontend(const float*, long long, const float*, int, int, int, int, int, float, float, float*, void*,
                               size_t, void*) { return DMST_EINVAL; }

@@ -606,7 +606,31 @@ __global__ void affine_relu_to_kernel(const float* z, float* y, int P, int Hp, i
 //   running statistics: dz = gamma * rstd * dyr
 // Pass 1 accumulates the two sums per channel over chunks of rows (fixed order => deterministic), pass 2 adds the
 // chunks in float64, pass 3 writes dz (zero on the border).
-__global__ void __launch_bounds__(256) bn_relu_bwd_partial_kernel(const float* z, const float* dy, int P, int Hp, int Wp, int C,
+// Where the gradient w.r.t. y = relu(BatchNorm(z)) comes from: a full zero-bordered NHWC tensor (dpool == nullptr), or
+// the gradient of the average-pooled y, gathered on the fly (the pooled unit never materialises y or its gradient):
+// dy[b][h][w][c] = dpool[b][h >> sh][w >> sw][c] / (kh * kw) inside the pooled region, 0 outside.  Pool sizes are
+// powers of two (every Cnn14 block).
+struct PoolGrad {
+    const float* dpool;   // (B, C, Ho, Wo) or zero-bordered NHWC (B, Ho+2, Wo+2, C)
+    int sh, sw, Ho, Wo, padded;
+    float inv;
+};
+__device__ __forceinline__ float4 load_dy4(const float* dy, const PoolGrad& pg, size_t r, int b, int hp, int wp, int C, int c) {
+    if (pg.dpool == nullptr) return __ldg(reinterpret_cast<const float4*>(dy + r * C + c));
+    const int ho = (hp - 1) >> pg.sh, wo = (wp - 1) >> pg.sw;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hp >= 1 && wp >= 1 && ho < pg.Ho && wo < pg.Wo) {
+        if (pg.padded) {
+            v = __ldg(reinterpret_cast<const float4*>(pg.dpool + (((size_t)b * (pg.Ho + 2) + ho + 1) * (pg.Wo + 2) + wo + 1) * C + c));
+        } else {
+            const size_t o = (((size_t)b * C + c) * pg.Ho + ho) * pg.Wo + wo, cs = (size_t)pg.Ho * pg.Wo;
+            v = make_float4(__ldg(pg.dpool + o), __ldg(pg.dpool + o + cs), __ldg(pg.dpool + o + 2 * cs), __ldg(pg.dpool + o + 3 * cs));
+        }
+        v.x *= pg.inv; v.y *= pg.inv; v.z *= pg.inv; v.w *= pg.inv;
+    }
+    return v;
+}
+__global__ void __launch_bounds__(256) bn_relu_bwd_partial_kernel(const float* z, const float* dy, PoolGrad pg, int P, int Hp, int Wp, int C,
                                                                   const float* scale, const float* shift, const float* mean,
                                                                   const float* rstd, float* partial /*[chunks][2][C]*/) {
     __shared__ float4 sh[512];
@@ -621,15 +645,16 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_partial_kernel(const float* z
             const float4 a = __ldg(reinterpret_cast<const float4*>(scale + c)), b = __ldg(reinterpret_cast<const float4*>(shift + c));
             const float4 m = __ldg(reinterpret_cast<const float4*>(mean + c)), rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
             // (hp, wp) of the row, advanced incrementally: no division in the loop
-            int rem = (r0 + L.rl) % (Hp * Wp);
+            int img = (r0 + L.rl) / (Hp * Wp);
+            int rem = (r0 + L.rl) - img * (Hp * Wp);
             int hp = rem / Wp, wp = rem - hp * Wp;
 #pragma unroll 2
             for (int r = r0 + L.rl; r < r1; r += L.lanes) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(z + (size_t)r * C + c));
-                const float4 d = __ldg(reinterpret_cast<const float4*>(dy + (size_t)r * C + c));
+                const float4 d = load_dy4(dy, pg, (size_t)r, img, hp, wp, C, c);
                 const bool in = hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2;   // border rows are padding
                 wp += L.lanes;
-                while (wp >= Wp) { wp -= Wp; if (++hp == Hp) hp = 0; }
+                while (wp >= Wp) { wp -= Wp; if (++hp == Hp) { hp = 0; ++img; } }
                 const float gx = (in && fmaf(v.x, a.x, b.x) > 0.0f) ? d.x : 0.0f, gy = (in && fmaf(v.y, a.y, b.y) > 0.0f) ? d.y : 0.0f;
                 const float gz = (in && fmaf(v.z, a.z, b.z) > 0.0f) ? d.z : 0.0f, gw = (in && fmaf(v.w, a.w, b.w) > 0.0f) ? d.w : 0.0f;
                 s1.x += gx; s1.y += gy; s1.z += gz; s1.w += gw;
@@ -648,19 +673,20 @@ __global__ void bn_relu_bwd_final_kernel(const float* partial, int chunks, int C
     stat_chunk_sums(partial, chunks, C, c, s1, s2);
     if ((threadIdx.x & 31) == 0) { dbeta[c] = (float)s1; dgamma[c] = (float)s2; }
 }
-__global__ void bn_relu_bwd_apply_kernel(const float* z, const float* dy, float* dz, int P, int Hp, int Wp, int C,
+__global__ void bn_relu_bwd_apply_kernel(const float* z, const float* dy, PoolGrad pg, float* dz, int P, int Hp, int Wp, int C,
                                          const float* scale, const float* shift, const float* mean, const float* rstd,
                                          const float* dgamma, const float* dbeta, float inv_count /* 0: running statistics */) {
     const int C4 = C >> 2;
     const long long total = (long long)P * C4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int p = (int)(i / C4), c = (int)(i - (long long)p * C4) << 2;
-        const int rem = p % (Hp * Wp);
+        const int img = p / (Hp * Wp);
+        const int rem = p - img * (Hp * Wp);
         const int hp = rem / Wp, wp = rem - hp * Wp;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2) {
             const float4 v4 = __ldg(reinterpret_cast<const float4*>(z + (size_t)p * C + c));
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + (size_t)p * C + c));
+            const float4 g4 = load_dy4(dy, pg, (size_t)p, img, hp, wp, C, c);
             const float v[4] = {v4.x, v4.y, v4.z, v4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
             const float4 a4 = __ldg(reinterpret_cast<const float4*>(scale + c)), b4 = __ldg(reinterpret_cast<const float4*>(shift + c));
             const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + c)), r4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
@@ -677,6 +703,40 @@ __global__ void bn_relu_bwd_apply_kernel(const float* z, const float* dy, float*
             o = make_float4(r[0], r[1], r[2], r[3]);
         }
         *reinterpret_cast<float4*>(dz + (size_t)p * C + c) = o;
+    }
+}
+
+// y = avgpool(relu(z * scale + shift)): the second unit of a ConvBlock under autograd never materialises its
+// BatchNorm+ReLU output (mst/panns.py:80-85); C % 4 == 0
+__global__ void bn_relu_avgpool_kernel(const float* z, const float* scale, const float* shift, float* y, int B, int C, int H, int W,
+                                       int kh, int kw, int out_nhwc_padded) {
+    const int Ho = H / kh, Wo = W / kw, Hp = H + 2, Wp = W + 2;
+    const float inv = 1.0f / (float)(kh * kw);
+    const int C4 = C >> 2;
+    const long long total = (long long)B * Ho * Wo * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned pix = (unsigned)(i / (unsigned)C4);
+        const int c = (int)(i - (long long)pix * C4) << 2;
+        const unsigned row = pix / (unsigned)Wo;
+        const int wo = (int)(pix - row * Wo);
+        const int b = (int)(row / (unsigned)Ho);
+        const int ho = (int)(row - (unsigned)b * Ho);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(scale + c)), sft = __ldg(reinterpret_cast<const float4*>(shift + c));
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* base = z + (((long long)b * Hp + (ho * kh + 1)) * Wp + (wo * kw + 1)) * C + c;
+        for (int dy = 0; dy < kh; ++dy)
+            for (int dx = 0; dx < kw; ++dx) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((long long)dy * Wp + dx) * C));
+                s.x += fmaxf(fmaf(v.x, a.x, sft.x), 0.f); s.y += fmaxf(fmaf(v.y, a.y, sft.y), 0.f);
+                s.z += fmaxf(fmaf(v.z, a.z, sft.z), 0.f); s.w += fmaxf(fmaf(v.w, a.w, sft.w), 0.f);
+            }
+        s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+        if (out_nhwc_padded) {
+            *reinterpret_cast<float4*>(y + (((long long)b * (Ho + 2) + ho + 1) * (Wo + 2) + wo + 1) * C + c) = s;
+        } else {
+            const long long o = (((long long)b * C + c) * Ho + ho) * Wo + wo, cs = (long long)Ho * Wo;
+            y[o] = s.x; y[o + cs] = s.y; y[o + 2 * cs] = s.z; y[o + 3 * cs] = s.w;
+        }
     }
 }
 

@@ -213,6 +213,16 @@ int dmst_conv_bn_relu_backward(const float* z_padded, const float* dy_padded, co
                                size_t workspace_bytes, void* stream);
 int dmst_conv_avgpool_backward(const float* dy, float* dx_padded, int B, int C, int H, int W, int kh, int kw,
                                int dy_padded_nhwc, void* stream);
+/* The second unit of a ConvBlock with its pooling fused (mst/panns.py:80-85): y = avg_pool2d(relu(z * scale + shift))
+ * without materialising the BatchNorm+ReLU output, and its backward from the gradient of the pooled tensor
+ * (gathered on the fly; kh and kw powers of two).  Same statistics / workspace conventions as the unfused pair. */
+int dmst_conv_bn_relu_avgpool(const float* z_padded, const float* scale, const float* shift, float* y, int B, int C,
+                              int H, int W, int kh, int kw, int out_padded_nhwc, void* stream);
+int dmst_conv_bn_relu_avgpool_backward(const float* z_padded, const float* dpooled, int kh, int kw,
+                                       int dpooled_padded_nhwc, const float* scale, const float* shift,
+                                       const float* mean, const float* rstd, int batch_stats, int B, int H, int W,
+                                       int C, float* dz_padded, float* dgamma, float* dbeta, void* workspace,
+                                       size_t workspace_bytes, void* stream);
 
 /* Spectrogram front-end of the encoder, replaces the torch.stft / abs / pow lines of
  * SpectrogramEncoder.forward (mst/modules.py:787-800): x holds B*C waveforms of T samples (row r = b*C + c at

@@ -148,7 +148,10 @@ def test_cnn14_backward_small():
     # the first block sees the gradient after it crossed all twelve TF32 layers
     cos = torch.nn.functional.cosine_similarity(ours.conv_block1.conv1.weight.grad.flatten(),
                                                 ref.conv_block1.conv1.weight.grad.flatten(), dim=0)
-    assert float(cos) > 0.99, float(cos)
+    # (measured: 0.9996 against the reference modules, 0.99976 against a float64 evaluation, which the reference itself
+    # matches to 0.99963 - tests/tools/cnn14_grad_probe.py; bitwise reproducible over 90 runs - tests/tools/cnn14_repro.py)
+    assert float(cos) > 0.99, (float(cos), relmax(got, want),
+                               [n for n, p in ours.named_parameters() if not torch.isfinite(p.grad).all()])
 
 
 def test_cnn14_forward_full_stack():
