@@ -147,10 +147,10 @@ class _Conv3x3Function(torch.autograd.Function):
             nbytes = lib.dmst_conv3x3_wgrad_workspace_bytes(B, Hp - 2, Wp - 2, Cin, Cout) if _TC_WGRAD else 0
             if nbytes:
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=gz.device)
-                g9 = torch.empty(9, Cout, Cin, dtype=torch.float32, device=gz.device)
-                _lib.check(lib.dmst_conv3x3_wgrad(_ptr(x_pad), _ptr(gz), _ptr(g9), B, Hp - 2, Wp - 2, Cin, Cout, _ptr(ws), nbytes,
+                gw = torch.empty(Cout, Cin, 3, 3, dtype=torch.float32, device=gz.device)
+                _lib.check(lib.dmst_conv3x3_wgrad(_ptr(x_pad), _ptr(gz), _ptr(gw), B, Hp - 2, Wp - 2, Cin, Cout, _ptr(ws), nbytes,
                                                   _stream(gz.device)), "dmst_conv3x3_wgrad")
-                return gx, g9.permute(1, 2, 0).reshape(Cout, Cin, 3, 3), None
+                return gx, gw, None
             # channel counts the kernels do not cover (Cin neither 1 nor a multiple of 32): library GEMMs.
             # dW[tap] = dz^T @ x shifted by the tap (a constant row offset in the flattened layout; dz is zero on the
             # border, so rows that would cross an image edge contribute nothing); K = all pixels is split into S chunks

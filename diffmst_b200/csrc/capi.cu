@@ -218,9 +218,9 @@ size_t dmst_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return 0;
     return dmst::conv3x3_wgrad_workspace_bytes(B, H, W, Cin, Cout);
 }
-int dmst_conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* g9, int B, int H, int W, int Cin, int Cout,
+int dmst_conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* dw, int B, int H, int W, int Cin, int Cout,
                        void* workspace, size_t workspace_bytes, void* stream) {
-    return dmst::conv3x3_wgrad(x_padded, dz_padded, g9, B, H, W, Cin, Cout, workspace, workspace_bytes,
+    return dmst::conv3x3_wgrad(x_padded, dz_padded, dw, B, H, W, Cin, Cout, workspace, workspace_bytes,
                                reinterpret_cast<cudaStream_t>(stream));
 }
 int dmst_conv_affine_relu_to(const float* z_padded, float* y_padded, const float* scale, const float* shift, int B, int H,

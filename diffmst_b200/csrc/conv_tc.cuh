@@ -525,11 +525,13 @@ __device__ __forceinline__ void stat_lane_reduce(const StatLayout& L, float4 a, 
     }
     __syncthreads();
 }
-// C % 4 == 0 (every Cnn14 layer); blockDim.x == 256
+// C % 4 == 0 (every Cnn14 layer); blockDim.x == 256.  CTAs take the chunks last-first: the tensor was just written
+// front to back by its producer, so its tail is what the L2 still holds (and the pass leaves the front in L2 for the
+// consumer that follows and reads front to back).
 __global__ void __launch_bounds__(256) channel_partial_kernel(const float* y, int P, int C, float* partial /*[chunks][2][C]*/) {
     __shared__ float4 sh[512];
     const StatLayout L(C);
-    const int chunk = blockIdx.x;
+    const int chunk = gridDim.x - 1 - blockIdx.x;
     const int rows = stat_rows(P);
     const int r0 = chunk * rows, r1 = min(r0 + rows, P);
     for (int g = 0; g * L.cols < (C >> 2); ++g) {
@@ -635,7 +637,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_partial_kernel(const float* z
                                                                   const float* rstd, float* partial /*[chunks][2][C]*/) {
     __shared__ float4 sh[512];
     const StatLayout L(C);
-    const int chunk = blockIdx.x;
+    const int chunk = gridDim.x - 1 - blockIdx.x;   // last-first, as channel_partial_kernel: dy was just written front to back
     const int rows = stat_rows(P);
     const int r0 = chunk * rows, r1 = min(r0 + rows, P);
     for (int g = 0; g * L.cols < (C >> 2); ++g) {
@@ -879,7 +881,8 @@ conv3x3_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dz, const __gr
     __shared__ uint32_t tmem_base_smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = blockIdx.x % kGroups, b1 = blockIdx.x / kGroups;
-    const int split = b1 % a.splits, t2 = b1 / a.splits;
+    // (pixel chunks last-first: dz was just written front to back by the BatchNorm backward, its tail is still in L2)
+    const int split = a.splits - 1 - b1 % a.splits, t2 = b1 / a.splits;
     const int n0 = (t2 % a.tiles_n) * BN, m0 = (t2 / a.tiles_n) * kWgBM;
     const int tap0 = group == 0 ? 0 : wg_max_taps(BN), ntaps = kGroups == 1 ? 9 : (group == 0 ? 5 : 4);
     const int r0 = split * a.rows_per_split;
@@ -982,15 +985,28 @@ conv3x3_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dz, const __gr
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
-// g9[i] = sum over splits of partial[split][i], fixed order; n = 9 * Cout * Cin (multiple of 4)
-__global__ void wgrad_reduce_kernel(const float* partial, int splits, long long n, float* g9) {
-    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < splits; ++k) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (size_t)k * n + i));
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-        *reinterpret_cast<float4*>(g9 + i) = s;
+// dW[co][ci][tap] = sum over splits of partial[split][tap][co][ci] (fixed order): the reduction also turns the
+// kernel's [tap][Cout][Cin] layout into nn.Conv2d's (Cout, Cin, 3, 3).  One thread per (co, ci): its nine reads are
+// coalesced across the warp, its nine outputs are contiguous.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* partial, int splits, int Cout, int Cin, float* dw) {
+    // a CTA owns 64 consecutive (co, ci) pairs = 576 contiguous outputs; thread = (pair, tap group of 3 taps)
+    __shared__ float stage[64 * 9];
+    const long long n = (long long)Cout * Cin;   // multiple of 64 (Cin % 32 == 0, Cout % 32 == 0)
+    const int j = threadIdx.x & 63, g = threadIdx.x >> 6;
+    for (long long base = (long long)blockIdx.x * 64; base < n; base += (long long)gridDim.x * 64) {
+        float acc[3] = {0.0f, 0.0f, 0.0f};
+        for (int k = 0; k < splits; ++k)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int t = g + 4 * q;
+                if (t < 9) acc[q] += __ldg(partial + ((size_t)k * 9 + t) * n + base + j);
+            }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (g + 4 * q < 9) stage[j * 9 + g + 4 * q] = acc[q];
+        __syncthreads();
+        for (int o = threadIdx.x; o < 64 * 9; o += 256) dw[base * 9 + o] = stage[o];   // coalesced
+        __syncthreads();
     }
 }
 
@@ -1035,15 +1051,15 @@ __global__ void __launch_bounds__(256) wgrad_cin1_partial_kernel(const float* dz
         }
     }
 }
-// g9[tap][co] (Cin = 1): one warp per (tap, co), lanes stride over the chunks in float64
-__global__ void wgrad_cin1_final_kernel(const float* partial, int chunks, int C, float* g9) {
+// dW[co][0][tap] (Cin = 1): one warp per (tap, co), lanes stride over the chunks in float64
+__global__ void wgrad_cin1_final_kernel(const float* partial, int chunks, int C, float* dw) {
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // tap * C + co
     if (i >= 9 * C) return;
     const int lane = threadIdx.x & 31;
     double s = 0.0;
     for (int k = lane; k < chunks; k += 32) s += partial[(size_t)k * 9 * C + i];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) g9[i] = (float)s;
+    if (lane == 0) dw[(i % C) * 9 + i / C] = (float)s;
 }
 
 struct WgradPlan { int bn, tiles_m, tiles_n, splits, rows_per_split; };
@@ -1073,10 +1089,10 @@ inline size_t conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Co
     const WgradPlan w = wgrad_plan((long long)B * (H + 2) * (W + 2), Cin, Cout);
     return (size_t)w.splits * 9 * Cout * Cin * sizeof(float);
 }
-// x_padded (B, H+2, W+2, Cin), dz_padded (B, H+2, W+2, Cout) with a zero border -> g9 [9][Cout][Cin]
-inline int conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* g9, int B, int H, int W, int Cin, int Cout,
+// x_padded (B, H+2, W+2, Cin), dz_padded (B, H+2, W+2, Cout) with a zero border -> dw (Cout, Cin, 3, 3)
+inline int conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* dw, int B, int H, int W, int Cin, int Cout,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    if (!x_padded || !dz_padded || !g9 || !workspace || B <= 0 || H <= 0 || W <= 0) return DMST_EINVAL;
+    if (!x_padded || !dz_padded || !dw || !workspace || B <= 0 || H <= 0 || W <= 0) return DMST_EINVAL;
     if (!wgrad_supported(Cin, Cout)) return DMST_EINVAL;
     const long long P = (long long)B * (H + 2) * (W + 2);
     if (P > 0x7fffffffLL) return DMST_EINVAL;
@@ -1085,7 +1101,7 @@ inline int conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* g
         const int chunks = (int)((P + stat_rows(P) - 1) / stat_rows(P));
         float* partial = reinterpret_cast<float*>(workspace);
         wgrad_cin1_partial_kernel<<<chunks, 256, 0, stream>>>(dz_padded, x_padded, (int)P, W + 2, Cout, partial);
-        wgrad_cin1_final_kernel<<<(9 * Cout + 7) / 8, 256, 0, stream>>>(partial, chunks, Cout, g9);
+        wgrad_cin1_final_kernel<<<(9 * Cout + 7) / 8, 256, 0, stream>>>(partial, chunks, Cout, dw);
         return (int)cudaGetLastError();
     }
     const WgradPlan w = wgrad_plan(P, Cin, Cout);
@@ -1105,8 +1121,7 @@ inline int conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* g
     const int grid = w.tiles_m * w.tiles_n * w.splits * wg_groups(w.bn);
     if (w.bn == 64) conv3x3_wgrad_tf32_kernel<64><<<grid, kConvThreads, smem, stream>>>(mdz, mx, a);
     else conv3x3_wgrad_tf32_kernel<32><<<grid, kConvThreads, smem, stream>>>(mdz, mx, a);
-    const long long n = 9LL * Cout * Cin;
-    wgrad_reduce_kernel<<<grid_for(n / 4), 256, 0, stream>>>(a.partial, w.splits, n, g9);
+    wgrad_reduce_kernel<<<grid_for((long long)Cout * Cin * 4), 256, 0, stream>>>(a.partial, w.splits, Cout, Cin, dw);  // (Cout * Cin) / 64 CTAs at most
     return (int)cudaGetLastError();
 }
 

@@ -193,11 +193,11 @@ int dmst_conv_avgpool(const float* x_padded, float* y, int B, int C, int H, int 
                       int out_padded_nhwc, void* stream);
 
 /* Weight gradient of the 3x3 convolution on the tensor cores (tcgen05, TF32, MN-major operands straight from the
- * NHWC tensors): g9[tap][co][ci] = sum over pixels of dz[p][co] * x[p + tap offset][ci]; dz_padded must be zero on
- * its border.  Needs Cin % 32 == 0 and Cout % 32 == 0, or Cin == 1 (the first layer: a streaming kernel, the layer is
- * memory bound); workspace_bytes returns 0 for other shapes.  g9 is the layout of dmst_conv_repack_weights. */
+ * NHWC tensors): dw[co][ci][tap] = sum over pixels of dz[p][co] * x[p + tap offset][ci], i.e. the gradient in
+ * nn.Conv2d's own (Cout, Cin, 3, 3) layout; dz_padded must be zero on its border.  Needs Cin % 32 == 0 and Cout % 32 == 0, or Cin == 1 (the first layer: a streaming kernel, the layer is
+ * memory bound); workspace_bytes returns 0 for other shapes. */
 size_t dmst_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout);
-int dmst_conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* g9, int B, int H, int W, int Cin,
+int dmst_conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* dw, int B, int H, int W, int Cin,
                        int Cout, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Differentiable path of the same units (autograd of mst/panns.py:79-85).  y = relu(z * scale + shift) out of place
