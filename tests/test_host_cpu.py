@@ -56,3 +56,33 @@ def test_param_ranges_and_dict_layout_match_reference_tables():
     assert len(con.state_dict()) == 0 and len(BasicMixConsole(44100).state_dict()) == 0
     r = con._c_ranges()
     assert (r.track_lo[20], r.track_hi[20]) == (1.0, 10.0) and (r.master_lo[25], r.master_hi[25]) == (-48.0, 48.0)
+
+
+def test_host_side_sizing_and_refusals_of_the_encoder_path():
+    """Host arithmetic of the convolution entry points (no GPU work): the weight-gradient workspace follows the
+    split plan (about two CTAs per SM, whole 32-row stages), unsupported channel counts report 0 so that the caller
+    takes the library arm, and the graph / encoder front ends refuse CPU tensors."""
+    from diffmst_b200 import GraphedStep, SpectrogramEncoder, _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    f = lib.dmst_conv3x3_wgrad_workspace_bytes
+    f.restype = ctypes.c_size_t
+    f.argtypes = [ctypes.c_int] * 5
+    # block1.conv2 at batch 4: 64 -> 64, one 128 x 64 tile, two tap groups -> 148 pixel splits of partial sums
+    P = 4 * 1027 * 259
+    n = f(4, 1025, 257, 64, 64)
+    assert n % (9 * 64 * 64 * 4) == 0
+    splits = n // (9 * 64 * 64 * 4)
+    assert 140 <= splits <= 148 and splits * ((P + splits - 1) // splits + 31) >= P
+    # the deepest layer: many tiles, one split
+    assert f(4, 2, 4, 2048, 2048) == 9 * 2048 * 2048 * 4
+    # first layer (streaming kernel), and shapes neither kernel covers
+    assert f(4, 1025, 257, 1, 64) > 0
+    assert f(1, 8, 8, 3, 64) == 0 and f(1, 8, 8, 48, 40) == 0 and f(0, 8, 8, 64, 64) == 0
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        GraphedStep(lambda: None, params=[torch.zeros(1, requires_grad=True)])
+    with pytest.raises(ValueError, match="at least one parameter"):
+        GraphedStep(lambda: None, params=[])
+    enc = SpectrogramEncoder(embed_dim=8)
+    assert set(k.split(".")[0] for k in enc.state_dict()) == {"window", "model"}
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        enc(torch.zeros(1, 1, 40000))
