@@ -131,27 +131,53 @@ def test_conv3x3_function_gradients_single_layer():
 
 
 def test_cnn14_backward_small():
+    """Whole-network gradient against the FLOAT64 evaluation of the reference modules (the oracle principle; the
+    reference's own TF32 cuDNN path is 0.9996 away from float64 in cosine on the same case,
+    tests/tools/cnn14_grad_probe.py).  Ours is bitwise reproducible within and across processes
+    (tests/tools/cnn14_repro.py, cnn14_checksum.py, cnn14_poison.py).  The weights come from the seeded global generator
+    (conftest.py).  This torch build seeds itself randomly per process, and about one weight draw in twelve is
+    pathological for this quantity: with seed 20261017 even the reference's float32 CPU evaluation has cosine 0.75 to
+    its own float64 evaluation in the first layer (a ReLU / max decision sits on a tie), and so did ours (0.74); for
+    seeds 0..3 float32 agrees with float64 to 1e-10 or better."""
     from diffmst_b200 import Cnn14
     g = torch.Generator().manual_seed(3)
     # running-statistics BatchNorm: the last blocks see 1x2 / 1x1 maps, where batch statistics over two items are
     # ill-conditioned (batch-statistics BatchNorm is covered per block in test_conv_block_backward)
-    ref = OracleCnn14(num_classes=32).cuda().eval()
+    ref = OracleCnn14(num_classes=32).cuda().double().eval()
     ours = Cnn14(num_classes=32).cuda().eval()
-    ours.load_state_dict(ref.state_dict(), strict=True)
+    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()}, strict=True)
     x = (torch.rand(2, 1, 1024, 128, generator=g) ** 2).cuda()   # smallest input that survives the six poolings
-    want, got = ref(x), ours(x)
+    want, got = ref(x.double()), ours(x)
     assert relmax(got, want) <= 2e-2
     want.square().mean().backward()
     got.square().mean().backward()
     for (n, po), (_, pr) in zip(ours.named_parameters(), ref.named_parameters()):
         assert po.grad is not None and torch.isfinite(po.grad).all(), n
-    # the first block sees the gradient after it crossed all twelve TF32 layers
-    cos = torch.nn.functional.cosine_similarity(ours.conv_block1.conv1.weight.grad.flatten(),
-                                                ref.conv_block1.conv1.weight.grad.flatten(), dim=0)
-    # (measured: 0.9996 against the reference modules, 0.99976 against a float64 evaluation, which the reference itself
-    # matches to 0.99963 - tests/tools/cnn14_grad_probe.py; bitwise reproducible over 90 runs - tests/tools/cnn14_repro.py)
-    assert float(cos) > 0.99, (float(cos), relmax(got, want),
-                               [n for n, p in ours.named_parameters() if not torch.isfinite(p.grad).all()])
+    cos = lambda a, b: float(torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0))
+    # The reference's own numerics (float32 modules on cuDNN with TF32 convolutions, torch's default) on the same
+    # weights and input: for weight draws whose deep 1x1 / 2x2 maps leave little gradient signal, the first block's
+    # gradient - after twelve TF32 layers - is rounding-noise dominated for ANY TF32 evaluation, so the bound is the
+    # reference's own distance from float64 where that is larger than the nominal one (SURVEY.md section 8c protocol).
+    ref32 = OracleCnn14(num_classes=32).cuda().eval()
+    ref32.load_state_dict({k: v.float() for k, v in ref.state_dict().items()}, strict=True)
+    torch.backends.cudnn.allow_tf32 = True
+    ref32(x).square().mean().backward()
+    torch.backends.cudnn.allow_tf32 = False
+    report = {}
+    for name in ("conv_block1.conv1", "conv_block3.conv1", "conv_block6.conv2"):
+        w64 = dict(ref.named_parameters())[name + ".weight"].grad
+        c_ours = cos(dict(ours.named_parameters())[name + ".weight"].grad, w64)
+        c_ref = cos(dict(ref32.named_parameters())[name + ".weight"].grad, w64)
+        report[name] = (c_ours, c_ref)
+    print("cosine to float64 (ours, reference TF32):", report)
+    for name, (c_ours, c_ref) in report.items():
+        assert 1.0 - c_ours <= max(2e-3, 2.0 * (1.0 - c_ref)), (name, report, relmax(got, want))
+    # and the step is reproducible bit for bit
+    g1 = ours.conv_block1.conv1.weight.grad.clone()
+    for p in ours.parameters():
+        p.grad = None
+    ours(x).square().mean().backward()
+    assert torch.equal(g1, ours.conv_block1.conv1.weight.grad)
 
 
 def test_cnn14_forward_full_stack():
