@@ -43,5 +43,3 @@ conv._CUDA_BN_POOL = True
 torch.cuda.reset_peak_memory_stats()
 t, m = timeit(ref)
 print(f"                                              reference modules (cuDNN TF32, NCHW) {t:8.2f} ms   peak {m:.1f} GiB")
-refcl = ref.to(memory_format=torch.channels_last)
-xcl = x.contiguous(memory_format=torch.channels_last)
