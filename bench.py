@@ -54,7 +54,7 @@ class ClockSampler:
         self.index = index
         self.rows = []      # (host time, fields)
         self.proc = None
-        self.window = None  # (t0, t1) host times of the timed region
+        self.windows = []   # (t0, t1) host times of the timed regions
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -84,9 +84,9 @@ class ClockSampler:
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = self.rows
-        if self.window is not None:
-            inside = [r for r in rows if self.window[0] <= r[0] <= self.window[1] + 0.05]
-            rows = inside if inside else rows[-3:]   # region shorter than the sampling period
+        if self.windows:
+            inside = [r for r in rows if any(w[0] <= r[0] <= w[1] + 0.05 for w in self.windows)]
+            rows = inside if inside else rows[-3:]   # regions shorter than the sampling period
         for _, r in rows:
             if len(r) < 6:
                 continue
@@ -237,10 +237,7 @@ def run_ours(args):
         step(tracks)
     ev1.record()
     barrier()
-    sampler.window = (t_host0, time.perf_counter())
-    if rank == 0:
-        time.sleep(0.06)         # let the sampler deliver the sample taken during the region
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.windows.append((t_host0, time.perf_counter()))
     ms = ev0.elapsed_time(ev1)
     kern_ms = {}
     buf = (ctypes.c_float * args.steps)()
@@ -271,11 +268,13 @@ def run_ours(args):
     use_graph = int(ok.item()) == 1
     if use_graph:
         barrier()
+        t_host1 = time.perf_counter()
         ev0.record()
         for _ in range(args.steps):
             graphed()
         ev1.record()
         barrier()
+        sampler.windows.append((t_host1, time.perf_counter()))
         t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -287,6 +286,11 @@ def run_ours(args):
         ms_max = ms_eager_max
         step_loss = float(step(tracks).detach())
         launch_note = f"eager launches (CUDA-graph capture failed on some rank: {graph_err})"
+
+    # clocks / throttle reasons: the samples that fall inside the two timed regions (eager, graph replay)
+    if rank == 0:
+        time.sleep(0.06)         # let the sampler deliver the sample taken during the region
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- end to end: host buffers, H2D of the step's inputs, D2H of its results ----
     pinned = [tracks_h.pin_memory(), tracks_h.clone().pin_memory()]
@@ -385,8 +389,8 @@ def run_ours(args):
                            "l2": "inputs larger than L2 (134 MB of tracks per step, re-read every step)"},
                 "eager": {"ms_per_step": ms_eager_max / args.steps,
                           "value": units / (ms_eager_max / 1e3 / args.steps), "unit": UNIT,
-                          "note": "same step launched eagerly from Python; the per-kernel times of `roofline` and "
-                                  "the clock samples were taken over this region"},
+                          "note": "same step launched eagerly from Python; the per-kernel times of `roofline` were "
+                                  "taken over this region (`clocks`: samples inside this region and the graph-replay region)"},
                 "loss": step_loss,
                 "clocks": clocks, "gpu_launches": GPU_LAUNCHES_PER_STEP * args.steps,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
