@@ -37,7 +37,7 @@ def rel_l2(a, b):
 
 # (lengths >= 32768: below that the oracle's own FFT method time-aliases; the second case has a
 # ragged last tile and more than one item)
-@pytest.mark.parametrize("shape", [(1, 2, 32768), (2, 3, 36871)])
+@pytest.mark.parametrize("shape", [(1, 2, 32768), (2, 3, 36871), (1, 1, 33001)])
 def test_emulated_console_kernels_match_float64_oracle(emul_console, shape):
     from oracle.console import OracleAdvancedMixConsole
     B, N, T = shape
