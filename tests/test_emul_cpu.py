@@ -92,3 +92,27 @@ def test_emulated_console_flag_combinations(emul_console, flags):
         assert rel_l2(gmp, o64[4]) <= max(1e-3, 1.5 * rel_l2(o32[4], o64[4]))
     else:
         assert float(np.abs(np.nan_to_num(gmp)).max()) == 0.0
+
+
+def test_emulated_basic_console_config0_shape(emul_console):
+    """BASELINE configs[0]: BasicMixConsole (gain + pan + bus sum), 4 tracks x 44100 samples, batch 1.  Gain and pan are
+    per-track scalars and the bus sum is an indexing contract: float32-exact against the oracle evaluated in float32
+    is not required of a different summation order, so the bound is 1e-6 relative (observed ~1e-7)."""
+    from oracle.console import OracleBasicMixConsole
+    B, N, T = 1, 4, 44100
+    g = torch.Generator().manual_seed(44100)
+    tracks = torch.randn(B, N, T, generator=g) * 0.1
+    tp = torch.rand(B, N, 2, generator=g)
+    probe = torch.randn(B, 2, T, generator=g)
+    con = emul_console.EmulConsole()
+    flags = emul_console.BASIC_CONSOLE | emul_console.USE_TRACK_INPUT_FADER | emul_console.USE_TRACK_PANNER
+    mix, mixed, _ = con.forward(tracks.numpy(), tp.numpy(), None, flags, la_t=0, la_m=0, want_mixed=True)
+    gtp, _, gtr = con.backward(probe.numpy())
+    tpd, trd = tp.double().requires_grad_(True), tracks.double().requires_grad_(True)
+    omixed, omix, _, _, _ = OracleBasicMixConsole(44100)(trd, tpd)
+    (omix * probe.double()).sum().backward()
+    assert mix.shape == (B, 2, T) and mixed.shape == (B, 2, N, T)
+    assert rel_max(mix, omix.detach().numpy()) <= 1e-6
+    assert rel_max(mixed, omixed.detach().numpy()) <= 1e-6
+    assert rel_l2(gtp, tpd.grad.numpy()) <= 1e-5
+    assert rel_l2(gtr, trd.grad.numpy()) <= 1e-6
