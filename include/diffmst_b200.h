@@ -192,7 +192,8 @@ int dmst_conv_affine_relu(float* y_padded, const float* scale, const float* shif
 int dmst_conv_avgpool(const float* x_padded, float* y, int B, int C, int H, int W, int kh, int kw,
                       int out_padded_nhwc, void* stream);
 
-/* Weight gradient of the 3x3 convolution on the tensor cores (tcgen05, TF32, MN-major operands straight from the
+/* Weight gradient of the 3x3 convolution (what autograd computes for the nn.Conv2d layers of mst/panns.py:33-47,
+ * i.e. torch.nn.grad.conv2d_weight) on the tensor cores (tcgen05, TF32, MN-major operands straight from the
  * NHWC tensors): dw[co][ci][tap] = sum over pixels of dz[p][co] * x[p + tap offset][ci], i.e. the gradient in
  * nn.Conv2d's own (Cout, Cin, 3, 3) layout; dz_padded must be zero on its border.  Needs Cin % 32 == 0 and Cout % 32 == 0, or Cin == 1 (the first layer: a streaming kernel, the layer is
  * memory bound); workspace_bytes returns 0 for other shapes. */
