@@ -109,3 +109,51 @@ def test_bark_and_peaknorm_golden(golden):
     assert np.array_equal(fb.argmax(0).numpy(), d["argmax"])
     d = golden("peaknorm")
     assert np.array_equal(batch_stereo_peak_normalize(torch.from_numpy(d["x"])).numpy(), d["y"])
+
+
+def test_panns_oracle_matches_reference_golden(golden):
+    """oracle/panns.py against the reference's own mst.panns.ConvBlock / Cnn14 (tests/golden/make_golden_panns.py,
+    float64, generator-free parameter fill of tests/golden/panns_fill.py): the a11 row's oracle is pinned."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from panns_fill import fill_state
+    from oracle.panns import OracleCnn14, OracleConvBlock
+    d = golden("panns")
+    blk = OracleConvBlock(3, 8).double().train()
+    fill_state(blk)
+    x = torch.from_numpy(d["block_x"]).requires_grad_(True)
+    y = blk(x, (2, 2))
+    (y * torch.from_numpy(d["block_probe"])).sum().backward()
+    assert _relmax(y.detach().numpy(), d["block_y"]) <= 1e-12
+    assert _relmax(x.grad.numpy(), d["block_gx"]) <= 1e-11
+    for n, p in blk.named_parameters():
+        assert _relmax(p.grad.numpy(), d["block_g_" + n.replace(".", "_")]) <= 1e-10, n
+    assert _relmax(blk.bn1.running_mean.numpy(), d["block_running_mean1"]) <= 1e-12   # training-mode bookkeeping
+    assert _relmax(blk.bn1.running_var.numpy(), d["block_running_var1"]) <= 1e-12
+    net = OracleCnn14(num_classes=6).double().eval()
+    fill_state(net)
+    g = torch.Generator().manual_seed(42)
+    xin = (torch.rand(1, 1, 1024, 128, generator=g) ** 2).double()
+    out = net(xin)
+    out.square().mean().backward()
+    assert _relmax(out.detach().numpy(), d["cnn14_out"]) <= 1e-10
+    grads = dict(net.named_parameters())
+    for i, n in enumerate(d["cnn14_grad_names"]):
+        gsum, gabs = float(grads[str(n)].grad.sum()), float(grads[str(n)].grad.abs().sum())
+        assert abs(gabs - d["cnn14_grad_abs"][i]) <= 1e-9 * d["cnn14_grad_abs"][i], n
+        assert abs(gsum - d["cnn14_grad_sum"][i]) <= 1e-9 * d["cnn14_grad_abs"][i], n
+    assert _relmax(grads["conv_block1.conv1.weight"].grad.numpy(), d["cnn14_g_first"]) <= 1e-9
+    assert _relmax(grads["fc.weight"].grad.numpy(), d["cnn14_g_fc"]) <= 1e-10
+
+
+def test_spectrogram_front_end_formula_golden(golden):
+    """The spectrogram lines of the reference's SpectrogramEncoder.forward (mst/modules.py:787-800; golden written by
+    the reference class with its trunk replaced by an identity): STFT 2048 / 512, periodic Hann, centred with reflect
+    padding, (|X| + 1e-8)^0.3, layout (bs, chs, bins, frames).  This is the formula dmst_spectrogram_frontend
+    implements (GPU test: test_conv_gpu.py::test_spectrogram_frontend_matches_torch_stft_composition)."""
+    d = golden("panns")
+    w = torch.from_numpy(d["spec_wave"])
+    X = torch.stft(w.view(-1, w.shape[-1]), n_fft=2048, hop_length=512, window=torch.hann_window(2048), return_complex=True)
+    S = torch.pow(X.abs().view(w.shape[0], w.shape[1], 1025, -1) + 1e-8, 0.3)
+    assert S.shape == d["spec_out"].shape == (2, 1, 1025, 33)
+    assert _relmax(S.numpy(), d["spec_out"]) <= 1e-6
