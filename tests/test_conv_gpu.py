@@ -274,3 +274,35 @@ def test_wgrad_tensor_core_matches_float64(shape):
     assert relmax(got, want) <= (1e-5 if Cin == 1 else TOL), relmax(got, want)
     assert torch.equal(got, wgrad(True))
     assert relmax(wgrad(False), want) <= TOL
+
+
+def test_encoder_matches_reference_golden(golden):
+    """The product against the golden vectors written by the REFERENCE's own classes (tests/golden/make_golden_panns.py:
+    mst.panns.Cnn14 in float64 with the generator-free parameter fill, and the spectrogram lines of
+    mst.modules.SpectrogramEncoder.forward).  The case is well conditioned - the reference algorithm with its
+    operands rounded to TF32 on the CPU is 8.6e-5 from the golden output, cosine 0.99960 / 0.99998 for the first-layer
+    / head gradients - so the bounds below are the convolution tolerance and 5x those gradient distances."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from panns_fill import fill_state
+    from diffmst_b200 import Cnn14, SpectrogramEncoder
+    d = golden("panns")
+    net = Cnn14(num_classes=6).cuda().eval()
+    fill_state(net)
+    g = torch.Generator().manual_seed(42)
+    x = (torch.rand(1, 1, 1024, 128, generator=g) ** 2).cuda()
+    with torch.no_grad():
+        out_eval = net(x)                      # inference path (BatchNorm folded into the convolution epilogue)
+    out = net(x)                               # differentiable path
+    out.square().mean().backward()
+    want = torch.from_numpy(d["cnn14_out"]).cuda()
+    assert relmax(out_eval, want) <= TOL, relmax(out_eval, want)
+    assert relmax(out, want) <= TOL, relmax(out, want)
+    cos = lambda a, b: float(torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0))
+    c_first = cos(net.conv_block1.conv1.weight.grad, torch.from_numpy(d["cnn14_g_first"]).cuda())
+    c_fc = cos(net.fc.weight.grad, torch.from_numpy(d["cnn14_g_fc"]).cuda())
+    assert c_first >= 0.998 and c_fc >= 0.9999, (c_first, c_fc)
+    enc = SpectrogramEncoder(embed_dim=8).cuda().eval()
+    S = enc._frontend(torch.from_numpy(d["spec_wave"]).cuda())[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)
+    assert S.shape == d["spec_out"].shape
+    assert relmax(S, torch.from_numpy(d["spec_out"]).cuda()) <= 1e-4
