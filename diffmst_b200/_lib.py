@@ -71,6 +71,8 @@ def lib():
     l.dmst_peak_normalize.argtypes = [vp, ll, ll, vp, i, i, vp]
     l.dmst_conv_nchw_to_padded_nhwc.restype = i
     l.dmst_conv_nchw_to_padded_nhwc.argtypes = [vp, vp, i, i, i, i, vp]
+    l.dmst_conv_round_tf32.restype = i
+    l.dmst_conv_round_tf32.argtypes = [vp, vp, ll, i, i, i, i, vp]
     l.dmst_conv_repack_weights.restype = i
     l.dmst_conv_repack_weights.argtypes = [vp, vp, i, i, vp]
     l.dmst_conv_repack_weights_dgrad.restype = i

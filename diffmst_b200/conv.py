@@ -49,21 +49,58 @@ _CUDA_BN_POOL = True
 _TC_WGRAD = True       # False: weight gradient through the split-K batched library GEMMs (comparison / fallback arm)
 
 _REPACK_CACHE = {}   # id(parameter) -> (weak reference to it, data_ptr, version, [9][Cout][Cin] tensor)
+RELU, ROUND_TF32 = 1, 2   # mask of the `relu` argument of the convolution / affine entry points (include/diffmst_b200.h)
+
+
+def clear_repack_cache():
+    """Forget the repacked inference weights (call after modifying a weight through ``.data`` in eval mode)."""
+    _REPACK_CACHE.clear()
 
 
 def _repack(w):
-    """[Cout][Cin][3][3] -> [9][Cout][Cin], cached until the parameter is modified (inference repacks once)."""
+    """[Cout][Cin][3][3] -> [9][Cout][Cin] (rounded to TF32 for the tensor-core kernel).
+
+    Cached only for inference (autograd off, no CUDA-graph capture in progress): an optimizer step, or
+    ``weight.data.copy_()``, does not bump ``weight._version``, so a cache consulted while training - or a graph
+    captured after an eager warm-up had filled it - would silently keep the old weights in forward while dgrad
+    repacks fresh ones.  With autograd on, or while a stream is capturing, the (small) repack kernel always runs and is
+    part of the captured graph."""
+    cacheable = not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing()
     key = id(w)
-    hit = _REPACK_CACHE.get(key)
-    if hit is not None and hit[0]() is w and hit[1] == w.data_ptr() and hit[2] == w._version and hit[3].device == w.device:
-        return hit[3]
+    if cacheable:
+        hit = _REPACK_CACHE.get(key)
+        if hit is not None and hit[0]() is w and hit[1] == w.data_ptr() and hit[2] == w._version and hit[3].device == w.device:
+            return hit[3]
     lib = _lib.lib()
     Cout, Cin = w.shape[0], w.shape[1]
     w9 = torch.empty(9, Cout, Cin, dtype=torch.float32, device=w.device)
     _lib.check(lib.dmst_conv_repack_weights(_ptr(w.detach().contiguous()), _ptr(w9), Cout, Cin, _stream(w.device)),
                "dmst_conv_repack_weights")
-    _REPACK_CACHE[key] = (weakref.ref(w, lambda _r, k=key: _REPACK_CACHE.pop(k, None)), w.data_ptr(), w._version, w9)
+    if cacheable:
+        _REPACK_CACHE[key] = (weakref.ref(w, lambda _r, k=key: _REPACK_CACHE.pop(k, None)), w.data_ptr(), w._version, w9)
+    else:
+        _REPACK_CACHE.pop(key, None)
     return w9
+
+
+def _round_tf32(x, bordered_shape=None):
+    """Copy of x rounded to nearest TF32; bordered_shape = (B, Hp, Wp, C) also clears the one-pixel border."""
+    lib = _lib.lib()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    if x.numel() == 0:
+        return y
+    if bordered_shape is None:
+        B = H = W = C = 0
+    else:
+        B, Hp, Wp, C = bordered_shape
+        H, W = Hp - 2, Wp - 2
+    _lib.check(lib.dmst_conv_round_tf32(_ptr(x), _ptr(y), x.numel(), B, H, W, C, _stream(x.device)), "dmst_conv_round_tf32")
+    return y
+
+
+def _tc_operand(C):
+    return C % 32 == 0
 
 
 def _conv3x3(x_pad, w9, scale, shift, y, B, H, W, Cin, Cout, relu, what="dmst_conv3x3_forward"):
@@ -89,10 +126,10 @@ def _conv_bn_relu(x_pad, conv: nn.Conv2d, bn, training: bool):
     if is_bn and not use_batch_stats:
         scale = (bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)).float().contiguous()
         shift = (bn.bias.detach() - bn.running_mean * scale).float().contiguous()
-        _conv3x3(x_pad, w9, scale, shift, y, B, H, W, Cin, Cout, 1)
+        _conv3x3(x_pad, w9, scale, shift, y, B, H, W, Cin, Cout, RELU | ROUND_TF32)
         return y
     if not is_bn:
-        _conv3x3(x_pad, w9, None, None, y, B, H, W, Cin, Cout, 1)
+        _conv3x3(x_pad, w9, None, None, y, B, H, W, Cin, Cout, RELU | ROUND_TF32)
         return y
     # training-mode BatchNorm: raw conv -> batch statistics -> affine + ReLU in place
     _conv3x3(x_pad, w9, None, None, y, B, H, W, Cin, Cout, 0)
@@ -101,7 +138,7 @@ def _conv_bn_relu(x_pad, conv: nn.Conv2d, bn, training: bool):
         _update_running_stats(bn, mean, var, B * H * W)
     scale = (bn.weight.detach() * torch.rsqrt(var + bn.eps)).contiguous()
     shift = (bn.bias.detach() - mean * scale).contiguous()
-    _lib.check(lib.dmst_conv_affine_relu(_ptr(y), _ptr(scale), _ptr(shift), B, H, W, Cout, 1, _stream(dev)),
+    _lib.check(lib.dmst_conv_affine_relu(_ptr(y), _ptr(scale), _ptr(shift), B, H, W, Cout, RELU | ROUND_TF32, _stream(dev)),
                "dmst_conv_affine_relu")
     return y
 
@@ -110,14 +147,18 @@ class _Conv3x3Function(torch.autograd.Function):
     """z = conv3x3(x) on zero-bordered NHWC tensors (no bias, stride 1, padding 1; mst/panns.py:33-47)."""
 
     @staticmethod
-    def forward(ctx, x_pad, weight, clean_border=False):
-        # clean_border: the gradient that will arrive for z is known to be zero on the border (it comes from
-        # _BnReluFunction), so backward need not clear it
+    def forward(ctx, x_pad, weight, clean_border=False, x_rounded=False):
+        # clean_border: the gradient that will arrive for z is known to be zero on the border and rounded to TF32 (it
+        # comes from _BnReluFunction), so backward need not clear / round it.
+        # x_rounded: x_pad was produced by one of this library's kernels, which round what they hand to a convolution
+        # to TF32; any other input is rounded here (the tensor core would truncate it, see csrc/conv_tc.cuh).
         ctx.clean_border = bool(clean_border)
         lib = _lib.lib()
         B, Hp, Wp, Cin = x_pad.shape
         Cout = weight.shape[0]
         x_pad = x_pad.contiguous()
+        if not x_rounded and _tc_operand(Cin):
+            x_pad = _round_tf32(x_pad)
         w9 = _repack(weight)
         z = torch.empty(B, Hp, Wp, Cout, dtype=torch.float32, device=x_pad.device)
         _conv3x3(x_pad, w9, None, None, z, B, Hp - 2, Wp - 2, Cin, Cout, 0)
@@ -132,8 +173,13 @@ class _Conv3x3Function(torch.autograd.Function):
         Cout = w9.shape[1]
         gz = gz.contiguous()
         if not ctx.clean_border:
-            # the border of the output is padding: whatever gradient arrives there does not exist upstream
-            gz[:, 0, :, :] = 0; gz[:, -1, :, :] = 0; gz[:, :, 0, :] = 0; gz[:, :, -1, :] = 0
+            # the border of the output is padding: whatever gradient arrives there does not exist upstream.  Out of
+            # place (the incoming tensor belongs to autograd and may be shared), rounded to TF32 on the way.
+            if _tc_operand(Cout) and _tc_operand(Cin):   # a tensor-core dgrad / wgrad will read it
+                gz = _round_tf32(gz, (B, Hp, Wp, Cout))
+            else:
+                gz = gz.clone()
+                gz[:, 0, :, :] = 0; gz[:, -1, :, :] = 0; gz[:, :, 0, :] = 0; gz[:, :, -1, :] = 0
         gx = gw = None
         if ctx.needs_input_grad[0]:
             # dgrad: correlation with the flipped taps, channel roles swapped -> the same kernel
@@ -150,7 +196,7 @@ class _Conv3x3Function(torch.autograd.Function):
                 gw = torch.empty(Cout, Cin, 3, 3, dtype=torch.float32, device=gz.device)
                 _lib.check(lib.dmst_conv3x3_wgrad(_ptr(x_pad), _ptr(gz), _ptr(gw), B, Hp - 2, Wp - 2, Cin, Cout, _ptr(ws), nbytes,
                                                   _stream(gz.device)), "dmst_conv3x3_wgrad")
-                return gx, gw, None
+                return gx, gw, None, None
             # channel counts the kernels do not cover (Cin neither 1 nor a multiple of 32): library GEMMs.
             # dW[tap] = dz^T @ x shifted by the tap (a constant row offset in the flattened layout; dz is zero on the
             # border, so rows that would cross an image edge contribute nothing); K = all pixels is split into S chunks
@@ -180,7 +226,7 @@ class _Conv3x3Function(torch.autograd.Function):
             finally:
                 torch.backends.cuda.matmul.allow_tf32 = tf32
             gw = g9.permute(1, 2, 0).reshape(Cout, Cin, 3, 3)
-        return gx, gw, None
+        return gx, gw, None, None
 
 
 def _needs_grad(x, *modules):
@@ -319,13 +365,13 @@ class _AvgPoolFunction(torch.autograd.Function):
         return gx, None, None, None
 
 
-def _conv_bn_relu_autograd(x_pad, conv: nn.Conv2d, bn, training: bool, pool=None):
+def _conv_bn_relu_autograd(x_pad, conv: nn.Conv2d, bn, training: bool, pool=None, x_rounded=False):
     """Differentiable twin of _conv_bn_relu: tensor-core conv Function, then BatchNorm + ReLU as one CUDA Function
     (statistics, normalisation and their backward in csrc/conv_tc.cuh).  pool = (kh, kw, out_padded_nhwc) fuses the
     block's average pooling into that Function when the pool sizes are powers of two."""
     C = conv.weight.shape[0]
     cuda_bn = isinstance(bn, nn.BatchNorm2d) and C % 4 == 0 and _CUDA_BN_POOL
-    z = _Conv3x3Function.apply(x_pad, conv.weight, cuda_bn)
+    z = _Conv3x3Function.apply(x_pad, conv.weight, cuda_bn, x_rounded)
     if cuda_bn:
         batch_stats = bn.training or bn.running_mean is None   # nn.BatchNorm2d.forward's rule
         if batch_stats:
@@ -411,11 +457,14 @@ class ConvBlock(nn.Module):
             init_bn(self.bn1)
             init_bn(self.bn2)
 
-    def forward_nhwc(self, x_pad, pool_size, out_padded_nhwc: bool):
+    def forward_nhwc(self, x_pad, pool_size, out_padded_nhwc: bool, x_rounded: bool = False):
+        """x_rounded: x_pad comes from one of this library's kernels (already rounded to TF32 where it matters)."""
         kh, kw = int(pool_size[0]), int(pool_size[1])
         if _needs_grad(x_pad, self):
-            x = _conv_bn_relu_autograd(x_pad, self.conv1, self.bn1, self.training)
-            return _conv_bn_relu_autograd(x, self.conv2, self.bn2, self.training, pool=(kh, kw, out_padded_nhwc))
+            cuda_bn1 = isinstance(self.bn1, nn.BatchNorm2d) and self.conv1.weight.shape[0] % 4 == 0 and _CUDA_BN_POOL
+            x = _conv_bn_relu_autograd(x_pad, self.conv1, self.bn1, self.training, x_rounded=x_rounded)
+            return _conv_bn_relu_autograd(x, self.conv2, self.bn2, self.training, pool=(kh, kw, out_padded_nhwc),
+                                          x_rounded=cuda_bn1)
         x = _conv_bn_relu(x_pad, self.conv1, self.bn1, self.training)
         x = _conv_bn_relu(x, self.conv2, self.bn2, self.training)
         return _avgpool(x, kh, kw, out_padded_nhwc)
@@ -446,7 +495,10 @@ class Cnn14(nn.Module):
     def forward_padded_nhwc(self, h: torch.Tensor):
         """Same as forward for an input already in the zero-bordered NHWC layout (B, H+2, W+2, n_inputs)."""
         for i, pool in enumerate(self.POOLS):
-            h = getattr(self, f"conv_block{i + 1}").forward_nhwc(h, pool, out_padded_nhwc=(i < 5))
+            # blocks 2..6 read the previous block's pooled output (rounded to TF32 by the pooling kernels whenever
+            # _CUDA_BN_POOL units produced it; the fallback compositions are rounded inside the conv Function)
+            h = getattr(self, f"conv_block{i + 1}").forward_nhwc(h, pool, out_padded_nhwc=(i < 5),
+                                                                  x_rounded=(i > 0 and _CUDA_BN_POOL))
         h = torch.mean(h, dim=2)            # mean across stft bins
         x1, _ = torch.max(h, dim=2)
         x2 = torch.mean(h, dim=2)

@@ -160,6 +160,14 @@ int dmst_conv_repack_weights(const float* w, float* w9, int Cout, int Cin, void*
     dmst::repack_weights_kernel<<<dmst::grid_for(9LL * Cout * Cin), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, w9, Cout, Cin);
     return (int)cudaGetLastError();
 }
+int dmst_conv_round_tf32(const float* src, float* dst, long long n, int B, int H, int W, int C, void* stream) {
+    if (!src || !dst || n <= 0) return DMST_EINVAL;
+    const bool bordered = B > 0;
+    if (bordered && (H <= 0 || W <= 0 || C <= 0 || n != (long long)B * (H + 2) * (W + 2) * C)) return DMST_EINVAL;
+    dmst::round_tf32_kernel<<<dmst::grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        src, dst, n, bordered ? H + 2 : 0, bordered ? W + 2 : 0, C);
+    return (int)cudaGetLastError();
+}
 int dmst_conv_repack_weights_dgrad(const float* w, float* w9t, int Cout, int Cin, void* stream) {
     if (!w || !w9t || Cout <= 0 || Cin <= 0) return DMST_EINVAL;
     dmst::repack_weights_dgrad_kernel<<<dim3((Cin + 31) / 32, (Cout + 31) / 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -317,6 +325,7 @@ int dmst_conv3x3_forward_ws(const float*, const float*, const float*, const floa
 size_t dmst_conv_stats_workspace_bytes(int, int, int, int) { return 0; }
 int dmst_conv_channel_stats(const float*, int, int, int, int, float*, float*, void*, size_t, void*) { return DMST_EINVAL; }
 int dmst_conv_affine_relu(float*, const float*, const float*, int, int, int, int, int, void*) { return DMST_EINVAL; }
+int dmst_conv_round_tf32(const float*, float*, long long, int, int, int, int, void*) { return DMST_EINVAL; }
 int dmst_conv_avgpool(const float*, float*, int, int, int, int, int, int, int, void*) { return DMST_EINVAL; }
 #endif
 

@@ -90,6 +90,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Round-to-nearest conversion to TF32 (cvt.rna: the result is a float32 whose low 13 mantissa bits are zero).
+// tcgen05.mma.kind::tf32 reads float32 bits from shared memory and IGNORES those bits, i.e. it truncates; with
+// structured weights and non-negative activations the truncation errors add coherently over the twelve Cnn14
+// layers (measured on the reference-golden case: first-layer gradient cosine 0.982 truncated, 0.9997 rounded =
+// cuDNN's TF32 convolutions).  Nothing sits between TMA and the MMA, so every kernel that PRODUCES a tensor-core
+// operand rounds it: weight repacks, the ReLU / pooling outputs that feed a convolution, the BatchNorm backward's
+// dz, the layout conversions.
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 tf32_rn4(float4 v) { return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w)); }
+// operands of the tensor-core kernels have channel counts that are multiples of 32 (kConvBK); tensors with other
+// channel counts go to the FP32 CUDA-core kernels and keep full precision
+__host__ __device__ __forceinline__ bool tf32_operand_channels(int C) { return C % 32 == 0; }
+constexpr int kReluBit = 1, kRoundTf32Bit = 2;   // the `relu` argument of the convolution entry points is this mask
+
 struct ConvArgs {
     int P;            // padded pixels = B * Hp * Wp
     int Hp, Wp;       // H + 2, W + 2
@@ -266,7 +284,8 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                 const int n = n0 + c0 + j + q;
                                 if (a.scale) x *= __ldg(a.scale + n);
                                 if (a.shift) x += __ldg(a.shift + n);
-                                if (a.relu) x = fmaxf(x, 0.0f);
+                                if (a.relu & kReluBit) x = fmaxf(x, 0.0f);
+                                if (a.relu & kRoundTf32Bit) x = tf32_rn(x);
                                 vv[q] = interior ? x : 0.0f;
                             }
                             *reinterpret_cast<float4*>(o + j) = v;
@@ -295,7 +314,7 @@ __global__ void nchw_to_padded_nhwc_kernel(const float* x, float* y, int B, int 
         const int b = (int)(r / Hp);
         float v = 0.0f;
         if (hp >= 1 && hp <= H && wp >= 1 && wp <= W) v = __ldg(x + (((long long)b * C + c) * H + (hp - 1)) * W + (wp - 1));
-        y[i] = v;
+        y[i] = tf32_operand_channels(C) ? tf32_rn(v) : v;
     }
 }
 
@@ -317,7 +336,8 @@ __global__ void conv3x3_direct_kernel(const float* x, const float* w9 /*[9][Cout
             }
             if (scale) acc *= __ldg(scale + n);
             if (shift) acc += __ldg(shift + n);
-            if (relu) acc = fmaxf(acc, 0.0f);
+            if (relu & kReluBit) acc = fmaxf(acc, 0.0f);
+            if (relu & kRoundTf32Bit) acc = tf32_rn(acc);
         }
         y[i] = acc;
     }
@@ -365,7 +385,8 @@ __global__ void conv3x3_small_cin_kernel(const float* x, const float* w9 /*[9][C
             const float4 sh = *reinterpret_cast<const float4*>(sm_shift + 4 * g);
             acc.x = fmaf(acc.x, sc.x, sh.x); acc.y = fmaf(acc.y, sc.y, sh.y);
             acc.z = fmaf(acc.z, sc.z, sh.z); acc.w = fmaf(acc.w, sc.w, sh.w);
-            if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+            if (relu & kReluBit) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+            if (relu & kRoundTf32Bit) acc = tf32_rn4(acc);
         }
         *reinterpret_cast<float4*>(y + (long long)p * Cout + 4 * g) = acc;
     }
@@ -402,7 +423,8 @@ __global__ void __launch_bounds__(256) conv3x3_cin1_kernel(const float* __restri
             }
             acc.x = fmaf(acc.x, sc.x, sh.x); acc.y = fmaf(acc.y, sc.y, sh.y);
             acc.z = fmaf(acc.z, sc.z, sh.z); acc.w = fmaf(acc.w, sc.w, sh.w);
-            if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+            if (relu & kReluBit) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+            if (relu & kRoundTf32Bit) acc = tf32_rn4(acc);
         }
         *reinterpret_cast<float4*>(y + (long long)p * Cout + 4 * g) = acc;
     }
@@ -431,7 +453,8 @@ __global__ void avgpool_kernel(const float* x, float* y, int B, int C, int H, in
                     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
                 }
             s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
-            if (out_nhwc_padded) {
+            if (out_nhwc_padded) {   // feeds the next block's convolution
+                if (tf32_operand_channels(C)) s = tf32_rn4(s);
                 *reinterpret_cast<float4*>(y + (((long long)b * (Ho + 2) + ho + 1) * (Wo + 2) + wo + 1) * C + c) = s;
             } else {
                 const long long o = (((long long)b * C + c) * Ho + ho) * Wo + wo, cs = (long long)Ho * Wo;
@@ -457,12 +480,32 @@ __global__ void avgpool_kernel(const float* x, float* y, int B, int C, int H, in
     }
 }
 
+// dst = src rounded to nearest TF32, optionally with the one-pixel border of a [P][C] zero-bordered NHWC tensor
+// cleared (Hp == 0: plain element-wise).  For tensors that reach a tensor-core convolution from outside this library
+// (a user's input, an upstream gradient produced by PyTorch ops).
+__global__ void round_tf32_kernel(const float* src, float* dst, long long n, int Hp, int Wp, int C) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = tf32_rn(__ldg(src + i));
+        if (Hp > 0) {
+            const long long p = i / C;
+            const int rem = (int)(p % ((long long)Hp * Wp));
+            const int hp = rem / Wp, wp = rem - hp * Wp;
+            if (hp == 0 || hp == Hp - 1 || wp == 0 || wp == Wp - 1) v = 0.0f;
+        }
+        dst[i] = v;
+    }
+}
+
 // [Cout][Cin][3][3] -> [9][Cout][Cin]
+// (rounded to TF32 when the tensor-core kernel will read them: conv3x3_forward's dispatch rule)
+__host__ __device__ __forceinline__ bool conv_uses_tensor_cores(int Cin, int Cout) { return Cin % kConvBK == 0 && Cout % 64 == 0; }
 __global__ void repack_weights_kernel(const float* w, float* w9, int Cout, int Cin) {
     const int total = 9 * Cout * Cin;
+    const bool rnd = conv_uses_tensor_cores(Cin, Cout);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int c = i % Cin, n = (i / Cin) % Cout, tap = i / (Cin * Cout);
-        w9[i] = __ldg(w + ((long long)n * Cin + c) * 9 + tap);
+        const float v = __ldg(w + ((long long)n * Cin + c) * 9 + tap);
+        w9[i] = rnd ? tf32_rn(v) : v;
     }
 }
 
@@ -482,8 +525,10 @@ __global__ void repack_weights_dgrad_kernel(const float* w, float* w9t, int Cout
     __syncthreads();
     for (int i = threadIdx.x; i < 9 * 32 * 32; i += blockDim.x) {
         const int co = i & 31, ci = (i >> 5) & 31, tap = i >> 10;
-        if (co0 + co < Cout && ci < nci)
-            w9t[((size_t)(8 - tap) * Cin + ci0 + ci) * Cout + co0 + co] = tile[co][ci * 9 + tap];
+        if (co0 + co < Cout && ci < nci) {   // dgrad runs conv3x3_forward with the channel roles swapped
+            const float v = tile[co][ci * 9 + tap];
+            w9t[((size_t)(8 - tap) * Cin + ci0 + ci) * Cout + co0 + co] = conv_uses_tensor_cores(Cout, Cin) ? tf32_rn(v) : v;
+        }
     }
 }
 
@@ -576,7 +621,8 @@ __global__ void affine_relu_kernel(float* y, int P, int Hp, int Wp, int C, const
         const int hp = rem / Wp, wp = rem - hp * Wp;
         if (hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2) {
             float v = fmaf(y[i], __ldg(scale + c), __ldg(shift + c));
-            y[i] = relu ? fmaxf(v, 0.0f) : v;
+            if (relu & kReluBit) v = fmaxf(v, 0.0f);
+            y[i] = (relu & kRoundTf32Bit) ? tf32_rn(v) : v;
         }
     }
 }
@@ -596,6 +642,7 @@ __global__ void affine_relu_to_kernel(const float* z, float* y, int P, int Hp, i
             const float4 a = __ldg(reinterpret_cast<const float4*>(scale + c)), b = __ldg(reinterpret_cast<const float4*>(shift + c));
             o.x = fmaxf(fmaf(v.x, a.x, b.x), 0.f); o.y = fmaxf(fmaf(v.y, a.y, b.y), 0.f);
             o.z = fmaxf(fmaf(v.z, a.z, b.z), 0.f); o.w = fmaxf(fmaf(v.w, a.w, b.w), 0.f);
+            if (tf32_operand_channels(C)) o = tf32_rn4(o);   // y feeds the block's second convolution
         }
         *reinterpret_cast<float4*>(y + (size_t)p * C + c) = o;
     }
@@ -703,6 +750,7 @@ __global__ void bn_relu_bwd_apply_kernel(const float* z, const float* dy, PoolGr
                 r[e] = a[e] * (gr - inv_count * (db[e] + zh * dg[e]));
             }
             o = make_float4(r[0], r[1], r[2], r[3]);
+            if (tf32_operand_channels(C)) o = tf32_rn4(o);   // dz is the dgrad / wgrad operand
         }
         *reinterpret_cast<float4*>(dz + (size_t)p * C + c) = o;
     }
@@ -733,7 +781,8 @@ __global__ void bn_relu_avgpool_kernel(const float* z, const float* scale, const
                 s.z += fmaxf(fmaf(v.z, a.z, sft.z), 0.f); s.w += fmaxf(fmaf(v.w, a.w, sft.w), 0.f);
             }
         s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
-        if (out_nhwc_padded) {
+        if (out_nhwc_padded) {   // feeds the next block's convolution
+            if (tf32_operand_channels(C)) s = tf32_rn4(s);
             *reinterpret_cast<float4*>(y + (((long long)b * (Ho + 2) + ho + 1) * (Wo + 2) + wo + 1) * C + c) = s;
         } else {
             const long long o = (((long long)b * C + c) * Ho + ho) * Wo + wo, cs = (long long)Ho * Wo;
@@ -816,7 +865,8 @@ __global__ void conv_splitk_reduce_kernel(const float* partial, int ksplit, floa
             }
             if (scale) { const float4 q = __ldg(reinterpret_cast<const float4*>(scale + c)); s.x *= q.x; s.y *= q.y; s.z *= q.z; s.w *= q.w; }
             if (shift) { const float4 q = __ldg(reinterpret_cast<const float4*>(shift + c)); s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w; }
-            if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+            if (relu & kReluBit) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+            if (relu & kRoundTf32Bit) s = tf32_rn4(s);
         }
         *reinterpret_cast<float4*>(y + (size_t)p * C + c) = s;
     }

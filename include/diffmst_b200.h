@@ -163,8 +163,20 @@ int dmst_peak_normalize(const float* x, long long batch_stride, long long ch_str
                         int B, int T, void* stream);
 
 /* ---- Cnn14 ConvBlock on the tensor cores (mst/panns.py:27-85: conv3x3 -> BatchNorm -> ReLU, twice,
- *      then average pooling; forward only in this round).  Activations between these calls are
- *      NHWC float32 with a one-pixel zero border: (B, H+2, W+2, C). ---- */
+ *      then average pooling).  Activations between these calls are NHWC float32 with a one-pixel zero
+ *      border: (B, H+2, W+2, C).
+ *
+ *      TF32 operand contract.  The tensor core reads float32 bits and ignores the low 13 mantissa bits
+ *      (truncation), so operands of the tensor-core entry points (dmst_conv3x3_forward[_ws] with Cin % 32 == 0
+ *      and Cout % 64 == 0, dmst_conv3x3_wgrad) should already be rounded to nearest TF32 - as cuDNN's TF32
+ *      convolutions (the reference's numerics, torch's default) do internally.  Every entry point below that
+ *      PRODUCES such an operand rounds it (cvt.rna.tf32.f32): the weight repacks, dmst_conv_nchw_to_padded_nhwc,
+ *      dmst_conv_affine_relu_to, dmst_conv_bn_relu_avgpool / dmst_conv_avgpool with padded NHWC output, the dz of
+ *      the BatchNorm backward (all when the channel count is a multiple of 32), and the convolution / affine
+ *      epilogues when bit 1 of `relu` is set.  dmst_conv_round_tf32 is for tensors that come from elsewhere. ---- */
+/* dst = src rounded to nearest TF32 (n elements; in place allowed).  With B > 0 the tensor is a zero-bordered NHWC
+ * (B, H+2, W+2, C) and its border is cleared as well; B == 0: plain element-wise. */
+int dmst_conv_round_tf32(const float* src, float* dst, long long n, int B, int H, int W, int C, void* stream);
 int dmst_conv_nchw_to_padded_nhwc(const float* x, float* y, int B, int C, int H, int W, void* stream);
 /* nn.Conv2d weight (Cout, Cin, 3, 3) -> (9, Cout, Cin) */
 int dmst_conv_repack_weights(const float* w, float* w9, int Cout, int Cin, void* stream);
@@ -172,7 +184,8 @@ int dmst_conv_repack_weights(const float* w, float* w9, int Cout, int Cin, void*
  * dL/dx = dmst_conv3x3_forward(dL/dz, w9t) with the channel counts swapped */
 int dmst_conv_repack_weights_dgrad(const float* w, float* w9t, int Cout, int Cin, void* stream);
 /* y = [relu](conv3x3(x) * scale[c] + shift[c]); scale/shift may be NULL (1 / 0).  TF32 tensor-core
- * path (tcgen05 + TMA) when Cin % 32 == 0 and Cout % 64 == 0, CUDA-core path otherwise (first layer). */
+ * path (tcgen05 + TMA) when Cin % 32 == 0 and Cout % 64 == 0, CUDA-core path otherwise (first layer).
+ * `relu` is a mask: bit 0 = apply ReLU, bit 1 = round the output to TF32 (it feeds another convolution). */
 int dmst_conv3x3_forward(const float* x_padded, const float* w9, const float* scale, const float* shift,
                          float* y_padded, int B, int H, int W, int Cin, int Cout, int relu, void* stream);
 /* training-mode BatchNorm: batch mean and biased variance per channel of a raw conv output */

@@ -281,8 +281,9 @@ def test_encoder_matches_reference_golden(golden):
     mst.panns.Cnn14 in float64 with the generator-free parameter fill, and the spectrogram lines of
     mst.modules.SpectrogramEncoder.forward).  The case is well conditioned - the reference algorithm with its
     operands rounded to TF32 on the CPU is 8.6e-5 from the golden output, cosine 0.99960 / 0.99998 for the first-layer
-    / head gradients - so the bounds below are the convolution tolerance and about 10x those gradient distances (the
-    tensor core's own TF32 conversion need not be the round-to-nearest of that emulation)."""
+    / head gradients - so the bounds below are the convolution tolerance and about 3x those gradient distances.  Every
+    producer of a tensor-core operand rounds it to nearest TF32 (csrc/conv_tc.cuh: tf32_rn); the tensor core itself
+    truncates, which on this structured case put the first-layer gradient at cosine 0.982."""
     import os, sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
     from panns_fill import fill_state
@@ -302,7 +303,10 @@ def test_encoder_matches_reference_golden(golden):
     cos = lambda a, b: float(torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0))
     c_first = cos(net.conv_block1.conv1.weight.grad, torch.from_numpy(d["cnn14_g_first"]).cuda())
     c_fc = cos(net.fc.weight.grad, torch.from_numpy(d["cnn14_g_fc"]).cuda())
-    assert c_first >= 0.995 and c_fc >= 0.9995, (c_first, c_fc)
+    # measured with operands rounded to nearest TF32 (tests/tools/cnn14_tf32_diag.py, profiles/cnn14_tf32_diag_r2.txt):
+    # 1 - cosine = 3.9e-4 / 2.4e-5, cuDNN's TF32 convolutions on the same case 3.0e-4 / 2.3e-5; with the operands
+    # truncated (what the tensor core does to unrounded float32 bits) it was 1.8e-2 / 1.6e-4
+    assert c_first >= 0.999 and c_fc >= 0.9999, (c_first, c_fc)
     enc = SpectrogramEncoder(embed_dim=8).cuda().eval()
     S = enc._frontend(torch.from_numpy(d["spec_wave"]).cuda())[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)
     assert S.shape == d["spec_out"].shape
