@@ -56,6 +56,8 @@ def lib():
     l.dmst_console_backward.restype = i
     l.dmst_console_backward.argtypes = [vp, ll, ll, vp, vp, ctypes.POINTER(Ranges), f, i, i, i, u, i, i,
                                         vp, vp, vp, vp, vp, vp, sz, vp]
+    l.dmst_console_check_ranges.restype = i
+    l.dmst_console_check_ranges.argtypes = [vp, i, i, i, vp, vp]
     l.dmst_mrstft_workspace_bytes.restype = sz
     l.dmst_mrstft_workspace_bytes.argtypes = [ctypes.POINTER(MrstftCfg), i, i]
     l.dmst_mrstft_forward.restype = i

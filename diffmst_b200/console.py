@@ -91,6 +91,7 @@ class _ConsoleFunction(torch.autograd.Function):
         ctx.ws, ctx.nbytes, ctx.ranges = ws, nbytes, ranges
         ctx.cfg = (float(sample_rate), flags, la_t, la_m)
         ctx.mark_non_differentiable(status)
+        ctx.set_materialize_grads(False)   # an unused mixed_tracks output must not cost a (B,2,N,T) zero tensor
         if mixed is None:
             mixed = torch.empty(0, device=dev)
         return mix, mixed, status
@@ -193,9 +194,15 @@ class AdvancedMixConsole(torch.nn.Module):
         self.num_master_bus_control_params = 26
         # Not part of the upstream interface: set False to skip materialising the
         # (bs, 2, num_tracks, seq_len) tensor that forward returns first (an empty tensor is
-        # returned instead); set check_ranges False to skip the device sync of the range test.
+        # returned instead).
         self.materialize_tracks = True
+        # Range test of mst/modules.py:86-89.  True: as upstream, the ValueError is raised inside the call (one
+        # host sync per call instead of 156).  "async": the test runs on the device inside the console's own
+        # prepare kernel (plus one tiny launch for the fx-bus block), the verdict is copied to pinned host memory
+        # without synchronising, and the ValueError is raised by the first later forward() that finds it, or by
+        # check_pending_ranges(); CUDA-graph capturable.  False: no test.
         self.check_ranges = True
+        self._pending_ranges = []   # [(pinned int32 host tensor, event or None)]
 
     # ---- parameter plumbing (mst/modules.py:353-466) ----
     def _track_ranges(self):
@@ -285,20 +292,99 @@ class AdvancedMixConsole(torch.nn.Module):
                 if lo[i] < 0 or hi[i] > 1:
                     raise ValueError(f"Parameter {name} of effect {effect} is out of range.")
 
+    # ---- asynchronous range test (check_ranges = "async") ----
+    _TRACK_NAMES = [("input_fader", "gain_db")] + [("parametric_eq", k) for k in EQ_KEYS] + \
+        [("compressor", k) for k in COMP_KEYS] + [("stereo_panner", "pan"), ("fx_bus", "send_db")]
+    _FX_NAMES = [("reverberation", f"band{i}_gain") for i in range(12)] + \
+        [("reverberation", f"band{i}_decay") for i in range(12)] + [("reverberation", "mix")]
+    _MASTER_NAMES = [("parametric_eq", k) for k in EQ_KEYS] + [("compressor", k) for k in COMP_KEYS] + \
+        [("output_fader", "gain_db"), ("input_fader", "gain_db")]
+
+    @classmethod
+    def _status_error(cls, code: int):
+        """Device status word (include/diffmst_b200.h) -> the reference's ValueError, or None."""
+        if code == _lib.STATUS_OK or code <= 0:
+            return None
+        if code > 1000:
+            effect, name = cls._MASTER_NAMES[code - 1001]
+        elif code > 500:
+            effect, name = cls._FX_NAMES[code - 501]
+        else:
+            effect, name = cls._TRACK_NAMES[code - 1]
+        return ValueError(f"Parameter {name} of effect {effect} is out of range.")
+
+    def _queue_range_status(self, status, fx_bus_params):
+        lib = _lib.lib()
+        dev = status.device
+        capturing = torch.cuda.is_current_stream_capturing()
+        with torch.cuda.device(dev):
+            if fx_bus_params is not None and fx_bus_params.numel():
+                # 24 tested columns: upstream forces "mix" (column 24) to ones before the test (mst/modules.py:420)
+                fx = fx_bus_params.detach().reshape(-1, fx_bus_params.shape[-1])[:, :24].contiguous()
+                _lib.check(lib.dmst_console_check_ranges(_ptr(fx), fx.shape[0], fx.shape[1], 500, _ptr(status),
+                                                         ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                           "dmst_console_check_ranges")
+            host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+            host.fill_(_lib.STATUS_OK)
+            host.copy_(status[:1], non_blocking=True)
+            ev = None
+            if not capturing:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+        self._pending_ranges.append((host, ev))
+        if len(self._pending_ranges) > 64:   # bounded: the oldest verdicts have long landed
+            self.check_pending_ranges(wait=False)
+            if len(self._pending_ranges) > 64:
+                self.check_pending_ranges(wait=True)
+
+    def check_pending_ranges(self, wait: bool = True):
+        """Raise the reference's ValueError (mst/modules.py:86-89) for the oldest earlier forward() whose parameters
+        were out of range (check_ranges="async").  wait=True synchronises with the device first; wait=False looks only
+        at verdicts that have already landed in host memory."""
+        if wait and self._pending_ranges:
+            torch.cuda.synchronize()
+        keep, err = [], None
+        for host, ev in self._pending_ranges:
+            # ev is None: recorded during CUDA-graph capture; every replay rewrites that host word, so the entry
+            # (and its pinned buffer) lives as long as the console and is only read after a synchronisation
+            done = wait or (ev is not None and ev.query())
+            if ev is None or not done:
+                keep.append((host, ev))
+            if done and err is None:
+                err = self._status_error(int(host[0]))
+                if ev is None:
+                    host.fill_(_lib.STATUS_OK)
+        self._pending_ranges = keep
+        if err is not None:
+            self._pending_ranges = [e for e in keep if e[1] is None]
+            raise err
+
     # ---- the chain (mst/modules.py:186-314) ----
-    def _run(self, tracks, track_params_norm, master_params_norm, flags):
-        mix, mixed, _ = _ConsoleFunction.apply(
-            tracks, track_params_norm, master_params_norm, self._c_ranges(), self.sample_rate, flags,
-            TRACK_LOOKAHEAD, MASTER_LOOKAHEAD, self.materialize_tracks)
+    def _run(self, tracks, track_params_norm, master_params_norm, flags, ranges=None, fx_bus_params=None):
+        mix, mixed, status = _ConsoleFunction.apply(
+            tracks, track_params_norm, master_params_norm, ranges if ranges is not None else self._c_ranges(),
+            self.sample_rate, flags, TRACK_LOOKAHEAD, MASTER_LOOKAHEAD, self.materialize_tracks)
+        if self.check_ranges == "async" and ranges is None:
+            self._queue_range_status(status, fx_bus_params)
         return mixed, mix
 
     @staticmethod
-    def _normalize_dict(denorm_dict, ranges, keys):
+    def _identity_ranges():
+        r = _lib.Ranges()
+        for i in range(_lib.NUM_TRACK_PARAMS):
+            r.track_lo[i], r.track_hi[i] = 0.0, 1.0
+        for i in range(_lib.NUM_MASTER_PARAMS):
+            r.master_lo[i], r.master_hi[i] = 0.0, 1.0
+        return r
+
+    @staticmethod
+    def _stack_dict(denorm_dict, keys, like):
         cols = []
         for effect, name in keys:
-            lo, hi = ranges[effect][name]
-            cols.append((denorm_dict[effect][name] - lo) / (hi - lo))
-        return torch.stack(cols, dim=-1)
+            v = denorm_dict[effect][name]
+            cols.append(v if torch.is_tensor(v) else torch.as_tensor(v, dtype=like.dtype, device=like.device))
+        cols = torch.broadcast_tensors(*cols)
+        return torch.stack(cols, dim=-1).to(like.dtype)
 
     def forward_mix_console(
         self,
@@ -315,18 +401,16 @@ class AdvancedMixConsole(torch.nn.Module):
         use_output_fader: bool = True,
     ):
         """Same contract as mst/modules.py:186-314: takes DENORMALISED parameter dicts and
-        returns (tracks (bs, 2, num_tracks, seq_len), master_bus (bs, 2, seq_len)).  The
-        kernels consume normalised parameters, so the dicts are mapped back with the inverse
-        affine (exact up to float32 rounding)."""
+        returns (tracks (bs, 2, num_tracks, seq_len), master_bus (bs, 2, seq_len)).  As upstream, the values are
+        applied as given: no range test and no clamping (mst/mixing.py's knowledge-engineering mix passes values
+        outside ``param_ranges``).  The kernels denormalise `p * (hi - lo) + lo` in float64 themselves, so the
+        denormalised values go to them with the identity range (lo, hi) = (0, 1): exact, and gradients arrive with
+        respect to the dictionary entries."""
         flags = _flags(use_track_input_fader, use_track_eq, use_track_compressor, use_track_panner,
                        use_fx_bus, use_master_bus, use_output_fader)
-        tkeys = [("input_fader", "gain_db")] + [("parametric_eq", k) for k in EQ_KEYS] + \
-            [("compressor", k) for k in COMP_KEYS] + [("stereo_panner", "pan"), ("fx_bus", "send_db")]
-        mkeys = [("parametric_eq", k) for k in EQ_KEYS] + [("compressor", k) for k in COMP_KEYS] + \
-            [("output_fader", "gain_db"), ("input_fader", "gain_db")]
-        tp = self._normalize_dict(track_param_dict, self.param_ranges, tkeys).clamp(0, 1)
-        mp = self._normalize_dict(master_bus_param_dict, self.param_ranges, mkeys).clamp(0, 1)
-        return self._run(tracks, tp, mp, flags)
+        tp = self._stack_dict(track_param_dict, self._TRACK_NAMES, tracks)
+        mp = self._stack_dict(master_bus_param_dict, self._MASTER_NAMES, tracks)
+        return self._run(tracks, tp, mp, flags, ranges=self._identity_ranges())
 
     def forward(
         self,
@@ -345,7 +429,9 @@ class AdvancedMixConsole(torch.nn.Module):
         """Create a mix from tracks and mixing parameters in (0, 1); mst/modules.py:316-487."""
         flags = _flags(use_track_input_fader, use_track_eq, use_track_compressor, use_track_panner,
                        use_fx_bus, use_master_bus, use_output_fader)
-        if self.check_ranges:
+        if self.check_ranges == "async":
+            self.check_pending_ranges(wait=False)   # verdicts of earlier calls that have landed
+        elif self.check_ranges:
             self._raise_if_out_of_range(track_params, fx_bus_params, master_bus_params)
         # two elementwise kernels per tensor instead of two per dictionary entry (156 upstream)
         track_param_dict = self._denormalize_batched(track_params, self._track_ranges(), self._split_track)
@@ -355,7 +441,7 @@ class AdvancedMixConsole(torch.nn.Module):
         fx_bus_param_dict = self._denormalize_batched(fx_bus_params, fx_ranges, self._split_fx)
         master_bus_param_dict = self._denormalize_batched(master_bus_params, self._master_ranges(),
                                                           self._split_master)
-        mixed_tracks, mix = self._run(tracks, track_params, master_bus_params, flags)
+        mixed_tracks, mix = self._run(tracks, track_params, master_bus_params, flags, fx_bus_params=fx_bus_params)
         return mixed_tracks, mix, track_param_dict, fx_bus_param_dict, master_bus_param_dict
 
 

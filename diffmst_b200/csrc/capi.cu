@@ -44,6 +44,23 @@ int dmst_console_backward(const float* tracks, long long tracks_batch_stride, lo
                                   reinterpret_cast<cudaStream_t>(stream));
 }
 
+// status[0] = min(status[0], base + 1 + column) over the entries of params (rows x np) outside [0, 1]
+__global__ void range_check_kernel(const float* params, long long n, int np, int base, int* status) {
+    int bad = 0x7fffffff;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = params[i];
+        if (v < 0.0f || v > 1.0f) bad = min(bad, base + 1 + (int)(i % np));
+    }
+    if (bad != 0x7fffffff) atomicMin(status, bad);
+}
+int dmst_console_check_ranges(const float* params, int rows, int np, int base, int* status, void* stream) {
+    if (!params || !status || rows <= 0 || np <= 0) return DMST_EINVAL;
+    const long long n = (long long)rows * np;
+    const int blocks = (int)((n + 255) / 256 > 64 ? 64 : (n + 255) / 256);
+    DMST_LAUNCH(range_check_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), params, n, np, base, status);
+    return DMST_LAST_ERROR();
+}
+
 int dmst_profile_enable(int max_records) {
 #ifndef DMST_EMULATE
     dmst::Profiler& p = dmst::profiler();

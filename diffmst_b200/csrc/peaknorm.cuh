@@ -12,15 +12,18 @@ __global__ void peak_scale_kernel(const float* x, long long bs, long long cs, fl
     const int b = blockIdx.y;
     const float* L = x + (long long)b * bs;
     const float* R = L + cs;
+    // NaN-propagating maximum, as torch.max / torch.clamp in the reference: one NaN sample makes the whole item NaN
+    // (mst/system.py:251-253 relies on that to raise "Found nan in ref_mix"); fmaxf would drop it
+    auto nmax = [](float m, float a) { return (a > m || a != a) ? a : m; };
     float m = 0.0f;
-    for (int t = threadIdx.x; t < T; t += blockDim.x) m = fmaxf(m, fmaxf(fabsf(__ldg(L + t)), fabsf(__ldg(R + t))));
+    for (int t = threadIdx.x; t < T; t += blockDim.x) m = nmax(nmax(m, fabsf(__ldg(L + t))), fabsf(__ldg(R + t)));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int o = 16; o > 0; o >>= 1) m = nmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sh[w]);
-        sh[32] = fmaxf(m, 1e-8f);
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = nmax(m, sh[w]);
+        sh[32] = m < 1e-8f ? 1e-8f : m;
     }
     __syncthreads();
     const float g = sh[32];

@@ -41,7 +41,13 @@ class _MrstftFunction(torch.autograd.Function):
             raise ValueError(f"input {tuple(x.shape)} and target {tuple(y.shape)} differ in shape")
         xv, rows, T, xs = _rows_view(x)
         yv, _, _, ys = _rows_view(y)
-        need_grad = ctx.needs_input_grad[0]
+        if ctx.needs_input_grad[1]:
+            # auraloss differentiates both arguments; the reference only ever passes a detached target
+            # (mst/system.py:232-258: the reference mix comes out of torch.no_grad()).  Refuse rather than return a
+            # silent zero gradient.
+            raise NotImplementedError("MultiResolutionSTFTLoss: a target that requires grad is not supported; "
+                                      "detach it (the reference's target is a no-grad reference mix)")
+        need_grad = ctx.needs_input_grad[0]   # False under torch.no_grad(): the gradient pass is skipped
         dev = x.device
         with torch.cuda.device(dev):
             nbytes = lib.dmst_mrstft_workspace_bytes(ctypes.byref(cfg), rows, T)

@@ -100,6 +100,13 @@ int dmst_console_backward(const float* tracks, long long tracks_batch_stride,
                           float* grad_master_params, float* grad_tracks, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Range check of any other normalised parameter block on the device (the fx-bus parameters of
+ * mst/modules.py:462-466, which the kernels do not consume): status[0] = min(status[0], base + 1 + column) over
+ * the entries of params (rows x np) outside [0, 1].  `status` must have been initialised by dmst_console_forward
+ * of the same call (or hold 0x7f7f7f7f).  Convention: fx-bus block base = 500 (track 0, master 1000), so that the
+ * smallest code is the reference's first offender in its traversal order (track, fx bus, master bus). */
+int dmst_console_check_ranges(const float* params, int rows, int np, int base, int* status, void* stream);
+
 /* ---- measurement hooks (used by bench.py only) ----
  * dmst_profile_enable(n > 0): from now on every console chain-kernel launch is bracketed by a
  * pair of CUDA events on its stream (at most n per kernel kind); n <= 0 disables.

@@ -1,0 +1,200 @@
+"""Parity at the shapes the benchmark numbers are quoted on (BASELINE.json configs[1] and configs[4]; VERDICT r1
+item 2): the CUDA path through the C ABI against the float64 oracle at T = 262 144 (32 chained track tiles, 64
+master tiles) and against the exact time-domain recursion at T = 1 048 576 (128 tiles), where error growth along
+the tile-to-tile chain would show.
+
+Protocol: forward <= 1e-4 relative to the largest value, gradients <= 1e-3 relative L2, or
+1.5 x the distance of the reference algorithm's own float32 evaluation from its float64 evaluation on the same
+inputs where that is larger."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.auraloss.freq import MultiResolutionSTFTLoss as OracleMRSTFT
+from oracle.console import OracleAdvancedMixConsole, EQ_KEYS, COMP_KEYS
+from oracle.loss import batch_stereo_peak_normalize as oracle_peak_normalize
+
+pytestmark = pytest.mark.gpu
+SR = 44100
+RES = dict(fft_sizes=[512, 2048, 8192], hop_sizes=[256, 1024, 4096], win_lengths=[512, 2048, 8192])
+FLAGS = dict(use_track_input_fader=True, use_track_eq=True, use_track_compressor=True, use_track_panner=True,
+             use_master_bus=True, use_fx_bus=False, use_output_fader=True)
+
+
+def relmax(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def rell2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _inputs(B, N, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    tracks = torch.randn(B, N, T, generator=g) * 0.1
+    tp, fp, mp = torch.rand(B, N, 27, generator=g), torch.rand(B, 25, generator=g), torch.rand(B, 26, generator=g)
+    tp2, mp2 = torch.rand(B, N, 27, generator=g), torch.rand(B, 26, generator=g)
+    return tracks, tp, fp, mp, tp2, mp2
+
+
+def _oracle_step(inputs, dtype):
+    tracks, tp, fp, mp, tp2, mp2 = (t.to(dtype) for t in inputs)
+    con = OracleAdvancedMixConsole(SR)
+    loss_fn = OracleMRSTFT(**RES)
+    with torch.no_grad():
+        target = oracle_peak_normalize(con(tracks, tp2, fp, mp2, **FLAGS)[1])
+    tp = tp.clone().requires_grad_(True); mp = mp.clone().requires_grad_(True)
+    mixed, mix = con(tracks, tp, fp, mp, **FLAGS)[:2]
+    loss = loss_fn(mix, target)
+    loss.backward()
+    return dict(mix=mix.detach().numpy(), mixed=mixed.detach().numpy(), loss=float(loss.detach()),
+                gtp=tp.grad.numpy(), gmp=mp.grad.numpy(), target=target.numpy())
+
+
+def _our_step(inputs, materialize):
+    from diffmst_b200 import AdvancedMixConsole, MRSTFTLoss, batch_stereo_peak_normalize
+    tracks, tp, fp, mp, tp2, mp2 = (t.cuda() for t in inputs)
+    con = AdvancedMixConsole(SR).cuda()
+    con.materialize_tracks = materialize
+    loss_fn = MRSTFTLoss(**RES)
+    with torch.no_grad():
+        target = batch_stereo_peak_normalize(con(tracks, tp2, fp, mp2, **FLAGS)[1])
+    tp = tp.clone().requires_grad_(True); mp = mp.clone().requires_grad_(True)
+    mixed, mix = con(tracks, tp, fp, mp, **FLAGS)[:2]
+    loss = loss_fn(mix, target)
+    loss.backward()
+    return dict(mix=mix.detach().cpu().numpy(), mixed=mixed.detach().cpu().numpy(), loss=float(loss.detach()),
+                gtp=tp.grad.cpu().numpy(), gmp=mp.grad.cpu().numpy(), target=target.cpu().numpy())
+
+
+@pytest.fixture(scope="module")
+def headline():
+    """One item of BASELINE configs[1] (16 tracks x 262 144 samples, training flags, MRSTFT against a random
+    peak-normalised reference mix): the float64 and float32 oracle evaluations, shared by the tests below."""
+    inputs = _inputs(1, 16, 262144, seed=2026)
+    o64 = _oracle_step(inputs, torch.float64)
+    o32 = _oracle_step(inputs, torch.float32)
+    return inputs, o64, o32
+
+
+def test_headline_step_bus_only_matches_float64_oracle(headline):
+    """The mode bench.py's `value` runs (materialize_tracks=False): mix, loss, both parameter gradients."""
+    inputs, o64, o32 = headline
+    ours = _our_step(inputs, materialize=False)
+    assert ours["mixed"].size == 0
+    b = 1.5 * max(1e-4, relmax(o32["target"], o64["target"]))
+    assert relmax(ours["target"], o64["target"]) <= b, ("target", relmax(ours["target"], o64["target"]), b)
+    b = 1.5 * max(1e-4, relmax(o32["mix"], o64["mix"]))
+    assert relmax(ours["mix"], o64["mix"]) <= b, ("mix", relmax(ours["mix"], o64["mix"]), b)
+    bl = max(1e-4, 1.5 * abs(o32["loss"] - o64["loss"]) / abs(o64["loss"]))
+    assert abs(ours["loss"] - o64["loss"]) <= bl * abs(o64["loss"]), (ours["loss"], o64["loss"], o32["loss"])
+    for key in ("gtp", "gmp"):
+        bg = max(1e-3, 1.5 * rell2(o32[key], o64[key]))
+        assert np.isfinite(ours[key]).all()
+        assert rell2(ours[key], o64[key]) <= bg, (key, rell2(ours[key], o64[key]), bg)
+    print("headline parity (ours vs f64 | reference-f32 vs f64): mix %.2e | %.2e, loss %.2e | %.2e, gtp %.2e | %.2e, gmp %.2e | %.2e" % (
+        relmax(ours["mix"], o64["mix"]), relmax(o32["mix"], o64["mix"]),
+        abs(ours["loss"] - o64["loss"]) / abs(o64["loss"]), abs(o32["loss"] - o64["loss"]) / abs(o64["loss"]),
+        rell2(ours["gtp"], o64["gtp"]), rell2(o32["gtp"], o64["gtp"]), rell2(ours["gmp"], o64["gmp"]), rell2(o32["gmp"], o64["gmp"])))
+
+
+def test_headline_step_full_contract_matches_float64_oracle(headline):
+    """The reference's full return contract (mixed_tracks (B,2,N,T), mst/modules.py:314) at T = 262 144: every
+    panned track against float64, and the step's numbers bit-identical to the bus-only mode."""
+    inputs, o64, o32 = headline
+    ours = _our_step(inputs, materialize=True)
+    lean = _our_step(inputs, materialize=False)
+    assert ours["mixed"].shape == (1, 2, 16, 262144)
+    for n in range(16):
+        b = 1.5 * max(1e-4, relmax(o32["mixed"][0, :, n], o64["mixed"][0, :, n]))
+        assert relmax(ours["mixed"][0, :, n], o64["mixed"][0, :, n]) <= b, (n, relmax(ours["mixed"][0, :, n], o64["mixed"][0, :, n]), b)
+    assert np.array_equal(ours["mix"], lean["mix"]) and ours["loss"] == lean["loss"]
+    assert np.array_equal(ours["gtp"], lean["gtp"]) and np.array_equal(ours["gmp"], lean["gmp"])
+
+
+def test_million_sample_track_matches_time_domain_recursion():
+    """BASELINE configs[4] corner: 1 track x 1 048 576 samples (128 chained tiles) through EQ + compressor + pan +
+    master bus, against the exact float64 recursion (oracle/timedomain.py, scipy lfilter): error must not grow along
+    the chain.  Compared per 65 536-sample segment so that growth would be visible."""
+    from oracle import timedomain as td
+    from diffmst_b200 import AdvancedMixConsole
+    g = torch.Generator().manual_seed(77)
+    N, T = 1, 1048576
+    tracks = torch.randn(1, N, T, generator=g) * 0.1
+    tp, fp, mp = torch.rand(1, N, 27, generator=g), torch.rand(1, 25, generator=g), torch.rand(1, 26, generator=g)
+    con = AdvancedMixConsole(SR).cuda()
+    with torch.no_grad():
+        mixed, mix, tpd, _, mpd = con(tracks.cuda(), tp.cuda(), fp.cuda(), mp.cuda(), **FLAGS)
+    tpn = np.zeros((N, 27)); mpn = np.zeros(26)
+    tpn[:, 0] = tpd["input_fader"]["gain_db"][0].cpu().numpy()
+    for i, k in enumerate(EQ_KEYS):
+        tpn[:, 1 + i] = tpd["parametric_eq"][k][0].cpu().numpy(); mpn[i] = float(mpd["parametric_eq"][k][0])
+    for i, k in enumerate(COMP_KEYS):
+        tpn[:, 19 + i] = tpd["compressor"][k][0].cpu().numpy(); mpn[18 + i] = float(mpd["compressor"][k][0])
+    tpn[:, 25] = tpd["stereo_panner"]["pan"][0].cpu().numpy()
+    mpn[24] = float(mpd["output_fader"]["gain_db"][0]); mpn[25] = float(mpd["input_fader"]["gain_db"][0])
+    want_mixed, want_mix = td.console(tracks[0].numpy().astype(np.float64), tpn, mpn, SR)
+    got_mix, got_mixed = mix[0].cpu().numpy(), mixed[0].cpu().numpy()
+    scale = np.abs(want_mix).max()
+    seg = 65536
+    errs = [float(np.abs(got_mix[:, s:s + seg] - want_mix[:, s:s + seg]).max() / scale) for s in range(0, T, seg)]
+    assert max(errs) <= 2e-4, errs
+    assert max(errs[8:]) <= 3 * max(max(errs[:8]), 2e-5), errs   # no growth along the 128-tile chain
+    assert relmax(got_mixed, want_mixed) <= 2e-4
+
+
+def test_async_range_check_and_forward_mix_console_without_clamp():
+    """check_ranges="async": the verdict is computed on the device, no synchronisation inside forward(), the
+    reference's ValueError (mst/modules.py:86-89) surfaces at check_pending_ranges() / a later call.
+    forward_mix_console applies denormalised values as given, like upstream (no clamp): a cutoff outside
+    param_ranges changes the audio and matches the float64 oracle."""
+    from diffmst_b200 import AdvancedMixConsole
+    con = AdvancedMixConsole(SR).cuda()
+    con.check_ranges = "async"
+    g = torch.Generator().manual_seed(4)
+    B, N, T = 1, 2, 40000
+    x = (torch.randn(B, N, T, generator=g) * 0.1)
+    tp, fp, mp = torch.rand(B, N, 27, generator=g), torch.rand(B, 25, generator=g), torch.rand(B, 26, generator=g)
+    out = con(x.cuda(), tp.cuda(), fp.cuda(), mp.cuda(), use_fx_bus=False)
+    con.check_pending_ranges()                      # in range: nothing raised
+    bad_fx = fp.clone(); bad_fx[0, 13] = 1.25       # second traversal block of the reference (fx bus)
+    bad_mp = mp.clone(); bad_mp[0, 24] = -0.5
+    con(x.cuda(), tp.cuda(), bad_fx.cuda(), bad_mp.cuda(), use_fx_bus=False)   # returns without raising
+    with pytest.raises(ValueError, match="Parameter band1_decay of effect reverberation is out of range."):
+        con.check_pending_ranges()
+    con.check_pending_ranges()                      # the verdict was consumed
+    bad_tp = tp.clone(); bad_tp[0, 1, 25] = 2.0
+    con(x.cuda(), bad_tp.cuda(), fp.cuda(), bad_mp.cuda(), use_fx_bus=False)
+    with pytest.raises(ValueError, match="Parameter pan of effect stereo_panner is out of range."):
+        con.check_pending_ranges()
+    # denormalised dictionaries with an out-of-range cutoff (sr/2 - 1, as mst/mixing.py's rule-based mix produces)
+    tpd, fxd, mpd = out[2], out[3], out[4]
+    tpd["parametric_eq"]["high_shelf_cutoff_freq"] = torch.full_like(tpd["parametric_eq"]["high_shelf_cutoff_freq"], SR / 2 - 1.0)
+    tpd["input_fader"]["gain_db"] = tpd["input_fader"]["gain_db"] + 60.0     # beyond +48 dB
+    with torch.no_grad():
+        got = con.forward_mix_console(x.cuda(), tpd, fxd, mpd, True, True, True, True, False, True, True)[1].cpu().numpy()
+    orc = OracleAdvancedMixConsole(SR)
+    to64 = lambda d: {e: {k: v.detach().cpu().double() for k, v in p.items()} for e, p in d.items()}
+    want = orc.forward_mix_console(x.double(), to64(tpd), to64(fxd), to64(mpd), True, True, True, True, False, True, True)[1].numpy()
+    want32 = orc.forward_mix_console(x, {e: {k: v.float() for k, v in p.items()} for e, p in to64(tpd).items()},
+                                     {e: {k: v.float() for k, v in p.items()} for e, p in to64(fxd).items()},
+                                     {e: {k: v.float() for k, v in p.items()} for e, p in to64(mpd).items()},
+                                     True, True, True, True, False, True, True)[1].numpy()
+    assert relmax(got, want) <= 1.5 * max(1e-4, relmax(want32, want)), (relmax(got, want), relmax(want32, want))
+
+
+def test_peak_normalize_propagates_nan_and_mrstft_refuses_target_grad():
+    from diffmst_b200 import MRSTFTLoss, batch_stereo_peak_normalize
+    x = (torch.randn(2, 2, 5000, generator=torch.Generator().manual_seed(1)) * 0.1).cuda()
+    x[1, 0, 1234] = float("nan")
+    y = batch_stereo_peak_normalize(x)
+    assert torch.isfinite(y[0]).all() and torch.isnan(y[1]).all()   # torch.max / clamp semantics of mst/utils.py:14-29
+    loss_fn = MRSTFTLoss(**RES)
+    a = (torch.randn(1, 2, 20000) * 0.1).cuda().requires_grad_(True)
+    b = (torch.randn(1, 2, 20000) * 0.1).cuda().requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="target"):
+        loss_fn(a, b)
+    with torch.no_grad():
+        assert torch.isfinite(loss_fn(a, b))
