@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libdiffmst_b200.so")
 NUM_TRACK_PARAMS, NUM_FX_PARAMS, NUM_MASTER_PARAMS = 27, 25, 26
 USE_TRACK_INPUT_FADER, USE_TRACK_EQ, USE_TRACK_COMPRESSOR, USE_TRACK_PANNER = 1, 2, 4, 8
 USE_MASTER_BUS, USE_FX_BUS, USE_OUTPUT_FADER = 16, 32, 64
-WANT_MIXED_TRACKS, WANT_GRAD_TRACKS, BASIC_CONSOLE = 128, 256, 512
+WANT_MIXED_TRACKS, WANT_GRAD_TRACKS, BASIC_CONSOLE, FORWARD_ONLY = 128, 256, 512, 1024
 EINVAL = -22
 STATUS_OK = 0x7F7F7F7F
 MRSTFT_MAX_RES = 8

@@ -61,7 +61,7 @@ class _ConsoleFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, tracks, track_params, master_params, ranges, sample_rate, flags, la_t, la_m,
-                want_mixed):
+                want_mixed, grad_enabled=True):
         lib = _lib.lib()
         _require_cuda(tracks, "tracks")
         _require_cuda(track_params, "track_params")
@@ -74,6 +74,14 @@ class _ConsoleFunction(torch.autograd.Function):
             master_params = master_params.contiguous()
         dev = tracks.device
         flags = int(flags) | (_lib.WANT_MIXED_TRACKS if want_mixed else 0)
+        # what backward will be asked for shapes what forward keeps: per-section checkpoints only when a gradient
+        # w.r.t. the audio is wanted (the classic adjoint), nothing at all under torch.no_grad() (mst/mixing.py:72)
+        # (needs_input_grad ignores torch.no_grad(); the caller passes the grad mode it was called under)
+        need = [bool(grad_enabled) and n for n in ctx.needs_input_grad[:3]]
+        if need[0]:
+            flags |= _lib.WANT_GRAD_TRACKS
+        if not any(need):
+            flags |= _lib.FORWARD_ONLY
         with torch.cuda.device(dev):
             nbytes = lib.dmst_console_workspace_bytes(B, N, T, flags)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -104,9 +112,7 @@ class _ConsoleFunction(torch.autograd.Function):
         sample_rate, flags, la_t, la_m = ctx.cfg
         B, N, T = tracks.shape
         dev = tracks.device
-        want_gtracks = ctx.needs_input_grad[0]
-        if want_gtracks:
-            flags |= _lib.WANT_GRAD_TRACKS
+        want_gtracks = bool(flags & _lib.WANT_GRAD_TRACKS)
         if gmix is None:
             gmix = torch.zeros(B, 2, T, dtype=torch.float32, device=dev)
         gmix = gmix.contiguous()
@@ -122,7 +128,7 @@ class _ConsoleFunction(torch.autograd.Function):
                 ctypes.byref(ctx.ranges), sample_rate, B, N, T, flags, la_t, la_m, _ptr(gmix), _ptr(gmixed),
                 _ptr(gtp), _ptr(gmp), _ptr(gtr), _ptr(ctx.ws), ctx.nbytes, ctypes.c_void_p(stream))
         _lib.check(rc, "dmst_console_backward")
-        return gtr, gtp, gmp, None, None, None, None, None, None
+        return gtr, gtp, gmp, None, None, None, None, None, None, None
 
 
 def _flags(use_track_input_fader, use_track_eq, use_track_compressor, use_track_panner,
@@ -363,7 +369,7 @@ class AdvancedMixConsole(torch.nn.Module):
     def _run(self, tracks, track_params_norm, master_params_norm, flags, ranges=None, fx_bus_params=None):
         mix, mixed, status = _ConsoleFunction.apply(
             tracks, track_params_norm, master_params_norm, ranges if ranges is not None else self._c_ranges(),
-            self.sample_rate, flags, TRACK_LOOKAHEAD, MASTER_LOOKAHEAD, self.materialize_tracks)
+            self.sample_rate, flags, TRACK_LOOKAHEAD, MASTER_LOOKAHEAD, self.materialize_tracks, torch.is_grad_enabled())
         if self.check_ranges == "async" and ranges is None:
             self._queue_range_status(status, fx_bus_params)
         return mixed, mix
@@ -482,5 +488,5 @@ class BasicMixConsole(torch.nn.Module):
                                                  pr["stereo_panner"]["pan"][0])}}
         f = (_lib.BASIC_CONSOLE | _lib.USE_TRACK_INPUT_FADER | _lib.USE_TRACK_PANNER)
         mix, mixed, _ = _ConsoleFunction.apply(tracks, track_params, None, self._c_ranges(),
-                                               self.sample_rate, f, 0, 0, self.materialize_tracks)
+                                               self.sample_rate, f, 0, 0, self.materialize_tracks, torch.is_grad_enabled())
         return mixed, mix, track_param_dict, {}, {}

@@ -12,10 +12,9 @@ int dmst_version(void) { return 1; }
 int dmst_is_device_build(void) { return DMST_DEVICE_BUILD; }
 
 size_t dmst_console_workspace_bytes(int B, int N, int T, unsigned flags) {
-    (void)flags;
     if (B <= 0 || N <= 0 || T <= 0) return 0;
     // sized for the largest look-ahead the kernels accept (one tile)
-    return dmst::carve_console(nullptr, B, N, T, dmst::kTrackTile, dmst::kMasterTile).total;
+    return dmst::carve_console(nullptr, B, N, T, dmst::kTrackTile, dmst::kMasterTile, flags).total;
 }
 
 int dmst_console_forward(const float* tracks, long long tracks_batch_stride, long long tracks_row_stride,

@@ -50,6 +50,8 @@ struct ChainArgs {
     // optional checkpoints that let backward skip the forward EQ recompute (tracks):
     float* esave;                // (nrows, Tp) EQ output, or null
     float* ssave;                // [nrows*ntiles][6*NCH*2][TILE/kBwdChunk] section states every kBwdChunk samples
+    float* gmid;                 // tracks: smoother state every 2^gmid_shift samples inside a tile, [nrows*ntiles][(TILE >> gmid_shift) - 1]
+    int gmid_shift;              //   (the track backward kernel's tile boundaries), or null
     // ---- backward only ----
     const float* gout;           // tracks: dbus (B*2, Tp); master: caller's grad_mix (B,2,T)
     const float* gmixed;         // tracks: caller's grad of mixed_tracks (B,2,N,T) or null
@@ -177,7 +179,7 @@ __device__ __forceinline__ float4 load4(const float* p, int valid, bool vec_ok) 
 
 // Static-curve gain computer of the dasp compressor, branch-free:
 // t = x_db - (thr - knee/2); g_c = slope * (clamp(t,0,W)^2/(2W) + max(t-W,0)).
-__device__ __forceinline__ float gain_computer(float side, const RowTab& tb, float& tc, float& lin) {
+__device__ __forceinline__ float gain_computer(float side, const CompTab& tb, float& tc, float& lin) {
     float d = kDbPerLog2 * __log2f(fmaxf(fabsf(side), kCompEps));
     float t = d - tb.thr_lo;
     tc = fminf(fmaxf(t, 0.0f), tb.knee);

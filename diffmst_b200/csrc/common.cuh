@@ -50,8 +50,9 @@ struct SectionTab {
     float Ppow[32][4];
 };
 
-struct RowTab {
-    SectionTab sec[kNumSections];
+// Everything of a row that is not an EQ section: gains, pan, compressor constants and smoother scan tables.
+// (First base of RowTab, so that a kernel that needs no section tables can fetch just sizeof(CompTab) bytes.)
+struct CompTab {
     // input gain (linear), output gain (linear; master only), pan gains (tracks only)
     float g_in, g_out, gL, gR;
     // compressor: y = x_delayed * 10^((g_s + makeup)/20)
@@ -67,6 +68,41 @@ struct RowTab {
     float a_lane[32];       // alpha^(L*l)
     float a_i[kMaxL];       // alpha^(i+1)
 };
+static_assert(sizeof(CompTab) % 16 == 0, "CompTab is copied with 16-byte cp.async");
+
+struct RowTab : CompTab {
+    SectionTab sec[kNumSections];
+};
+
+// ---------------------------------------------------------------------------------
+// Tables of the track backward kernel (console_bwd2.cuh): per EQ section two reverse-time all-pole
+// recursions driven by the gradient u at the EQ output, g = A^-T u (type 0) and h = (B/b0)^-T u (type 1),
+// run in DELTA form: state (s, v) with v[n] = s[n] - s[n+1],
+//     v[n] = u[n] - c0 s[n+1] + c2 v[n+1],   s[n] = s[n+1] + v[n],      c0 = 1 + c1 + c2
+// for the polynomial 1 + c1 z^-1 + c2 z^-2.  For roots near z = 1 (low shelf / low band) c0 ~ w0^2 is tiny: it
+// is computed in float64 and stored as its own float32, so the pole position keeps full relative precision
+// (direct-form a1 ~ -2, a2 ~ 1 in float32 would lose it), the rounding noise of the recursion is amplified by
+// ~1/w0 instead of ~1/w0^2, and the differences of the (smooth, huge) filtered signal that the coefficient
+// gradients need are state variables instead of float32 cancellations.
+// M = [[1-c0, c2], [-c0, c2]] advances (s, v) by one sample with zero input; P = M^32 (chunk of 32 samples).
+// (built from the float32 c0 and c2 the kernel uses: tables and recursion agree exactly.)
+// ---------------------------------------------------------------------------------
+constexpr int kBwd2Chunk = 32;     // samples per thread in the EQ-gradient phase
+// The two recursions of a section run in lock step as the halves of packed float2 operations
+// (fma.rn.f32x2 / add.rn.f32x2: one issue slot for both): .x = g (poles), .y = h (zeros), both in the form
+//     t = nc0 s + u,   v' = k2 v + t,   s' = s + v',   and off the recurrence  w = nd2 v + t  (= v' - v, the second
+//     difference, with -(1 - c2) held as its own float32),      nc0 = -c0, k2 = c2, nd2 = -(1 - c2).
+struct PairTab {
+    float2 nc0;          // -c0
+    float2 nd2;          // -(1 - c2)
+    float2 scale;        // factor of each recursion's sums in the tile partials: (1, 1/b0)
+    float2 k2;           // c2
+    float2 P2[6][4];     // P^(2^j), j = 0..4 warp scan, P2[5] = P^32 across a warp; P = M^32, M row-major
+    float2 Ppow[32][4];  // P^l
+};
+static_assert(sizeof(PairTab) == 312 * 4 && sizeof(PairTab) % 16 == 0, "PairTab layout");
+constexpr int kNumRec = 2 * kNumSections;
+struct EqBwdTab { PairTab sec[kNumSections]; };
 
 // Flags understood by the chain kernels
 constexpr unsigned kChainGain = 1u, kChainEq = 2u, kChainComp = 4u, kChainOutGain = 8u;
@@ -204,6 +240,30 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 #endif
+}
+
+// packed pairs of FP32 operations (sm_100: FFMA2 / FADD2, one issue slot for two IEEE operations)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+#ifdef DMST_EMULATE
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#else
+    return __ffma2_rn(a, b, c);
+#endif
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+#ifdef DMST_EMULATE
+    return make_float2(a.x + b.x, a.y + b.y);
+#else
+    return __fadd2_rn(a, b);
+#endif
+}
+__device__ __forceinline__ float2 shfl_down2(float2 v, int d) {
+    return make_float2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
+}
+// (s1, s2) += M (t1, t2) for a pair of 2x2 matrices m = {m00, m01, m10, m11} (each a pair)
+__device__ __forceinline__ void mat2_apply_acc2(const float2* m, float2 t1, float2 t2, float2& s1, float2& s2) {
+    s1 = fma2(m[0], t1, fma2(m[1], t2, s1));
+    s2 = fma2(m[2], t1, fma2(m[3], t2, s2));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

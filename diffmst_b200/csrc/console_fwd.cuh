@@ -415,7 +415,9 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
             // __syncthreads above are visible to whoever acquires this flag
             st_release(my_flag, kFlagSmooth);
         }
-        const float carry = fmaf(tb.a_lane[lane], cw, ex);
+        const float carry = fmaf(tb.a_lane[lane], cw, ex);   // g_s just before this thread's chunk
+        if (a.gmid && tid > 0 && ((tid * L) & ((1 << a.gmid_shift) - 1)) == 0)   // the backward kernel's tile boundaries inside this tile
+            a.gmid[((long long)row * a.ntiles + tile) * ((TILE >> a.gmid_shift) - 1) + ((tid * L) >> a.gmid_shift) - 1] = carry;
         // checkpoint of the EQ output for backward: coalesced store from the delay line
         if (a.esave) {
 #pragma unroll

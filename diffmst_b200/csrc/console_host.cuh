@@ -6,6 +6,7 @@
 
 #include "../../include/diffmst_b200.h"
 #include "console_bwd.cuh"
+#include "console_bwd2.cuh"
 #include "console_fwd.cuh"
 #include "console_prepare.cuh"
 
@@ -26,7 +27,13 @@ constexpr int kMasterL = 16, kMasterNT = 256;       // 4096-sample tiles, 2 chan
 constexpr int kMasterBwdNT = DMST_MASTER_BWD_NT;
 constexpr int kMasterBwdL = kMasterL * kMasterNT / kMasterBwdNT;
 static_assert(kMasterBwdL * kMasterBwdNT == kMasterL * kMasterNT && kMasterBwdL % 4 == 0, "master tile in the backward CTA shape");
+// track backward without audio gradient (console_bwd2.cuh): its own, smaller tiles, two CTAs per SM
+constexpr int kTrackBwd2L = 16, kTrackBwd2NT = 256;
+constexpr int kTrackBwd2Tile = kTrackBwd2L * kTrackBwd2NT;
+constexpr int kTrackBwd2Shift = 12;
+static_assert((1 << kTrackBwd2Shift) == kTrackBwd2Tile, "power-of-two tile");
 constexpr int kTrackTile = kTrackFwdL * kTrackFwdNT;
+static_assert(kTrackTile % kTrackBwd2Tile == 0, "backward tiles nest in forward tiles");
 constexpr int kMasterTile = kMasterL * kMasterNT;
 static_assert(kTrackFwdL * kTrackFwdNT == kTrackBwdL * kTrackBwdNT, "forward/backward tiles must agree");
 static_assert(kTrackBwdL == kBwdChunk && kTrackFwdL % kBwdChunk == 0, "checkpoint spacing");
@@ -89,7 +96,8 @@ struct Carver {
 struct ConsoleWs {
     int* header;          // [0..3] tickets (fwd track, fwd master, bwd master, bwd track)
     RowTab *track_tab, *track_tab_b, *master_tab, *master_tab_b;  // *_b: tables for the backward chunk length
-    float *y, *bus_pre, *dbus, *esave, *ssave, *m_esave, *m_ssave;
+    EqBwdTab* track_etab;  // recursion tables of track_bwd2_kernel
+    float *y, *bus_pre, *dbus, *esave, *ssave, *m_esave, *m_ssave, *gmid;
     // forward chain (kept for backward)
     int *t_flag, *m_flag, *t_done;
     Mail *t_state, *m_state;
@@ -100,17 +108,23 @@ struct ConsoleWs {
     float *t_dhead, *m_dhead, *t_partial, *m_partial;
     size_t flags_begin, flags_end;    // byte range of forward flags (zeroed per forward)
     size_t bflags_begin, bflags_end;  // byte range of backward flags
-    int Tp, nt_track, nt_master;
+    int Tp, nt_track, nt_master, nt_track_b2;
     size_t total;
 };
 
-inline ConsoleWs carve_console(void* base, int B, int N, int T, int la_t, int la_m) {
+// flags: DMST_WANT_GRAD_TRACKS -> the per-section state checkpoints the classic track backward needs;
+//        DMST_FORWARD_ONLY     -> no checkpoints at all (no backward will follow)
+inline ConsoleWs carve_console(void* base, int B, int N, int T, int la_t, int la_m, unsigned flags) {
+    const bool fwd_only = (flags & DMST_FORWARD_ONLY) != 0;
+    const bool classic_track_bwd = (flags & DMST_WANT_GRAD_TRACKS) != 0 && !fwd_only;
     ConsoleWs w;
     Carver c{reinterpret_cast<unsigned char*>(base), 0};
     w.Tp = (T + 3) & ~3;
     w.nt_track = (T + kTrackTile - 1) / kTrackTile;
     w.nt_master = (T + kMasterTile - 1) / kMasterTile;
+    w.nt_track_b2 = (T + kTrackBwd2Tile - 1) / kTrackBwd2Tile;
     const size_t rows = (size_t)B * N, rt = rows * w.nt_track, rm = (size_t)B * w.nt_master;
+    const size_t rtb = rows * (size_t)w.nt_track_b2;   // backward work items (the finer of the two tilings)
     w.header = c.take<int>(64);
     w.track_tab = c.take<RowTab>(rows);
     w.track_tab_b = (kTrackBwdL == kTrackFwdL) ? w.track_tab : c.take<RowTab>(rows);
@@ -119,10 +133,12 @@ inline ConsoleWs carve_console(void* base, int B, int N, int T, int la_t, int la
     w.y = c.take<float>(rows * w.Tp);
     w.bus_pre = c.take<float>((size_t)B * 2 * w.Tp);
     w.dbus = c.take<float>((size_t)B * 2 * w.Tp);
-    w.esave = c.take<float>(rows * w.Tp);
-    w.ssave = c.take<float>(rows * w.nt_track * (size_t)(kNumSections * 2) * (kTrackTile / kBwdChunk));
-    w.m_esave = c.take<float>((size_t)B * 2 * w.Tp);
-    w.m_ssave = c.take<float>((size_t)B * w.nt_master * (size_t)(kNumSections * 2 * 2) * (kMasterTile / kMasterBwdL));
+    w.track_etab = fwd_only ? nullptr : c.take<EqBwdTab>(rows);
+    w.esave = fwd_only ? nullptr : c.take<float>(rows * w.Tp);
+    w.gmid = fwd_only ? nullptr : c.take<float>(rt * (kTrackTile / kTrackBwd2Tile - 1));
+    w.ssave = classic_track_bwd ? c.take<float>(rows * w.nt_track * (size_t)(kNumSections * 2) * (kTrackTile / kBwdChunk)) : nullptr;
+    w.m_esave = fwd_only ? nullptr : c.take<float>((size_t)B * 2 * w.Tp);
+    w.m_ssave = fwd_only ? nullptr : c.take<float>((size_t)B * w.nt_master * (size_t)(kNumSections * 2 * 2) * (kMasterTile / kMasterBwdL));
     w.flags_begin = (c.off + 255) & ~size_t(255);   // zeroed before every forward
     w.t_flag = c.take<int>(rt);
     w.m_flag = c.take<int>(rm);
@@ -131,18 +147,18 @@ inline ConsoleWs carve_console(void* base, int B, int N, int T, int la_t, int la
     w.m_state = c.take<Mail>(rm * kStateStride);
     w.flags_end = c.off;
     w.bflags_begin = (c.off + 255) & ~size_t(255);  // zeroed before every backward
-    w.t_bflag = c.take<int>(rt);
+    w.t_bflag = c.take<int>(rtb);
     w.m_bflag = c.take<int>(rm);
-    w.t_bstate = c.take<Mail>(rt * kStateStride);
+    w.t_bstate = c.take<Mail>(rtb * kStateStride);
     w.m_bstate = c.take<Mail>(rm * kStateStride);
     w.bflags_end = c.off;
     w.t_tail2 = c.take<float>(rt * kTail2Stride);
     w.m_tail2 = c.take<float>(rm * kTail2Stride);
     w.t_etail = c.take<float>(rt * (size_t)la_t + 4);
     w.m_etail = c.take<float>(rm * 2 * (size_t)la_m + 4);
-    w.t_dhead = c.take<float>(rt * (size_t)la_t + 4);
+    w.t_dhead = c.take<float>(rtb * (size_t)la_t + 4);
     w.m_dhead = c.take<float>(rm * 2 * (size_t)la_m + 4);
-    w.t_partial = c.take<float>(rt * kGradCount);
+    w.t_partial = c.take<float>(rtb * kGradCount);
     w.m_partial = c.take<float>(rm * kGradCount);
     w.total = (c.off + 255) & ~size_t(255);
     return w;
@@ -206,7 +222,7 @@ inline int check_call(const ConsoleCall& k) {
     if (!(k.flags & DMST_USE_TRACK_PANNER)) return DMST_EINVAL;     // broken upstream (modules.py:269)
     if (!(k.flags & DMST_BASIC_CONSOLE) && !k.master_params) return DMST_EINVAL;
     // (limits: the backward kernels keep two look-ahead + tile lines and the prefetched gradient in shared memory)
-    if (k.la_t < 0 || k.la_t > kTrackTile / 2 || k.la_m < 0 || k.la_m > kMasterTile) return DMST_EINVAL;
+    if (k.la_t < 0 || k.la_t > kTrackBwd2Tile || k.la_m < 0 || k.la_m > kMasterTile) return DMST_EINVAL;
     if ((k.la_t & 31) || (k.la_m & 31)) return DMST_EINVAL;  // look-ahead must be a multiple of 32 samples
     return 0;
 }
@@ -251,6 +267,7 @@ inline void fill_chain(ChainArgs& a, const ConsoleCall& k, bool master, ConsoleW
         a.src_vec_ok = aligned16(k.tracks) && (k.tbs % 4 == 0) && (k.trs % 4 == 0);
         a.tab = w.track_tab; a.track_tab = w.track_tab; a.y = w.y;
         if (a.flags & kChainEq) { a.esave = w.esave; a.ssave = w.ssave; }
+        if (a.flags & kChainComp) { a.gmid = w.gmid; a.gmid_shift = kTrackBwd2Shift; }
         a.ticket = w.header + 0; a.flag = w.t_flag; a.state = w.t_state; a.tail2 = w.t_tail2; a.etail = w.t_etail;
         a.partial = w.t_partial; a.bflag = w.t_bflag; a.bstate = w.t_bstate; a.dhead = w.t_dhead;
     } else {
@@ -274,7 +291,7 @@ inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* 
     DMST_CHECK(check_call(k));
     if (!mix || !status || !ws) return DMST_EINVAL;
     if ((k.flags & DMST_WANT_MIXED_TRACKS) && !mixed) return DMST_EINVAL;
-    ConsoleWs w = carve_console(ws, k.B, k.N, k.T, k.la_t, k.la_m);
+    ConsoleWs w = carve_console(ws, k.B, k.N, k.T, k.la_t, k.la_m, k.flags);
     if (ws_bytes < w.total || !aligned16(ws)) return DMST_EINVAL;
     unsigned char* base = reinterpret_cast<unsigned char*>(ws);
     DMST_CHECK(DMST_MEMSET_ASYNC(w.header, 0, 64 * sizeof(int), stream));
@@ -323,8 +340,9 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
                             float* gmp, float* gtracks, void* ws, size_t ws_bytes, cudaStream_t stream) {
     DMST_CHECK(check_call(k));
     if (!gmix || !gtp || !ws) return DMST_EINVAL;
+    if (k.flags & DMST_FORWARD_ONLY) return DMST_EINVAL;   // the forward call kept no checkpoints
     if ((k.flags & DMST_WANT_GRAD_TRACKS) && !gtracks) return DMST_EINVAL;
-    ConsoleWs w = carve_console(ws, k.B, k.N, k.T, k.la_t, k.la_m);
+    ConsoleWs w = carve_console(ws, k.B, k.N, k.T, k.la_t, k.la_m, k.flags);
     if (ws_bytes < w.total || !aligned16(ws)) return DMST_EINVAL;
     unsigned char* base = reinterpret_cast<unsigned char*>(ws);
     DMST_CHECK(DMST_MEMSET_ASYNC(w.header, 0, 64 * sizeof(int), stream));
@@ -366,7 +384,34 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
     at.tab = w.track_tab_b;
     ft.total = at.nrows * at.ntiles; ft.ticket = w.header + 3;
     ft.area = bwd_area_floats(1, kTrackTile, k.la_t);
-    {
+    int epilogue_tiles = w.nt_track;
+    if (!(k.flags & DMST_WANT_GRAD_TRACKS)) {
+        // parameter gradients only (training): commuting-sections formulation, needs only the EQ-output checkpoint
+        Bwd2Args f2;
+        memset(&f2, 0, sizeof(f2));
+        f2.b = ft;
+        f2.b.a.ntiles = w.nt_track_b2;
+        f2.b.total = at.nrows * w.nt_track_b2;
+        f2.etab = w.track_etab;
+        f2.fwd_ntiles = w.nt_track;
+        f2.fwd_ratio = kTrackTile / kTrackBwd2Tile;
+        epilogue_tiles = w.nt_track_b2;
+        if (at.flags & kChainEq) {
+            PrepareBwdArgs pb;
+            memset(&pb, 0, sizeof(pb));
+            pb.params = k.track_params; pb.rows = at.nrows; pb.np = DMST_NUM_TRACK_PARAMS; pb.sr = (double)k.sr; pb.tab = w.track_etab;
+            for (int i = 0; i < DMST_NUM_TRACK_PARAMS; ++i) { pb.lo[i] = k.ranges->track_lo[i]; pb.hi[i] = k.ranges->track_hi[i]; }
+            DMST_LAUNCH(prepare_bwd_kernel, dim3(pb.rows), dim3(kNumRec * 32), 0, stream, pb);
+        }
+        auto kern = track_bwd2_kernel<kTrackBwd2L, kTrackBwd2NT>;
+        const size_t smem = bwd_smem_bytes(1, kTrackBwd2Tile, k.la_t, kTrackBwd2NT, false);
+        DMST_CHECK(DMST_SET_SMEM(kern, smem));
+        int ctas = persistent_ctas(kern, kTrackBwd2NT, smem);
+        if (ctas <= 0) return DMST_EINVAL;
+        if (ctas > f2.b.total) ctas = f2.b.total;
+        ScopedTimer tm(3, stream);
+        DMST_LAUNCH(kern, dim3(ctas), dim3(kTrackBwd2NT), smem, stream, f2);
+    } else {
         auto kern = chain_bwd_kernel<1, kTrackBwdL, kTrackBwdNT, false>;
         const size_t smem = bwd_smem_bytes(1, kTrackTile, k.la_t, kTrackBwdNT, false);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
@@ -388,7 +433,7 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
         } else {
             for (int i = 0; i < DMST_NUM_TRACK_PARAMS; ++i) { e.lo[i] = k.ranges->track_lo[i]; e.hi[i] = k.ranges->track_hi[i]; }
         }
-        e.sr = (double)k.sr; e.partial = w.t_partial; e.ntiles = w.nt_track; e.flags = at.flags; e.grad = gtp;
+        e.sr = (double)k.sr; e.partial = w.t_partial; e.ntiles = epilogue_tiles; e.flags = at.flags; e.grad = gtp;
         DMST_LAUNCH(grad_epilogue_kernel, dim3(e.rows), dim3(64), 0, stream, e);
     }
     return DMST_LAST_ERROR();

@@ -197,6 +197,51 @@ __global__ void prepare_kernel(PrepareArgs a) {
     }
 }
 
+// Tables of the track backward kernel (console_bwd2.cuh): per (row, section) the two delta-form recursions
+// g = A^-T u and h = (B/b0)^-T u (common.cuh, RecTab), designed in float64 from the denormalised parameters.
+struct PrepareBwdArgs {
+    const float* params;   // (rows, np) normalised track parameters
+    int rows, np;
+    float lo[32], hi[32];
+    double sr;
+    EqBwdTab* tab;         // [rows]
+};
+// grid: rows blocks of kNumRec warps; warp r builds recursion r = 2 * section + type, lane l builds P^l
+__global__ void prepare_bwd_kernel(PrepareBwdArgs a) {
+    const int row = blockIdx.x;
+    const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (r >= kNumRec) return;
+    const int sec = r >> 1, type = r & 1;
+    const float* p = a.params + (long long)row * a.np;
+    const int i0 = 1 + 3 * sec;   // advanced track layout (mst/modules.py:353-380)
+    Dual o[5];
+    rbj_design(denorm(a, p, i0), denorm(a, p, i0 + 1), denorm(a, p, i0 + 2), a.sr, section_kind(sec), o);
+    double c1, c2, scale;
+    if (type == 0) { c1 = o[3].v; c2 = o[4].v; scale = 1.0; }
+    else { c1 = o[1].v / o[0].v; c2 = o[2].v / o[0].v; scale = 1.0 / o[0].v; }
+    const float nc0 = (float)(-(1.0 + c1 + c2)), nd2 = (float)(-(1.0 - c2)), k2 = (float)c2;
+    // one-sample transition of (s, v) of the recursion the kernel actually runs (its float32 constants), in float64
+    const double c0e = -(double)nc0, a2e = (double)k2;
+    M2 P = {1.0 - c0e, a2e, -c0e, a2e};
+    for (int s = 1; s < kBwd2Chunk; s <<= 1) P = mmul(P, P);   // M^32: one chunk
+    M2 sq[6];
+    sq[0] = P;
+    for (int j = 1; j < 6; ++j) sq[j] = mmul(sq[j - 1], sq[j - 1]);
+    M2 pw = {1, 0, 0, 1};
+    for (int j = 0; j < 5; ++j)
+        if ((lane >> j) & 1) pw = mmul(pw, sq[j]);
+    PairTab& pt = a.tab[row].sec[sec];
+    auto put = [&](float2* m4, M2 m) {   // this recursion's half of a pair of row-major 2x2 matrices
+        float* f = reinterpret_cast<float*>(m4) + type;
+        f[0] = (float)m.a; f[2] = (float)m.b; f[4] = (float)m.c; f[6] = (float)m.d;
+    };
+    put(pt.Ppow[lane], pw);
+    if (lane < 6) put(pt.P2[lane], sq[lane]);
+    if (lane == 6) {
+        (&pt.nc0.x)[type] = nc0; (&pt.nd2.x)[type] = nd2; (&pt.scale.x)[type] = (float)scale; (&pt.k2.x)[type] = k2;
+    }
+}
+
 struct EpilogueArgs {
     const float* params;
     int rows, np, kind;

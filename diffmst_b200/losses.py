@@ -33,7 +33,7 @@ def _rows_view(t: torch.Tensor):
 
 class _MrstftFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, y, windows, cfg):
+    def forward(ctx, x, y, windows, cfg, grad_enabled=True):
         lib = _lib.lib()
         _require_cuda(x, "input")
         _require_cuda(y, "target")
@@ -41,13 +41,13 @@ class _MrstftFunction(torch.autograd.Function):
             raise ValueError(f"input {tuple(x.shape)} and target {tuple(y.shape)} differ in shape")
         xv, rows, T, xs = _rows_view(x)
         yv, _, _, ys = _rows_view(y)
-        if ctx.needs_input_grad[1]:
+        if grad_enabled and ctx.needs_input_grad[1]:
             # auraloss differentiates both arguments; the reference only ever passes a detached target
             # (mst/system.py:232-258: the reference mix comes out of torch.no_grad()).  Refuse rather than return a
             # silent zero gradient.
             raise NotImplementedError("MultiResolutionSTFTLoss: a target that requires grad is not supported; "
                                       "detach it (the reference's target is a no-grad reference mix)")
-        need_grad = ctx.needs_input_grad[0]   # False under torch.no_grad(): the gradient pass is skipped
+        need_grad = bool(grad_enabled) and ctx.needs_input_grad[0]   # (no_grad: the gradient pass is skipped)
         dev = x.device
         with torch.cuda.device(dev):
             nbytes = lib.dmst_mrstft_workspace_bytes(ctypes.byref(cfg), rows, T)
@@ -69,8 +69,8 @@ class _MrstftFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, _gterms):
         if ctx.gx is None:
-            return None, None, None, None
-        return (ctx.gx.view(ctx.shape) * gloss), None, None, None
+            return None, None, None, None, None
+        return (ctx.gx.view(ctx.shape) * gloss), None, None, None, None
 
 
 class MultiResolutionSTFTLoss(torch.nn.Module):
@@ -132,7 +132,7 @@ class MultiResolutionSTFTLoss(torch.nn.Module):
         return self._windows[device]
 
     def forward(self, x: torch.Tensor, y: torch.Tensor):
-        loss, terms = _MrstftFunction.apply(x, y, self._windows_on(x.device), self._cfg())
+        loss, terms = _MrstftFunction.apply(x, y, self._windows_on(x.device), self._cfg(), torch.is_grad_enabled())
         self.last_terms = terms[1:].view(-1, 3)
         return loss
 

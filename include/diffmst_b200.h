@@ -39,8 +39,11 @@ extern "C" {
 #define DMST_USE_FX_BUS 32u /* accepted only when clear: fx bus is out of scope */
 #define DMST_USE_OUTPUT_FADER 64u
 #define DMST_WANT_MIXED_TRACKS 128u /* materialise (B,2,N,T) as modules.py:314 returns it */
-#define DMST_WANT_GRAD_TRACKS 256u  /* backward also writes dL/dtracks */
+#define DMST_WANT_GRAD_TRACKS 256u  /* backward also writes dL/dtracks (forward then keeps per-section checkpoints) */
 #define DMST_BASIC_CONSOLE 512u     /* BasicMixConsole layout: 2 track params [gain_db, pan] */
+#define DMST_FORWARD_ONLY 1024u     /* no backward will follow (torch.no_grad(), mst/mixing.py:72): no checkpoints */
+/* DMST_WANT_MIXED_TRACKS, DMST_WANT_GRAD_TRACKS and DMST_FORWARD_ONLY shape the workspace: pass the same flags
+ * to dmst_console_workspace_bytes, dmst_console_forward and the matching dmst_console_backward. */
 
 /* number of control parameters (mst/modules.py:182-184) */
 #define DMST_NUM_TRACK_PARAMS 27
@@ -61,7 +64,7 @@ int dmst_is_device_build(void);
 /* ---- mix console: replaces AdvancedMixConsole.forward / forward_mix_console
  *      (mst/modules.py:186-314, 316-487) and the dasp_pytorch calls inside it ---- */
 
-/* Bytes of workspace needed by dmst_console_forward/backward for this shape. */
+/* Bytes of workspace needed by dmst_console_forward/backward for this shape and these flags. */
 size_t dmst_console_workspace_bytes(int B, int N, int T, unsigned flags);
 
 /*

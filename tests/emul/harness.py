@@ -65,13 +65,15 @@ class EmulConsole:
         self.sr = sr
         self.ranges = default_ranges(sr)
 
-    def forward(self, tracks, tp, mp, flags, la_t=2048, la_m=1024, want_mixed=True):
+    def forward(self, tracks, tp, mp, flags, la_t=2048, la_m=1024, want_mixed=True, want_grad_tracks=True):
         B, N, T = tracks.shape
         tracks = np.ascontiguousarray(tracks, dtype=np.float32)
         tp = np.ascontiguousarray(tp, dtype=np.float32)
         mp = np.ascontiguousarray(mp, dtype=np.float32) if mp is not None else None
         if want_mixed:
             flags |= WANT_MIXED_TRACKS
+        if want_grad_tracks:   # shapes the checkpoints forward keeps: must be known at forward time
+            flags |= WANT_GRAD_TRACKS
         nbytes = self.lib.dmst_console_workspace_bytes(B, N, T, flags)
         ws = np.zeros(nbytes // 4 + 64, dtype=np.float32)
         off = (-ws.ctypes.data) % 256
@@ -87,11 +89,10 @@ class EmulConsole:
         self._saved = (tracks, tp, mp, flags, la_t, la_m, ws, wsp, nbytes)
         return mix, mixed, status
 
-    def backward(self, gmix, gmixed=None, want_grad_tracks=True):
+    def backward(self, gmix, gmixed=None):
         tracks, tp, mp, flags, la_t, la_m, ws, wsp, nbytes = self._saved
         B, N, T = tracks.shape
-        if want_grad_tracks:
-            flags |= WANT_GRAD_TRACKS
+        want_grad_tracks = bool(flags & WANT_GRAD_TRACKS)
         gmix = np.ascontiguousarray(gmix, dtype=np.float32)
         gtp = np.full(tp.shape, np.nan, dtype=np.float32)
         gmp = np.full((B, 26), np.nan, dtype=np.float32) if mp is not None else None

@@ -116,3 +116,30 @@ def test_emulated_basic_console_config0_shape(emul_console):
     assert rel_max(mixed, omixed.detach().numpy()) <= 1e-6
     assert rel_l2(gtp, tpd.grad.numpy()) <= 1e-5
     assert rel_l2(gtr, trd.grad.numpy()) <= 1e-6
+
+
+@pytest.mark.parametrize("shape,flagkw", [((1, 2, 32768), {}), ((2, 2, 36871), {}), ((1, 1, 33001), dict(use_track_compressor=False)),
+                                          ((1, 2, 32768), dict(use_track_eq=False))])
+def test_emulated_parameter_only_backward_matches_float64_oracle(emul_console, shape, flagkw):
+    """The training-mode track backward (console_bwd2.cuh: commuting-sections EQ gradients, delta-form recursions,
+    no section checkpoints) - taken when no gradient w.r.t. the audio is requested - against float64 autograd."""
+    from oracle.console import OracleAdvancedMixConsole
+    B, N, T = shape
+    g = torch.Generator().manual_seed(T + 1)
+    tracks = torch.randn(B, N, T, generator=g) * 0.1
+    tp, fp, mp = torch.rand(B, N, 27, generator=g), torch.rand(B, 25, generator=g), torch.rand(B, 26, generator=g)
+    probe = torch.randn(B, 2, T, generator=g)
+    con = emul_console.EmulConsole()
+    mix, mixed, status = con.forward(tracks.numpy(), tp.numpy(), mp.numpy(), emul_console.flags_from(**flagkw), want_mixed=False,
+                                     want_grad_tracks=False)
+    gtp, gmp, gtr = con.backward(probe.numpy())
+    assert gtr is None
+    orc = OracleAdvancedMixConsole(44100)
+    tpd, mpd = (t.double().requires_grad_(True) for t in (tp, mp))
+    kw = dict(use_fx_bus=False); kw.update(flagkw)
+    omix = orc(tracks.double(), tpd, fp.double(), mpd, **kw)[1]
+    (omix * probe.double()).sum().backward()
+    assert rel_max(mix, omix.detach().numpy()) <= 1e-4
+    assert np.isfinite(gtp).all()
+    assert rel_l2(gtp, tpd.grad.numpy()) <= 1e-3, (rel_l2(gtp, tpd.grad.numpy()), np.abs(gtp - tpd.grad.numpy()).max(axis=(0, 1)))
+    assert rel_l2(gmp, mpd.grad.numpy()) <= 1e-3

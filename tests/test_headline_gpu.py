@@ -137,12 +137,19 @@ def test_million_sample_track_matches_time_domain_recursion():
     mpn[24] = float(mpd["output_fader"]["gain_db"][0]); mpn[25] = float(mpd["input_fader"]["gain_db"][0])
     want_mixed, want_mix = td.console(tracks[0].numpy().astype(np.float64), tpn, mpn, SR)
     got_mix, got_mixed = mix[0].cpu().numpy(), mixed[0].cpu().numpy()
+    # the reference algorithm's own float32 evaluation (FFT method) of the same case, for the bound of SURVEY 8c
+    with torch.no_grad():
+        ref32 = OracleAdvancedMixConsole(SR)(tracks, tp, fp, mp, **FLAGS)
+    ref_mixed, ref_mix = ref32[0][0].numpy().astype(np.float64), ref32[1][0].numpy().astype(np.float64)
     scale = np.abs(want_mix).max()
     seg = 65536
     errs = [float(np.abs(got_mix[:, s:s + seg] - want_mix[:, s:s + seg]).max() / scale) for s in range(0, T, seg)]
-    assert max(errs) <= 2e-4, errs
+    refs = [float(np.abs(ref_mix[:, s:s + seg] - want_mix[:, s:s + seg]).max() / scale) for s in range(0, T, seg)]
+    print("1M-sample chain, mix error per 65536-sample segment: ours max %.2e (first 8: %.2e, last 8: %.2e); reference float32 max %.2e"
+          % (max(errs), max(errs[:8]), max(errs[8:]), max(refs)))
+    assert max(errs) <= 1.5 * max(2e-4, max(refs)), (errs, refs)
     assert max(errs[8:]) <= 3 * max(max(errs[:8]), 2e-5), errs   # no growth along the 128-tile chain
-    assert relmax(got_mixed, want_mixed) <= 2e-4
+    assert relmax(got_mixed, want_mixed) <= 1.5 * max(2e-4, relmax(ref_mixed, want_mixed))
 
 
 def test_async_range_check_and_forward_mix_console_without_clamp():
@@ -169,10 +176,11 @@ def test_async_range_check_and_forward_mix_console_without_clamp():
     con(x.cuda(), bad_tp.cuda(), fp.cuda(), bad_mp.cuda(), use_fx_bus=False)
     with pytest.raises(ValueError, match="Parameter pan of effect stereo_panner is out of range."):
         con.check_pending_ranges()
-    # denormalised dictionaries with an out-of-range cutoff (sr/2 - 1, as mst/mixing.py's rule-based mix produces)
     tpd, fxd, mpd = out[2], out[3], out[4]
-    tpd["parametric_eq"]["high_shelf_cutoff_freq"] = torch.full_like(tpd["parametric_eq"]["high_shelf_cutoff_freq"], SR / 2 - 1.0)
-    tpd["input_fader"]["gain_db"] = tpd["input_fader"]["gain_db"] + 60.0     # beyond +48 dB
+    # denormalised dictionaries with out-of-range entries (mst/mixing.py's rule-based mix produces such values)
+    tpd["parametric_eq"]["high_shelf_cutoff_freq"] = torch.full_like(tpd["parametric_eq"]["high_shelf_cutoff_freq"], 21800.0)  # > sr//2 - 1000
+    tpd["input_fader"]["gain_db"] = torch.full_like(tpd["input_fader"]["gain_db"], -54.0)   # below -48 dB
+    mpd["compressor"]["ratio"] = torch.full_like(mpd["compressor"]["ratio"], 14.0)           # above 10
     with torch.no_grad():
         got = con.forward_mix_console(x.cuda(), tpd, fxd, mpd, True, True, True, True, False, True, True)[1].cpu().numpy()
     orc = OracleAdvancedMixConsole(SR)
