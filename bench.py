@@ -12,7 +12,14 @@ parameters.  Metric: track-seconds per second = B*N*T / 44100 / step time, summe
 
 `--impl reference` times the reference algorithm's CPU path instead: the float32 oracle port
 (oracle/, the reference classes cannot travel to the GPU box because their third-party DSP
-dependencies are not installable) on all host cores, on a bounded sample (batch 1).
+dependencies are not installable) on all host cores, on the same configuration (batch 8), a bounded
+number of steps.
+
+Timing hygiene: the range test of mst/modules.py:86-89 stays ON inside every timed region (device-side,
+asynchronous: `check_ranges="async"`, verdict read after the region); the timed region lasts at least
+`--min-seconds` (default 1 s) whatever `--steps` says (`steps` in the JSON line is the number actually
+timed, `steps_requested` what was asked for); DRAM traffic and instruction counts of the dominant kernel
+come from the committed ncu summary under profiles/ (never hard-coded).
 """
 import argparse
 import ctypes
@@ -37,6 +44,29 @@ FLAGS = dict(use_track_input_fader=True, use_track_eq=True, use_track_compressor
 # algorithmic bytes per track-sample (SURVEY.md section 8d / BASELINE.md section 3, bus-only mode)
 BYTES_FWD = 4.0 + 8.0 / N
 BYTES_BWD = 4.0 + 8.0 / N
+
+
+def ncu_summary(kernel_substring):
+    """(dram bytes per launch, warp-instructions per launch, file) of the dominant kernel from the newest committed
+    profiles/ncu_r*_summary.json (written by scripts/make_profile_summary.py from an `ncu --set full` capture), or
+    (None, None, None) when no capture of this kernel exists."""
+    import glob
+    import re
+    def rnd(p):
+        m = re.search(r"ncu_r(\d+)", os.path.basename(p))
+        return int(m.group(1)) if m else -1
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*_summary.json")), key=rnd, reverse=True):
+        try:
+            with open(path) as f:
+                kernels = json.load(f).get("kernels", [])
+        except (OSError, ValueError):
+            continue
+        for k in kernels:
+            if kernel_substring in k.get("kernel", ""):
+                num = lambda v: float(str(v).replace(",", ""))
+                mb = num(k["dram_read_MB"]) + num(k["dram_write_MB"])
+                return mb * 1e6, num(k["warp_instructions"]), os.path.relpath(path, ROOT)
+    return None, None, None
 
 
 def measured_peaks():
@@ -113,7 +143,8 @@ def make_inputs(torch, seed, batch, device):
 
 
 def run_reference(args):
-    """CPU path of the reference algorithm (oracle port, float32), bounded sample: batch 1."""
+    """CPU path of the reference algorithm (oracle port, float32) on the arm's own configuration (batch 8: about
+    10 GB of temporaries, the box has 196 GB), bounded number of steps."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -123,7 +154,7 @@ def run_reference(args):
     from oracle.loss import batch_stereo_peak_normalize
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    batch = 1
+    batch = B
     tracks, tp, fp, mp, tp2, mp2 = make_inputs(torch, 0, batch, "cpu")
     con = OracleAdvancedMixConsole(SR)
     loss_fn = MultiResolutionSTFTLoss(**RES)
@@ -138,19 +169,20 @@ def run_reference(args):
         loss.backward()
         return float(loss.detach())
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(1, min(args.warmup, 1))):
         step()
-    steps = max(1, min(args.steps, 5))
+    steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
     value = batch * N * T / SR / dt
-    sample = f"batch 1 of the workload ({N} tracks x {T} samples), fwd+bwd+MRSTFT, float32, {steps} steps"
+    sample = f"the full batch of {batch} x {N} tracks x {T} samples, fwd+bwd+MRSTFT, float32, {steps} steps after 1 warm-up"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3,
+            "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "AdvancedMixConsole fwd+bwd + MRSTFT, 16 tracks x 262144 samples (CPU sample: batch 1)"},
+            "config": {"workload": "AdvancedMixConsole fwd+bwd + MRSTFT loss, batch 8 x 16 tracks x 262144 "
+                                   "samples (BASELINE configs[1])", "global_batch": batch, "tracks": N, "samples": T},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -162,28 +194,29 @@ def cpu_baseline_leg(torch):
     from oracle.loss import batch_stereo_peak_normalize
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    tracks, tp, fp, mp, tp2, mp2 = make_inputs(torch, 0, 1, "cpu")
+    tracks, tp, fp, mp, tp2, mp2 = make_inputs(torch, 0, B, "cpu")
     con = OracleAdvancedMixConsole(SR)
     loss_fn = MultiResolutionSTFTLoss(**RES)
     with torch.no_grad():
         target = batch_stereo_peak_normalize(con(tracks, tp2, fp, mp2, **FLAGS)[1])
     tp.requires_grad_(True); mp.requires_grad_(True)
     times = []
-    for i in range(4):
+    for i in range(3):
         tp.grad = None; mp.grad = None
         t0 = time.perf_counter()
         loss_fn(con(tracks, tp, fp, mp, **FLAGS)[1], target).backward()
         times.append(time.perf_counter() - t0)
     dt = statistics.median(times[1:])
-    return {"value": N * T / SR / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"batch 1 ({N} tracks x {T} samples) fwd+bwd+MRSTFT, float32 oracle port on {cores} host "
-                      f"threads, median of 3 after 1 warm-up ({dt:.2f} s/step)"}
+    return {"value": B * N * T / SR / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"the full batch ({B} x {N} tracks x {T} samples) fwd+bwd+MRSTFT, float32 oracle port on {cores} host "
+                      f"threads, median of 2 after 1 warm-up ({dt:.2f} s/step)"}
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from diffmst_b200 import AdvancedMixConsole, GraphedStep, MRSTFTLoss, batch_stereo_peak_normalize, _lib
+    from diffmst_b200.dist_util import max_over_ranks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,7 +231,9 @@ def run_ours(args):
 
     con = AdvancedMixConsole(SR).to(dev)
     con.materialize_tracks = False   # bus-only mode
-    con.check_ranges = False         # inputs are generated in range; skips one host sync per call
+    con.check_ranges = "async"       # the range test of mst/modules.py:86-89 runs on the device in every step
+    con_full = AdvancedMixConsole(SR).to(dev)   # the reference's full return contract: mixed_tracks (B,2,N,T) materialised
+    con_full.check_ranges = "async"
     loss_fn = MRSTFTLoss(**RES)
     tracks_h, tp_h, fp_h, mp_h, tp2, mp2 = make_inputs(torch, rank, B, "cpu")
     tracks = tracks_h.to(dev); fp = fp_h.to(dev)
@@ -206,12 +241,25 @@ def run_ours(args):
     with torch.no_grad():
         target = batch_stereo_peak_normalize(con(tracks, tp2.to(dev), fp, mp2.to(dev), **FLAGS)[1])
 
-    def step(x):
+    def step(x, console=con):
         tp.grad = None; mp.grad = None
-        mix = con(x, tp, fp, mp, **FLAGS)[1]
+        mix = console(x, tp, fp, mp, **FLAGS)[1]
         loss = loss_fn(mix, target)
         loss.backward()
         return loss
+
+    def timed(fn, steps):
+        """`steps` calls of fn between barriers; device time (CUDA events), max over ranks, and the host window."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        h0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        sampler.windows.append((h0, time.perf_counter()))
+        return max_over_ranks(e0.elapsed_time(e1), dev)
 
     def barrier():
         if world > 1:
@@ -228,28 +276,26 @@ def run_ours(args):
     for _ in range(3):
         step(tracks)
     barrier()
-    lib.dmst_profile_enable(args.steps)
+    # number of timed steps: what was asked for, but at least --min-seconds of device time (a 20-step region of this
+    # workload is 25 ms: three clock samples and a cold-boost burst); every rank agrees on the count
+    probe_ms = timed(lambda: step(tracks), 3) / 3
+    sampler.windows.clear()
+    steps = max(args.steps, int(-(-args.min_seconds * 1e3 // max(probe_ms, 1e-3))))
+    lib.dmst_profile_enable(steps)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_host0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        step(tracks)
-    ev1.record()
-    barrier()
-    sampler.windows.append((t_host0, time.perf_counter()))
-    ms = ev0.elapsed_time(ev1)
+    ms_eager_max = timed(lambda: step(tracks), steps)
     kern_ms = {}
-    buf = (ctypes.c_float * args.steps)()
+    buf = (ctypes.c_float * steps)()
     # kind 0: fused forward kernel (tracks + master bus), 2: master-bus backward, 3: track backward
     for kind, name in ((0, "console_fwd"), (2, "master_bwd"), (3, "track_bwd")):
-        n = lib.dmst_profile_read(kind, buf, args.steps)
+        n = lib.dmst_profile_read(kind, buf, steps)
         kern_ms[name] = sum(buf[i] for i in range(n)) / n if n > 0 else None
     lib.dmst_profile_enable(0)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_eager_max = float(t.item())
+    # full-contract mode (mst/modules.py:314 returns the panned tracks (B,2,N,T)): same step, mixed_tracks materialised
+    for _ in range(3):
+        step(tracks, con_full)
+    ms_full_max = timed(lambda: step(tracks, con_full), max(steps // 4, 10))
+    steps_full = max(steps // 4, 10)
 
     # ---------------- device-resident timing, the step replayed as one CUDA graph ----------------
     # (the public GraphedStep of the package: same kernels, same tensors, no launch gaps)
@@ -267,18 +313,7 @@ def run_ours(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # every rank takes the same branch
     use_graph = int(ok.item()) == 1
     if use_graph:
-        barrier()
-        t_host1 = time.perf_counter()
-        ev0.record()
-        for _ in range(args.steps):
-            graphed()
-        ev1.record()
-        barrier()
-        sampler.windows.append((t_host1, time.perf_counter()))
-        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
+        ms_max = timed(graphed, steps)
         step_loss = float(graphed.loss.detach())
         launch_note = ("the step replayed as one CUDA graph (diffmst_b200.GraphedStep); eager launches of the same "
                        "step: see `eager`")
@@ -287,7 +322,10 @@ def run_ours(args):
         step_loss = float(step(tracks).detach())
         launch_note = f"eager launches (CUDA-graph capture failed on some rank: {graph_err})"
 
-    # clocks / throttle reasons: the samples that fall inside the two timed regions (eager, graph replay)
+    # the asynchronous range verdicts of every step above (eager, full contract, graph replays)
+    con.check_pending_ranges()
+    con_full.check_pending_ranges()
+    # clocks / throttle reasons: the samples that fall inside the timed regions (eager, full contract, graph replay)
     if rank == 0:
         time.sleep(0.06)         # let the sampler deliver the sample taken during the region
     clocks = sampler.stop() if rank == 0 else None
@@ -343,58 +381,68 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     e2e_loop(max(args.warmup, 3))
+    e2e_steps = max(args.steps, int(-(-args.min_seconds * 1e3 // max(2 * probe_ms, 1e-3))))
     barrier()
-    t0 = time.perf_counter()
     ev0.record()
-    e2e_loop(args.steps)
+    e2e_loop(e2e_steps)
     ev1.record()
     barrier()
-    e2e_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(t.item())
+    e2e_ms_max = max_over_ranks(ev0.elapsed_time(ev1), dev)
+    con.check_pending_ranges()
 
     if rank == 0:
         units = world * B * N * T / SR  # track-seconds per step over all ranks
-        value = units / (ms_max / 1e3 / args.steps)
-        e2e_value = units / (e2e_ms_max / 1e3 / args.steps)
+        value = units / (ms_max / 1e3 / steps)
+        e2e_value = units / (e2e_ms_max / 1e3 / e2e_steps)
         peak, peak_src = measured_peaks()
         samples = B * N * T
         roof = None
         if kern_ms.get("track_bwd"):
             achieved = BYTES_BWD * samples / (kern_ms["track_bwd"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": "chain_bwd_kernel<tracks>", "achieved": achieved, "peak": peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum of one launch of this kernel,
+            # from the committed `ncu --set full` capture (profiles/); null when there is no capture of this kernel
+            traffic, winst, src = ncu_summary("track_bwd2_kernel")
+            sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+            roof = {"bound": "hbm", "kernel": "track_bwd2_kernel (per-track chain backward, parameter gradients)",
+                    "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": BYTES_BWD * samples,
                     "avg_launch_ms": kern_ms["track_bwd"],
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch,
-                    # from profiles/ (ncu --set full); None until a capture of this build exists
-                    "traffic": TRAFFIC_TRACK_BWD_BYTES,
+                    "traffic": traffic, "traffic_source": src,
                     "kernel_ms": kern_ms,
-                    # honest co-limit: the kernel is bound by instruction issue, not by HBM:
-                    # executed warp-instructions of one launch (ncu, profiles/) / (4 schedulers x SMs x SM clock)
-                    "issue_rate": {"warp_instructions_per_launch": TRACK_BWD_WARP_INSTRUCTIONS,
-                                   "peak_warp_instructions_per_s": 4 * 148 * 1.965e9,
-                                   "frac": TRACK_BWD_WARP_INSTRUCTIONS / (kern_ms["track_bwd"] * 1e-3) / (4 * 148 * 1.965e9)},
-                    "step_frac_of_hbm_roofline": (BYTES_FWD + BYTES_BWD) * samples / (ms_max / args.steps * 1e-3) / 1e9 / peak}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                    # honest co-limit: the kernel is bound by FP32 issue / pipe, not by HBM:
+                    # executed warp-instructions of one launch (ncu) / (4 schedulers x SMs x measured SM clock)
+                    "issue_rate": None if winst is None else {
+                        "warp_instructions_per_launch": winst,
+                        "peak_warp_instructions_per_s": 4 * 148 * sm_hz * 1e6,
+                        "frac": winst / (kern_ms["track_bwd"] * 1e-3) / (4 * 148 * sm_hz * 1e6)},
+                    "step_frac_of_hbm_roofline": (BYTES_FWD + BYTES_BWD) * samples / (ms_max / steps * 1e-3) / 1e9 / peak}
+        bytes_full = (BYTES_FWD + 8.0) + BYTES_BWD   # + the (B,2,N,T) write: 17 B per track-sample at N = 16
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+                "steps_requested": args.steps, "min_seconds": args.min_seconds,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_max / steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "AdvancedMixConsole fwd+bwd + MRSTFT loss, batch 8 x 16 tracks x 262144 "
                                        "samples per GPU (BASELINE configs[1])",
                            "global_batch": world * B, "tracks": N, "samples": T, "parallelism": f"dp{world}",
-                           "mode": "bus-only (mixed_tracks not materialised)",
+                           "mode": "bus-only (mixed_tracks not materialised); full-contract mode: see `full_contract`",
+                           "range_check": "on in every timed step (device-side, asynchronous verdict; mst/modules.py:86-89)",
                            "launch": launch_note,
                            "l2": "inputs larger than L2 (134 MB of tracks per step, re-read every step)"},
-                "eager": {"ms_per_step": ms_eager_max / args.steps,
-                          "value": units / (ms_eager_max / 1e3 / args.steps), "unit": UNIT,
+                "eager": {"ms_per_step": ms_eager_max / steps,
+                          "value": units / (ms_eager_max / 1e3 / steps), "unit": UNIT,
                           "note": "same step launched eagerly from Python; the per-kernel times of `roofline` were "
                                   "taken over this region (`clocks`: samples inside this region and the graph-replay region)"},
+                "full_contract": {"ms_per_step": ms_full_max / steps_full, "steps": steps_full,
+                                  "value": units / (ms_full_max / 1e3 / steps_full), "unit": UNIT,
+                                  "algorithmic_bytes_per_track_sample": bytes_full,
+                                  "step_frac_of_hbm_roofline": bytes_full * samples / (ms_full_max / steps_full * 1e-3) / 1e9 / peak,
+                                  "note": "same step launched eagerly with mixed_tracks (B,2,N,T) materialised, as "
+                                          "mst/modules.py:314 returns it (268 MB more written per step)"},
                 "loss": step_loss,
-                "clocks": clocks, "gpu_launches": GPU_LAUNCHES_PER_STEP * args.steps,
+                "clocks": clocks, "gpu_launches": GPU_LAUNCHES_PER_STEP * steps,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms_max / args.steps,
+                        "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps,
                         "note": "pinned host tracks + parameters copied in every step (copy of step i+1 overlaps "
                                 "compute of step i), loss and parameter gradients copied out every step"},
                 "roofline": roof}
@@ -405,17 +453,11 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# our kernels per step: console forward 3 (2 x prepare, fused chain kernel), MRSTFT 13 (per resolution framing,
-# fused loss, reduction, gradient; one overlap-add for all), console backward 4 (2 chain kernels, 2 gradient
-# epilogues); cuFFT's 6 kernels and torch's glue kernels are not counted
-GPU_LAUNCHES_PER_STEP = 20
-
-# dram__bytes_read.sum + dram__bytes_write.sum of the track-backward kernel, one launch, from the
-# committed capture profiles/ncu_r1_summary.md (287.4 MB read + 30.6 MB written: the EQ-output and
-# section-state checkpoints forward leaves for backward come on top of the 151 MB algorithmic)
-TRAFFIC_TRACK_BWD_BYTES = 318.0e6
-# smsp__inst_executed.sum of the same launch (profiles/ncu_r1_summary.md)
-TRACK_BWD_WARP_INSTRUCTIONS = 344.7e6
+# our kernels per step: console forward 4 (2 x prepare, fused chain kernel, fx-bus range check), MRSTFT 13 (per
+# resolution framing, fused loss, reduction, gradient; one overlap-add for all), console backward 5 (master chain
+# kernel + epilogue, recursion-table prepare, track chain kernel + epilogue); cuFFT's 6 kernels and torch's glue
+# kernels are not counted
+GPU_LAUNCHES_PER_STEP = 22
 
 
 def main():
@@ -425,6 +467,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-seconds", type=float, default=1.0,
+                    help="lower bound on the device time of each timed region (more steps are run if needed)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -209,6 +209,7 @@ class AdvancedMixConsole(torch.nn.Module):
         # check_pending_ranges(); CUDA-graph capturable.  False: no test.
         self.check_ranges = True
         self._pending_ranges = []   # [(pinned int32 host tensor, event or None)]
+        self._capture_slots = []    # pinned words reserved for calls made during a CUDA-graph capture
 
     # ---- parameter plumbing (mst/modules.py:353-466) ----
     def _track_ranges(self):
@@ -330,7 +331,14 @@ class AdvancedMixConsole(torch.nn.Module):
                 _lib.check(lib.dmst_console_check_ranges(_ptr(fx), fx.shape[0], fx.shape[1], 500, _ptr(status),
                                                          ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
                            "dmst_console_check_ranges")
-            host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+            if capturing:
+                # pinned memory cannot be allocated while a stream is capturing: take a slot reserved beforehand
+                if not self._capture_slots:
+                    raise RuntimeError("AdvancedMixConsole(check_ranges='async') inside a CUDA-graph capture needs "
+                                       "console.reserve_capture_slots(n) before the capture (GraphedStep does this)")
+                host = self._capture_slots.pop()
+            else:
+                host = torch.empty(1, dtype=torch.int32, pin_memory=True)
             host.fill_(_lib.STATUS_OK)
             host.copy_(status[:1], non_blocking=True)
             ev = None
@@ -342,6 +350,11 @@ class AdvancedMixConsole(torch.nn.Module):
             self.check_pending_ranges(wait=False)
             if len(self._pending_ranges) > 64:
                 self.check_pending_ranges(wait=True)
+
+    def reserve_capture_slots(self, n: int = 8):
+        """Pinned host words for the verdicts of up to n forward() calls inside a CUDA-graph capture."""
+        while len(self._capture_slots) < n:
+            self._capture_slots.append(torch.empty(1, dtype=torch.int32, pin_memory=True))
 
     def check_pending_ranges(self, wait: bool = True):
         """Raise the reference's ValueError (mst/modules.py:86-89) for the oldest earlier forward() whose parameters
@@ -474,7 +487,7 @@ class BasicMixConsole(torch.nn.Module):
         return r
 
     def forward(self, tracks, track_params, fx_bus_params=None, master_bus_params=None, **flags):
-        if self.check_ranges:
+        if self.check_ranges is True:   # (synchronous test only; "async" is the advanced console's device-side form)
             lo = track_params.reshape(-1, 2).amin(0).detach().cpu()
             hi = track_params.reshape(-1, 2).amax(0).detach().cpu()
             for i, (effect, name) in enumerate((("input_gain", "gain_db"), ("stereo_panner", "pan"))):

@@ -12,10 +12,11 @@ can be captured once and replayed.
     tracks.copy_(next_batch); tp.data.copy_(...)          # refill the static inputs in place
     loss = step()                                          # replay; loss, tp.grad, mp.grad are static tensors
 
-The console's range check (`check_ranges`, one host read per call) cannot run inside a capture: the
-callable is warmed up eagerly first, with the check on if the caller left it on, and the check is
-switched off for the capture itself (parameters produced by a sigmoid are in range by construction,
-mst/modules.py:881-905).
+The console's synchronous range check (`check_ranges=True`, one host read per call) cannot run inside a
+capture: the callable is warmed up eagerly first, with the check as the caller left it, and for the capture
+itself a console whose check is on runs it in its asynchronous, device-side form (`check_ranges="async"`: the
+verdict of every replay lands in pinned host memory; `console.check_pending_ranges()` raises the reference's
+ValueError for it).
 """
 from typing import Callable, Iterable, Optional
 
@@ -29,7 +30,7 @@ class GraphedStep:
               replays) and returning a scalar loss tensor.
     params:   leaf tensors whose ``.grad`` the step produces; after every replay ``p.grad`` holds the
               gradient of that replay (a static tensor: copy it out before the next replay).
-    consoles: modules whose ``check_ranges`` is switched off during capture.
+    consoles: modules whose synchronous range check is replaced by the asynchronous one during capture.
     """
 
     def __init__(self, loss_fn: Callable[[], torch.Tensor], params: Iterable[torch.Tensor],
@@ -55,8 +56,10 @@ class GraphedStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         saved = [getattr(c, "check_ranges", None) for c in consoles]
         for c in consoles:
-            if hasattr(c, "check_ranges"):
-                c.check_ranges = False
+            if getattr(c, "check_ranges", False):
+                c.check_ranges = "async"
+                if hasattr(c, "reserve_capture_slots"):
+                    c.reserve_capture_slots()
         try:
             for p in self.params:
                 p.grad = None  # the captured backward allocates .grad from the graph's private pool

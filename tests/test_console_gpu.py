@@ -361,5 +361,15 @@ def test_graphed_step_replays_the_eager_step_bit_for_bit():
     assert torch.equal(loss.detach(), e2[0]) and torch.equal(tp.grad, e2[1]) and torch.equal(mp.grad, e2[2])
     with pytest.raises(ValueError, match="out of range"):
         con(x, tp.detach() + 1.0, fp, mp.detach(), use_fx_bus=False)
+    # inside the graph the range test runs in its device-side form: a replay on out-of-range parameters is reported
+    con.check_pending_ranges()
+    keep = tp.detach().clone()
+    tp.data[0, 1, 20] = 1.5
+    step()
+    with pytest.raises(ValueError, match="Parameter ratio of effect compressor is out of range."):
+        con.check_pending_ranges()
+    tp.data.copy_(keep)
+    step()
+    con.check_pending_ranges()
     with pytest.raises(RuntimeError, match="no CPU path"):
         GraphedStep(lambda: None, params=[torch.zeros(1, requires_grad=True)])

