@@ -366,6 +366,7 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
         int ctas = persistent_ctas(kern, kMasterBwdNT, smem);
         if (ctas <= 0) return DMST_EINVAL;
         if (ctas > fm.total) ctas = fm.total;
+        if (const char* e = getenv("DMST_MASTER_BWD_CTAS")) { const int c = atoi(e); if (c > 0 && c < ctas) ctas = c; }  // tuning aid
         ScopedTimer tm(2, stream);
         DMST_LAUNCH(kern, dim3(ctas), dim3(kMasterBwdNT), smem, stream, fm);
     }
