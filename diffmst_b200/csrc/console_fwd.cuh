@@ -31,19 +31,19 @@ struct FwdArgs {
     int* done;        // [B * track tiles]: tracks of the item that finished the time tile
 };
 
-struct FwdWork { int role, row, tile; };  // role 0: nothing, 1: track tile, 2: master tile
+struct FwdWork { int role, row, tile, b; };  // role 0: nothing, 1: track tile, 2: master tile; b = batch item of the row
 
 __device__ __forceinline__ FwdWork fwd_decode(const FwdArgs& f, int ticket) {
-    FwdWork w{0, 0, 0};
+    FwdWork w{0, 0, 0, 0};
     if (ticket >= f.total) return w;
     const int g = ticket / f.group, r = ticket - g * f.group;
     const int nm = f.B * f.R;
     if (r < nm) {  // master tiles of track time-tile g-lag, earlier tile first
         const int mi = r / f.B, b = r - mi * f.B;
         const int mt = (g - f.lag) * f.R + mi;
-        if (g >= f.lag && mt < f.m.ntiles) { w.role = 2; w.row = b; w.tile = mt; }
+        if (g >= f.lag && mt < f.m.ntiles) { w.role = 2; w.row = b; w.tile = mt; w.b = b; }
     } else if (g < f.t.ntiles) {
-        w.role = 1; w.row = r - nm; w.tile = g;
+        w.role = 1; w.row = r - nm; w.tile = g; w.b = w.row / f.t.N;
     }
     return w;
 }
@@ -102,7 +102,7 @@ __device__ __forceinline__ void fwd_prefetch(const FwdArgs& f, const FwdWork& w,
     }
     if (w.role == 1) {
         const ChainArgs& a = f.t;
-        const int b = w.row / a.N, n = w.row - b * a.N;
+        const int b = w.b, n = w.row - b * a.N;
         const int tbase = w.tile * TILE_T;
         const float* p = a.src + (long long)b * a.src_batch_stride + (long long)n * a.src_row_stride + tbase;
         const int valid = a.T - tbase;
@@ -143,12 +143,13 @@ struct FwdShared {
     float pre[kStateStride];           // predecessor's end states ([sec][ch][2], smoother at 24)
     unsigned premask;                  // which of them were already published at tile start
     int next;                          // next ticket of this CTA
+    FwdWork next_work;                 // ... decoded by the claiming thread (the integer divisions run once per tile)
 };
 
 // One (row, tile) of a chain.  Returns the next ticket of this CTA (claimed on the way, inputs prefetched).
 // CHK: spacing of the section-state checkpoints left for backward = thread chunk of the backward kernel of this role
 template <int NCH, int L, int NT, bool MASTER, int TILE_T, int CHK>
-__device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, const int row, const int tile,
+__device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, const int row, const int tile, const int row_b,
                                         float* ebuf, float* inbuf, const RowTab& tb, float* tab_next,
                                         FwdShared<NT>& sh) {
     constexpr int NW = NT / 32;
@@ -266,7 +267,7 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
             float zm1[NCH][NSUB], zm2[NCH][NSUB];                  // zero-state states at the checkpoints
             if (tid == 0) {
                 if (!MASTER && k == 1) claimed = atomicAdd(f.ticket, 1);
-                if (k == kNumSections - 2) sh.next = claimed;  // visible after this section's barrier
+                if (k == kNumSections - 2) { sh.next = claimed; sh.next_work = fwd_decode(f, claimed); }  // visible after this section's barrier
             }
             // zero-state pass over the thread chunk (transposed direct form II)
 #pragma unroll
@@ -352,12 +353,12 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
             }
         }
     } else {
-        if (tid == 0) sh.next = claimed;
+        if (tid == 0) { sh.next = claimed; sh.next_work = fwd_decode(f, claimed); }
         __syncthreads();  // the claimed ticket (and warp 0's prefetched states) visible to all
     }
     // Every thread is past a barrier that follows its reads of `inbuf`: start the next item's copies.
     const int next_ticket = sh.next;
-    fwd_prefetch<NT, TILE_T>(f, fwd_decode(f, next_ticket), inbuf, tab_next, tid);
+    fwd_prefetch<NT, TILE_T>(f, sh.next_work, inbuf, tab_next, tid);
 
     if (a.esave && !(a.flags & kChainComp)) {  // (with the compressor on, e is stored from the delay line below)
 #pragma unroll
@@ -461,7 +462,7 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
         __syncthreads();
         stage_out4<NT, TILE>(a.y + (long long)row * a.Tp + tbase, ebuf, a.Tp - tbase, true, tid);
         if (a.want_mixed) {
-            const int b = row / a.N, n = row - b * a.N;
+            const int b = row_b, n = row - b * a.N;
             stage_out4<NT, TILE>(a.mixed + ((long long)(b * 2 + 0) * a.N + n) * a.T + tbase, ebuf, a.T - tbase,
                                  a.user_vec_ok != 0, tid, tb.gL);
             stage_out4<NT, TILE>(a.mixed + ((long long)(b * 2 + 1) * a.N + n) * a.T + tbase, ebuf, a.T - tbase,
@@ -495,16 +496,16 @@ __global__ void __launch_bounds__(NT, 2) console_fwd_kernel(FwdArgs f) {
     float* ebuf = reinterpret_cast<float*>(smem_raw);
     float* inbuf = ebuf + fwd_ebuf_floats(TILE_T, f.t.lookahead, NT * L_M, f.m.lookahead);
     DMST_SHARED_ARRAY(float, s_tabf, 2 * (sizeof(RowTab) / 4));
-    DMST_SHARED_ARRAY(int, s_first, 1);
     DMST_SHARED_ARRAY(FwdShared<NT>, sh_p, 1);
     FwdShared<NT>& sh = sh_p[0];
     const int tid = threadIdx.x;
 
-    if (tid == 0) s_first[0] = atomicAdd(f.ticket, 1);
+    if (tid == 0) { sh.next = atomicAdd(f.ticket, 1); sh.next_work = fwd_decode(f, sh.next); }
     __syncthreads();
-    int cur = s_first[0];
+    int cur = sh.next;
+    FwdWork w = sh.next_work;
     int par = 0;
-    fwd_prefetch<NT, TILE_T>(f, fwd_decode(f, cur), inbuf, s_tabf, tid);
+    fwd_prefetch<NT, TILE_T>(f, w, inbuf, s_tabf, tid);
     int* signal = nullptr;  // completion counter of the track tile just processed
     while (true) {
         cp_async_wait_all();
@@ -512,22 +513,22 @@ __global__ void __launch_bounds__(NT, 2) console_fwd_kernel(FwdArgs f) {
         if (signal != nullptr && tid == 0) red_release_add(signal, 1);  // (cumulative over the barrier)
         signal = nullptr;
         if (cur >= f.total) break;
-        const FwdWork w = fwd_decode(f, cur);
         const RowTab& tb = *reinterpret_cast<const RowTab*>(s_tabf + par * (sizeof(RowTab) / 4));
         float* tab_next = s_tabf + (par ^ 1) * (sizeof(RowTab) / 4);
         int nxt;
         if (w.role == 1) {
-            nxt = fwd_tile<1, L_T, NT, false, TILE_T, CHK_T>(f, f.t, w.row, w.tile, ebuf, inbuf, tb, tab_next, sh);
-            signal = f.done + (long long)(w.row / f.t.N) * f.t.ntiles + w.tile;
+            nxt = fwd_tile<1, L_T, NT, false, TILE_T, CHK_T>(f, f.t, w.row, w.tile, w.b, ebuf, inbuf, tb, tab_next, sh);
+            signal = f.done + (long long)w.b * f.t.ntiles + w.tile;
         } else if (w.role == 2) {
-            nxt = fwd_tile<2, L_M, NT, true, TILE_T, CHK_M>(f, f.m, w.row, w.tile, ebuf, inbuf, tb, tab_next, sh);
+            nxt = fwd_tile<2, L_M, NT, true, TILE_T, CHK_M>(f, f.m, w.row, w.tile, w.b, ebuf, inbuf, tb, tab_next, sh);
         } else {
-            if (tid == 0) sh.next = atomicAdd(f.ticket, 1);
+            if (tid == 0) { sh.next = atomicAdd(f.ticket, 1); sh.next_work = fwd_decode(f, sh.next); }
             __syncthreads();
             nxt = sh.next;
-            fwd_prefetch<NT, TILE_T>(f, fwd_decode(f, nxt), inbuf, tab_next, tid);
+            fwd_prefetch<NT, TILE_T>(f, sh.next_work, inbuf, tab_next, tid);
         }
         cur = nxt;
+        w = sh.next_work;   // (stable until the next item's hand-off, several barriers away)
         par ^= 1;
     }
 }
