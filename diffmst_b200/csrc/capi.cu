@@ -60,6 +60,28 @@ int dmst_console_check_ranges(const float* params, int rows, int np, int base, i
     return DMST_LAST_ERROR();
 }
 
+// Hann-weighted overlap-add of one console window into the running mix (mst/utils.py:151-163): out[r, off + t] +=
+// win[r, t] * w(t), w = periodic Hann of length W (torch.hann_window), with the first half forced to 1 for the first window.
+__global__ void ola_hann_add_kernel(const float* win, long long win_stride, float* out, long long out_stride, int rows,
+                                    int n, int W, int first) {
+    const int r = blockIdx.y;
+    const float k = 6.283185307179586f / (float)W;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        float w = 0.5f - 0.5f * cosf(k * (float)t);
+        if (first && t < W / 2) w = 1.0f;
+        out[(long long)r * out_stride + t] += win[(long long)r * win_stride + t] * w;
+    }
+}
+int dmst_ola_hann_add(const float* window_mix, long long window_row_stride, float* out, long long out_row_stride,
+                      int rows, int n, int window_length, int first_window, void* stream) {
+    if (!window_mix || !out || rows <= 0 || n < 0 || window_length <= 0 || n > window_length) return DMST_EINVAL;
+    if (n == 0) return 0;
+    const int bx = (n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256;
+    DMST_LAUNCH(ola_hann_add_kernel, dim3(bx, rows), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), window_mix,
+                window_row_stride, out, out_row_stride, rows, n, window_length, first_window);
+    return DMST_LAST_ERROR();
+}
+
 int dmst_profile_enable(int max_records) {
 #ifndef DMST_EMULATE
     dmst::Profiler& p = dmst::profiler();

@@ -110,6 +110,13 @@ int dmst_console_backward(const float* tracks, long long tracks_batch_stride,
  * smallest code is the reference's first offender in its traversal order (track, fx bus, master bus). */
 int dmst_console_check_ranges(const float* params, int rows, int np, int base, int* status, void* stream);
 
+/* Sliding-window inference (mst/utils.py:121-166, run_diffmst): Hann-weighted overlap-add of one console window
+ * into the running mix on the device.  out[r, t] += window_mix[r, t] * w(t) for t < n <= window_length, rows = bs * 2;
+ * w = torch.hann_window(window_length) (periodic), its first half forced to 1 when first_window != 0
+ * (mst/utils.py:151-157).  `out` points at the window's first output sample. */
+int dmst_ola_hann_add(const float* window_mix, long long window_row_stride, float* out, long long out_row_stride,
+                      int rows, int n, int window_length, int first_window, void* stream);
+
 /* ---- measurement hooks (used by bench.py only) ----
  * dmst_profile_enable(n > 0): from now on every console chain-kernel launch is bracketed by a
  * pair of CUDA events on its stream (at most n per kernel kind); n <= 0 disables.

@@ -65,5 +65,19 @@ if len(nodes) > 1 and node >= 0:
     os.sched_setaffinity(0, ids)
     y = torch.empty(n, dtype=torch.float32).pin_memory(); y.fill_(1.0)   # first touch on the GPU's node
     run(y, f"NUMA-local pinned buffer (node {node})")
+# (d) write-combined pinned memory (cudaHostAllocWriteCombined): no cache snooping on the host side of the DMA
+try:
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so")
+    ptr = ctypes.c_void_p()
+    rc = rt.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(n * 4), ctypes.c_uint(0x04))   # cudaHostAllocWriteCombined
+    assert rc == 0, rc
+    buf = (ctypes.c_float * n).from_address(ptr.value)
+    z = torch.frombuffer(buf, dtype=torch.float32)
+    z.fill_(1.0)
+    run(z, f"write-combined pinned buffer (is_pinned={z.is_pinned()})")
+except Exception as e:
+    if rank == 0:
+        print("write-combined arm failed:", repr(e)[:200], flush=True)
 if world > 1:
     dist.destroy_process_group()

@@ -225,3 +225,36 @@ def test_peak_normalize_propagates_nan_and_mrstft_refuses_target_grad():
         loss_fn(a, b)
     with torch.no_grad():
         assert torch.isfinite(loss_fn(a, b))
+
+
+def test_sliding_window_inference_matches_reference_loop():
+    """mst/utils.py:121-166 (run_diffmst's sliding-window render) on the device against the reference's loop run with
+    the float64 oracle console on the CPU: windows every window/2, Hann weights (first half of the first window = 1),
+    ragged last window, overlap-add."""
+    from diffmst_b200 import AdvancedMixConsole, sliding_window_mix
+    g = torch.Generator().manual_seed(12)
+    W, total, N = 131072, 131072 + 65536 + 40000, 3   # (every window >= 32768 samples: below that the oracle's FFT method time-aliases)
+    tracks = torch.randn(1, N, total, generator=g) * 0.1
+    tp, fp, mp = torch.rand(1, N, 27, generator=g), torch.rand(1, 25, generator=g), torch.rand(1, 26, generator=g)
+    con = AdvancedMixConsole(SR).cuda()
+    got, tpd, fxd, mpd = sliding_window_mix(tracks.cuda(), tp.cuda(), fp.cuda(), mp.cuda(), con, window=W)
+    assert got.shape == (1, 2, total) and con.materialize_tracks is True
+    assert list(tpd.keys()) == ["input_fader", "parametric_eq", "compressor", "stereo_panner", "fx_bus"]
+
+    def reference_loop(dtype):
+        orc = OracleAdvancedMixConsole(SR)
+        out = torch.zeros(1, 2, total, dtype=dtype)
+        for i in range(0, total, W // 2):   # the reference's loop, verbatim in structure
+            win = orc(tracks[..., i:i + W].to(dtype), tp.to(dtype), fp.to(dtype), mp.to(dtype), **FLAGS)[1]
+            if win.shape[-1] < W:
+                win = torch.nn.functional.pad(win, (0, W - win.shape[-1]))
+            w = torch.hann_window(W, dtype=dtype)
+            if i == 0:
+                w[: W // 2] = 1.0
+            win = win * w
+            n = out[..., i:i + W].shape[-1]
+            out[..., i:i + W] += win[..., :n]
+        return out.numpy()
+    want, want32 = reference_loop(torch.float64), reference_loop(torch.float32)
+    b = 1.5 * max(1e-4, relmax(want32, want))
+    assert relmax(got.cpu().numpy(), want) <= b, (relmax(got.cpu().numpy(), want), b)
