@@ -346,7 +346,7 @@ class AdvancedMixConsole(torch.nn.Module):
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))
         self._pending_ranges.append((host, ev))
-        if len(self._pending_ranges) > 64:   # bounded: the oldest verdicts have long landed
+        if len(self._pending_ranges) > 64 and not capturing:   # bounded: the oldest verdicts have long landed
             self.check_pending_ranges(wait=False)
             if len(self._pending_ranges) > 64:
                 self.check_pending_ranges(wait=True)
@@ -449,7 +449,8 @@ class AdvancedMixConsole(torch.nn.Module):
         flags = _flags(use_track_input_fader, use_track_eq, use_track_compressor, use_track_panner,
                        use_fx_bus, use_master_bus, use_output_fader)
         if self.check_ranges == "async":
-            self.check_pending_ranges(wait=False)   # verdicts of earlier calls that have landed
+            if not torch.cuda.is_current_stream_capturing():   # (event queries are not allowed during a capture)
+                self.check_pending_ranges(wait=False)          # verdicts of earlier calls that have landed
         elif self.check_ranges:
             self._raise_if_out_of_range(track_params, fx_bus_params, master_bus_params)
         # two elementwise kernels per tensor instead of two per dictionary entry (156 upstream)

@@ -26,7 +26,7 @@ md = [f'# profiles/ - round {tag} (B200, ncu, `--clock-control none`)\n',
       'Workload: BASELINE configs[1] - AdvancedMixConsole fwd+bwd + MRSTFT, B=8, N=16, T=262144, float32, bus-only mode.\n',
       'Commands (under gpurun):\n```\n'
       f'ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step_{tag}.csv python scripts/prof_step.py 3\n'
-      f'ncu --set full --clock-control none --import-source on -k regex:"console_fwd|chain_bwd" -s 3 -c 3 -o gpurun_out/prof_{tag} python scripts/prof_once.py 8 16 262144 2\n'
+      f'ncu --set full --clock-control none --import-source on -k regex:"console_fwd|chain_bwd|track_bwd2" -s 3 -c 3 -o gpurun_out/prof_{tag} python scripts/prof_once.py 8 16 262144 2\n'
       'python scripts/sweep_eq_comp.py ; python tests/tools/conv_bench.py\npython bench.py --steps 50 --warmup 5 ; python bench.py --impl reference --steps 3 --warmup 1\n```\n',
       '## 1. Launch list of one step (ncu per-launch times are cold-cache and serialised: compare shares)\n',
       '| us | share | kernel |\n|---:|---:|---|']

@@ -12,7 +12,7 @@ fp = torch.rand(B, 25).cuda()
 mp = torch.rand(B, 26).cuda().requires_grad_(True)
 con = AdvancedMixConsole(44100).cuda()
 con.materialize_tracks = False
-con.check_ranges = False
+con.check_ranges = "async"
 probe = torch.randn(B, 2, T).cuda()
 for _ in range(reps):
     tp.grad = None; mp.grad = None

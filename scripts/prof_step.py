@@ -6,7 +6,7 @@ import bench
 from diffmst_b200 import AdvancedMixConsole, MRSTFTLoss, batch_stereo_peak_normalize
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 dev = torch.device("cuda", 0)
-con = AdvancedMixConsole(bench.SR).to(dev); con.materialize_tracks = False; con.check_ranges = False
+con = AdvancedMixConsole(bench.SR).to(dev); con.materialize_tracks = False; con.check_ranges = "async"
 loss_fn = MRSTFTLoss(**bench.RES)
 tracks, tp, fp, mp, tp2, mp2 = bench.make_inputs(torch, 0, bench.B, "cpu")
 tracks = tracks.to(dev); fp = fp.to(dev)

@@ -350,6 +350,9 @@ def test_graphed_step_replays_the_eager_step_bit_for_bit():
     e1 = eager(x)
     e2 = eager(x2)
     static_x = x.clone()
+    con.check_ranges = "async"      # pending verdicts of eager calls must not disturb a later capture
+    con(x, tp.detach(), fp, mp.detach(), use_fx_bus=False)
+    con.check_ranges = True
     step = GraphedStep(lambda: loss_fn(con(static_x, tp, fp, mp, use_fx_bus=False)[1], target), params=[tp, mp],
                        consoles=[con])
     assert con.check_ranges is True  # restored after the capture
