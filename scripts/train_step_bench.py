@@ -59,7 +59,7 @@ def main():
     reducer = BucketedGradAllReduce(model.parameters())
     if args.no_allreduce:
         reducer.world = 1
-    opt = torch.optim.Adam(model.parameters(), lr=1e-5, betas=(0.9, 0.999), foreach=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, betas=(0.9, 0.999), fused=True)   # (torch's fused CUDA Adam: one pass)
     g = torch.Generator().manual_seed(1000 + rank)   # every rank its own shard of the data
     tracks = (torch.randn(B, N, T, generator=g) * 0.1).to(dev)
     gen = torch.Generator(device=dev).manual_seed(2000 + rank)
