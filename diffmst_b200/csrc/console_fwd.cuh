@@ -180,6 +180,7 @@ __device__ __forceinline__ int fwd_tile(const FwdArgs& f, const ChainArgs& a, co
         s_pre[lane] = pv;
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (lane == 0) sh.premask = m;
+        __syncwarp();   // section 0 reads premask / s_pre in this warp before the first CTA barrier (racecheck)
     }
     // Claim the next work item early in the tile; the ticket stays in a register until it is handed to
     // the other threads a few barriers later, so the atomic's latency is never waited for.  (Not at the
