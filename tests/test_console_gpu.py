@@ -376,3 +376,42 @@ def test_graphed_step_replays_the_eager_step_bit_for_bit():
     con.check_pending_ranges()
     with pytest.raises(RuntimeError, match="no CPU path"):
         GraphedStep(lambda: None, params=[torch.zeros(1, requires_grad=True)])
+
+
+@pytest.mark.parametrize("shape,flagkw", [((1, 1, 3000), {}), ((2, 3, 36871), dict(use_track_compressor=False)),
+                                          ((1, 2, 40001), dict(use_track_eq=False)),
+                                          ((1, 4, 33000), dict(use_track_eq=False, use_track_compressor=False, use_master_bus=False)),
+                                          ((1, 2, 50000), dict(use_track_input_fader=False, use_output_fader=False))])
+def test_parameter_only_backward_flag_combinations(shape, flagkw):
+    """The training-path track backward (console_bwd2.cuh; taken when the tracks need no gradient) under every flag
+    combination, ragged / tiny / odd lengths, with a loss on BOTH outputs (mix and the panned tracks): against
+    float64 autograd of the oracle."""
+    from diffmst_b200 import AdvancedMixConsole
+    B, N, T = shape
+    g = torch.Generator().manual_seed(300 + T)
+    tracks = torch.randn(B, N, T, generator=g) * 0.1
+    tp, fp, mp = torch.rand(B, N, 27, generator=g), torch.rand(B, 25, generator=g), torch.rand(B, 26, generator=g)
+    probe = torch.randn(B, 2, T, generator=g)
+    probe_tracks = torch.randn(B, 2, N, T, generator=g) * 0.3
+    kw = dict(use_fx_bus=False); kw.update(flagkw)
+
+    def run(con, dt, dev):
+        tpc = tp.to(dev, dt).requires_grad_(True); mpc = mp.to(dev, dt).requires_grad_(True)
+        mixed, mix = con(tracks.to(dev, dt), tpc, fp.to(dev, dt), mpc, **kw)[:2]
+        ((mix * probe.to(dev, dt)).sum() + (mixed * probe_tracks.to(dev, dt)).sum()).backward()
+        gm = mpc.grad if mpc.grad is not None else torch.zeros_like(mpc)
+        return mix.detach().cpu().numpy(), tpc.grad.cpu().numpy(), gm.cpu().numpy()
+    ours = run(AdvancedMixConsole(SR).cuda(), torch.float32, "cuda")
+    o64 = run(OracleAdvancedMixConsole(SR), torch.float64, "cpu")
+    o32 = run(OracleAdvancedMixConsole(SR), torch.float32, "cpu")
+    alias = 0.0 if T >= 32768 else 3e-3   # (the oracle's FFT method time-aliases at short lengths)
+    assert relmax(ours[0], o64[0]) <= SLACK * max(TOL, relmax(o32[0], o64[0])) + alias
+    if T >= 32768:
+        for i, name in ((1, "track"), (2, "master")):
+            if np.abs(o64[i]).max() == 0:
+                assert np.abs(ours[i]).max() == 0
+            else:
+                b = max(GRAD_TOL, 3.0 * rell2(o32[i], o64[i]))
+                assert rell2(ours[i], o64[i]) <= b, (name, rell2(ours[i], o64[i]), b)
+    else:
+        assert np.isfinite(ours[1]).all() and np.isfinite(ours[2]).all()
