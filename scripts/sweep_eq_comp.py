@@ -14,7 +14,7 @@ except Exception:
 lib = _lib.lib()
 con = AdvancedMixConsole(44100).cuda()
 con.materialize_tracks = False
-con.check_ranges = False
+con.check_ranges = "async"
 rows = []
 NS = [int(v) for v in sys.argv[1].split(',')] if len(sys.argv) > 1 else [1, 8, 64]
 for N in NS:
