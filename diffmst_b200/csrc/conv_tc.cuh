@@ -918,7 +918,7 @@ constexpr uint32_t kWgABytes = (kWgBM / 32) * kWgSlabBytes;                // 4 
 __host__ __device__ constexpr int wg_groups(int BN) { return BN == 64 ? 2 : 1; }
 __host__ __device__ constexpr int wg_max_taps(int BN) { return BN == 64 ? 5 : 9; }
 __host__ __device__ constexpr uint32_t wg_stage_bytes(int BN) { return kWgABytes + wg_max_taps(BN) * (BN / 32) * kWgSlabBytes; }
-__host__ __device__ constexpr int wg_stages(int BN) { return BN == 64 ? 3 : 4; }
+__host__ __device__ constexpr int wg_stages(int BN) { return 3; (void)BN; }   // (4 stages of the 32-channel shape would leave no room for the epilogue staging)
 
 // MN-major TF32 operand.  32-bit MN-major operands exist in one shared-memory layout only: 128-byte rows whose
 // 32-byte chunks are XOR-ed with the row index mod 4 (UMMA layout type "128B swizzle, 32-byte base" = TMA swizzle
@@ -1022,6 +1022,9 @@ conv3x3_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dz, const __gr
     } else {
         const int quarter = warp & 3;
         const int co = m0 + quarter * 32 + lane;
+        // (same coalescing as the forward kernel's epilogue: a 32 x 32 block per warp staged in shared memory and read
+        // back transposed, so a warp store writes four whole 128-byte lines of the partial-sum tensor)
+        float* stage = reinterpret_cast<float*>(tiles + (size_t)kStages * kStageBytes) + (warp - 2) * 32 * kEpiRow;
         if (iters > 0) {
             mbar_wait(&acc_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1046,14 +1049,26 @@ conv3x3_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dz, const __gr
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
-            if (co < a.Cout) {
-                float* o = a.partial + (((size_t)split * 9 + tap0 + tl) * a.Cout + co) * a.Cin + n0 + c0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(o + j) = make_float4(__int_as_float((int)r[j]), __int_as_float((int)r[j + 1]),
-                                                                    __int_as_float((int)r[j + 2]), __int_as_float((int)r[j + 3]));
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(stage + lane * kEpiRow + j) =
+                    make_float4(__int_as_float((int)r[j]), __int_as_float((int)r[j + 1]), __int_as_float((int)r[j + 2]),
+                                __int_as_float((int)r[j + 3]));
+            __syncwarp();
+            {
+                const int co_base = m0 + quarter * 32;
+                float* obase = a.partial + ((size_t)split * 9 + tap0 + tl) * a.Cout * a.Cin + n0 + c0 + 4 * (lane & 7);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = 4 * it + (lane >> 3);
+                    if (co_base + row < a.Cout)
+                        *reinterpret_cast<float4*>(obase + (size_t)(co_base + row) * a.Cin) =
+                            *reinterpret_cast<const float4*>(stage + row * kEpiRow + 4 * (lane & 7));
+                }
             }
+            __syncwarp();
         }
+        (void)co;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -1182,7 +1197,7 @@ inline int conv3x3_wgrad(const float* x_padded, const float* dz_padded, float* d
     const WgradPlan w = wgrad_plan(P, Cin, Cout);
     // (a runtime call first: in a thread that has made none yet - an autograd worker - the driver call below would
     // find no current context)
-    const size_t smem = (size_t)wg_stages(w.bn) * wg_stage_bytes(w.bn) + 1024;
+    const size_t smem = (size_t)wg_stages(w.bn) * wg_stage_bytes(w.bn) + 1024 + kEpiBytes;
     int e = w.bn == 64
                 ? (int)cudaFuncSetAttribute(conv3x3_wgrad_tf32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                 : (int)cudaFuncSetAttribute(conv3x3_wgrad_tf32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
