@@ -354,9 +354,9 @@ __device__ __forceinline__ int bwd2_tile(const Bwd2Args& f, const int row, const
         if (ct > 0) em1 = ebuf[pLA + pidx4(ct * LC - 1)];
         else em1 = e_before_tile;
         const float* ub = dbuf + pidx4(ct * LC);
-        float2 nc0[SPG], nd2[SPG], k2[SPG];
+        float2 nc0[SPG], k2[SPG];
 #pragma unroll
-        for (int k = 0; k < SPG; ++k) { nc0[k] = ptab[k].nc0; nd2[k] = ptab[k].nd2; k2[k] = ptab[k].k2; }
+        for (int k = 0; k < SPG; ++k) { nc0[k] = ptab[k].nc0; k2[k] = ptab[k].k2; }
         // zero-state pass over the chunk, last sample first (.x: poles, .y: zeros)
         float2 s[SPG], vv[SPG];
 #pragma unroll
@@ -425,7 +425,9 @@ __device__ __forceinline__ int bwd2_tile(const Bwd2Args& f, const int row, const
             mat2_apply_acc2(ptab[k].Ppow[31 - lane], c1, c2, x1[k], x2[k]);
         }
         // true pass fused with the correlations: accS = sum (e[n-1] g, e[n] h), accV = sum (e[n-1] vg, e[n] vh),
-        // accW = sum e[n] wh
+        // accW = sum e[n] wh with wh[n] = vh[n] - vh[n+1] the second difference.  Summed by parts it is
+        // sum (e[n] - e[n-1]) vh[n]: the boundary terms e[last] vh[last+1] - e[first-1] vh[first] of neighbouring
+        // chunks (and tiles) cancel, e[-1] = 0 and vh = 0 after the end of the signal, so wh is never formed
         float2 accS[SPG], accV[SPG];
         float accW[SPG];
 #pragma unroll
@@ -439,15 +441,14 @@ __device__ __forceinline__ int bwd2_tile(const Bwd2Args& f, const int row, const
                 const int i = 4 * i4 + j;
                 const float2 u2 = make_float2(uu[j], uu[j]);
                 const float2 ee = make_float2((i > 0) ? e[i > 0 ? i - 1 : 0] : em1, e[i]);
+                const float de = ee.y - ee.x;
 #pragma unroll
                 for (int k = 0; k < SPG; ++k) {
-                    const float2 t = fma2(nc0[k], x1[k], u2);
-                    const float2 w = fma2(nd2[k], x2[k], t);   // second difference v[n] - v[n+1]: off the recurrence
-                    x2[k] = fma2(k2[k], x2[k], t);
+                    x2[k] = fma2(k2[k], x2[k], fma2(nc0[k], x1[k], u2));
                     x1[k] = add2(x1[k], x2[k]);
                     accS[k] = fma2(ee, x1[k], accS[k]);
                     accV[k] = fma2(ee, x2[k], accV[k]);
-                    accW[k] = fmaf(ee.y, w.y, accW[k]);
+                    accW[k] = fmaf(de, x2[k].y, accW[k]);
                 }
             }
         }
