@@ -64,6 +64,10 @@ def lib():
     l.dmst_mrstft_workspace_bytes.argtypes = [ctypes.POINTER(MrstftCfg), i, i]
     l.dmst_mrstft_forward.restype = i
     l.dmst_mrstft_forward.argtypes = [vp, ll, vp, ll, vp, ctypes.POINTER(MrstftCfg), i, i, vp, vp, vp, sz, vp]
+    l.dmst_mrstft_forward_keep.restype = i
+    l.dmst_mrstft_forward_keep.argtypes = [vp, ll, vp, ll, vp, ctypes.POINTER(MrstftCfg), i, i, vp, vp, vp, sz, vp]
+    l.dmst_mrstft_backward.restype = i
+    l.dmst_mrstft_backward.argtypes = [vp, ctypes.POINTER(MrstftCfg), i, i, vp, vp, vp, sz, vp]
     l.dmst_afl_workspace_bytes.restype = sz
     l.dmst_afl_workspace_bytes.argtypes = [i, i, i, i]
     fp5 = ctypes.POINTER(ctypes.c_float)

@@ -138,8 +138,29 @@ int dmst_mrstft_forward(const float* x, long long x_row_stride, const float* y, 
                         const float* windows, const dmst_mrstft_cfg* cfg, int rows, int T, float* loss,
                         float* grad_x, void* workspace, size_t workspace_bytes, void* stream) {
 #ifndef DMST_EMULATE
-    return dmst::mrstft_run(x, x_row_stride, y, y_row_stride, windows, cfg, rows, T, loss, grad_x, workspace,
-                            workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+    return dmst::mrstft_run(x, x_row_stride, y, y_row_stride, windows, cfg, rows, T, loss, loss ? loss + 1 : nullptr,
+                            grad_x, false, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+#else
+    return DMST_EINVAL;
+#endif
+}
+
+int dmst_mrstft_forward_keep(const float* x, long long x_row_stride, const float* y, long long y_row_stride,
+                             const float* windows, const dmst_mrstft_cfg* cfg, int rows, int T, float* loss,
+                             float* terms, void* workspace, size_t workspace_bytes, void* stream) {
+#ifndef DMST_EMULATE
+    return dmst::mrstft_run(x, x_row_stride, y, y_row_stride, windows, cfg, rows, T, loss, terms, nullptr, true,
+                            workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+#else
+    return DMST_EINVAL;
+#endif
+}
+
+int dmst_mrstft_backward(const float* windows, const dmst_mrstft_cfg* cfg, int rows, int T, const float* grad_loss,
+                         float* grad_x, void* workspace, size_t workspace_bytes, void* stream) {
+#ifndef DMST_EMULATE
+    return dmst::mrstft_backward_run(windows, cfg, rows, T, grad_loss, grad_x, workspace, workspace_bytes,
+                                     reinterpret_cast<cudaStream_t>(stream));
 #else
     return DMST_EINVAL;
 #endif

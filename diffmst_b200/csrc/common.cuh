@@ -144,6 +144,15 @@ __device__ __forceinline__ void wait_flag_ge(const int* p, int v, bool skip = fa
     }
 }
 
+// Programmatic dependent launch: lets the next kernel of the stream (launched with launch_dependent, console_host.cuh)
+// start while this grid is still running.  The dependent must not rely on this grid's completion: it synchronises
+// with it through release / acquire flags.
+__device__ __forceinline__ void griddep_launch_dependents() {
+#ifndef DMST_EMULATE
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 // ---------------------------------------------------------------------------------
 // "Flag in data" mailboxes for the chained section states: a value and its validity tag travel
 // in one aligned 8-byte word, so a consumer needs a single L2 round trip and the producer needs

@@ -27,6 +27,8 @@
 namespace dmst {
 
 constexpr int kBFlagComp = 1;  // reverse smoother state + dhead halo published (section states use mailboxes)
+constexpr int kBFlagDone = 2;  // master: the tile's bus gradient is stored (the track kernel, launched as a programmatic
+                               // dependent, consumes it while later master tiles are still in flight)
 
 struct BwdArgs {
     ChainArgs a;
@@ -656,6 +658,7 @@ __device__ __forceinline__ int bwd_tile(const BwdArgs& f, const int row, const i
     const bool late_hand_off = !(a.flags & kChainEq);  // no EQ adjoint: the area was in use until here
     if (late_hand_off && tid == 0) sh.next = claimed;
     __syncthreads();
+    if (MASTER && tid == 0) st_release(my_flag, kBFlagDone);   // (cumulative over the barrier: every thread's dbus stores)
     if (late_hand_off) bwd_prefetch<NCH, L, NT, MASTER>(f, sh.next, area, tab_next, tid);
     if (tid < kGradCount) {
         float s = 0.0f;
@@ -681,6 +684,7 @@ __global__ void __launch_bounds__(NT, 1) chain_bwd_kernel(BwdArgs f) {
     Shared& sh = sh_p[0];
     const int tid = threadIdx.x;
 
+    if (MASTER) griddep_launch_dependents();   // every master CTA is resident: the track kernel may fill the other SMs
     if (tid == 0) s_first[0] = atomicAdd(f.ticket, 1);
     __syncthreads();
     int cur = s_first[0];

@@ -58,7 +58,22 @@ struct Bwd2Args {
     const EqBwdTab* etab;   // [nrows]
     int fwd_ntiles;         // forward tiles per row
     int fwd_ratio;          // tiles of this kernel per forward tile (forward tile = fwd_ratio * NT * L samples)
+    // the master kernel may still be running (programmatic dependent launch): its per-tile flags say which parts
+    // of the bus gradient are stored
+    const int* mflag;       // [B * m_ntiles], or null: the bus gradient is complete
+    int m_ntiles, m_tile_shift;   // master tiles per row, log2(master tile)
 };
+
+// Wait (one thread) until the master kernel has stored the bus gradient over the samples of work item (bb, tile)
+template <int TILE>
+__device__ __forceinline__ void bwd2_wait_bus_gradient(const Bwd2Args& f, int ticket, int tile, int bb) {
+    if (!f.mflag || ticket >= f.b.total) return;
+    const bool nowait = (f.b.a.flags & kChainDebugNoWait) != 0;
+    const int m0 = (tile * TILE) >> f.m_tile_shift;
+    int m1 = (tile * TILE + TILE - 1) >> f.m_tile_shift;
+    if (m1 > f.m_ntiles - 1) m1 = f.m_ntiles - 1;
+    for (int m = m0; m <= m1; ++m) wait_flag_ge(f.mflag + bb * f.m_ntiles + m, kBFlagDone, nowait);
+}
 
 // (row, tile) of a ticket: tiles in reverse time order, rows fastest
 __device__ __forceinline__ void bwd2_decode(const Bwd2Args& f, int ticket, int& row, int& tile, int& bb) {
@@ -336,7 +351,11 @@ __device__ __forceinline__ int bwd2_tile(const Bwd2Args& f, const int row, const
         const int idx = sl == 0 ? kGradMakeup : (sl == 1 ? kGradGin : (sl == 2 ? kGradGL : kGradGR));
         if ((lane & 7) == 0) s_part[warp * kGradCount + idx] = t;
     }
-    if (tid == 0) { sh.next = claimed; bwd2_decode(f, claimed, sh.next_row, sh.next_tile, sh.next_bb); }
+    if (tid == 0) {
+        sh.next = claimed;
+        bwd2_decode(f, claimed, sh.next_row, sh.next_tile, sh.next_bb);
+        bwd2_wait_bus_gradient<TILE>(f, claimed, sh.next_tile, sh.next_bb);   // before the barrier that precedes the prefetch
+    }
 
     // ------------------------------ phase 2: EQ coefficient gradients ------------------------------
     if (has_eq) {
@@ -486,6 +505,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1) track_bwd2_kernel(Bwd
     if (tid == 0) {
         sh.next = atomicAdd(f.b.ticket, 1);
         bwd2_decode(f, sh.next, sh.next_row, sh.next_tile, sh.next_bb);
+        bwd2_wait_bus_gradient<NT * L>(f, sh.next, sh.next_tile, sh.next_bb);
     }
     __syncthreads();
     int cur = sh.next, row = sh.next_row, tile = sh.next_tile;

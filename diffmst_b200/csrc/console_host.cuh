@@ -35,6 +35,12 @@ static_assert((1 << kTrackBwd2Shift) == kTrackBwd2Tile, "power-of-two tile");
 constexpr int kTrackTile = kTrackFwdL * kTrackFwdNT;
 static_assert(kTrackTile % kTrackBwd2Tile == 0, "backward tiles nest in forward tiles");
 constexpr int kMasterTile = kMasterL * kMasterNT;
+constexpr int kMasterTileShift = 12;
+static_assert((1 << kMasterTileShift) == kMasterTile, "power-of-two master tile");
+// CTAs of the master backward kernel per bus while the track kernel runs beside it (see console_backward): four
+// tiles of a bus in flight keep its chain of tiles busy (measured on B200, batch 8: 16 CTAs 1.46 ms per step,
+// 24 1.236, 32 1.198, 48 1.204, 64 1.207, all 148 1.217; without the overlap 1.239)
+constexpr int kMasterBwdOverlapCtasPerBus = 4, kMasterBwdOverlapMinCtas = 16;
 static_assert(kTrackFwdL * kTrackFwdNT == kTrackBwdL * kTrackBwdNT, "forward/backward tiles must agree");
 static_assert(kTrackBwdL == kBwdChunk && kTrackFwdL % kBwdChunk == 0, "checkpoint spacing");
 
@@ -203,6 +209,24 @@ inline int persistent_ctas(Kernel kern, int threads, size_t smem) {
     return sms * per_sm;
 #endif
 }
+// Launch `kern` as a programmatic dependent of the kernel launched just before it on `stream`: it may start as soon
+// as every CTA of that kernel has executed griddep_launch_dependents() (or exited) and runs beside it.  Everything
+// launched before that kernel has completed; what that kernel itself produces must be consumed through flags.
+template <class Kernel, class Arg>
+inline void launch_dependent(Kernel kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Arg& arg) {
+#ifdef DMST_EMULATE
+    DMST_LAUNCH(kern, grid, block, smem, stream, arg);
+#else
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, arg);
+#endif
+}
 inline size_t bwd_smem_bytes(int nch, int tile, int la, int nt, bool master) {
     // per-tile buffer area (+ the forward lane carry-ins of a chain without checkpoints)
     return (size_t)(bwd_area_floats(nch, tile, la) + (master ? 12 * nch * nt : 0)) * 4;
@@ -359,25 +383,6 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
     am.user_vec_ok = aligned16(gmix) && (k.T % 4 == 0);
     fm.total = am.nrows * am.ntiles; fm.ticket = w.header + 2;
     fm.area = bwd_area_floats(2, kMasterTile, k.la_m);
-    {
-        auto kern = chain_bwd_kernel<2, kMasterBwdL, kMasterBwdNT, true>;
-        const size_t smem = bwd_smem_bytes(2, kMasterTile, k.la_m, kMasterBwdNT, true);
-        DMST_CHECK(DMST_SET_SMEM(kern, smem));
-        int ctas = persistent_ctas(kern, kMasterBwdNT, smem);
-        if (ctas <= 0) return DMST_EINVAL;
-        if (ctas > fm.total) ctas = fm.total;
-        if (const char* e = getenv("DMST_MASTER_BWD_CTAS")) { const int c = atoi(e); if (c > 0 && c < ctas) ctas = c; }  // tuning aid
-        ScopedTimer tm(2, stream);
-        DMST_LAUNCH(kern, dim3(ctas), dim3(kMasterBwdNT), smem, stream, fm);
-    }
-    if (gmp && k.master_params) {
-        EpilogueArgs e;
-        memset(&e, 0, sizeof(e));
-        e.params = k.master_params; e.rows = k.B; e.np = DMST_NUM_MASTER_PARAMS; e.kind = 2;
-        for (int i = 0; i < DMST_NUM_MASTER_PARAMS; ++i) { e.lo[i] = k.ranges->master_lo[i]; e.hi[i] = k.ranges->master_hi[i]; }
-        e.sr = (double)k.sr; e.partial = w.m_partial; e.ntiles = w.nt_master; e.flags = am.flags; e.grad = gmp;
-        DMST_LAUNCH(grad_epilogue_kernel, dim3(e.rows), dim3(64), 0, stream, e);
-    }
     fill_chain(at, k, false, w);
     at.gout = w.dbus; at.gmixed = gmixed;
     at.gsrc = (k.flags & DMST_WANT_GRAD_TRACKS) ? gtracks : nullptr;
@@ -385,9 +390,39 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
     at.tab = w.track_tab_b;
     ft.total = at.nrows * at.ntiles; ft.ticket = w.header + 3;
     ft.area = bwd_area_floats(1, kTrackTile, k.la_t);
+    const bool params_only = !(k.flags & DMST_WANT_GRAD_TRACKS);
+    // Parameter gradients only (training): the track kernel is launched as a programmatic dependent of the master
+    // kernel.  The master chain is latency bound (B chains of tiles, each hop a round trip through L2): it gets a
+    // fraction of the SMs, the track kernel starts on the others at once and follows the master's per-tile flags.
+    static const bool overlap_env = !(getenv("DMST_BWD_OVERLAP") && getenv("DMST_BWD_OVERLAP")[0] == '0');   // tuning aid
+    const bool overlap = overlap_env && !profiler().enabled;   // (per-kernel timing brackets each kernel with events: serial)
+    if (params_only && (at.flags & kChainEq)) {   // (before the master kernel: nothing may sit between it and its dependent)
+        PrepareBwdArgs pb;
+        memset(&pb, 0, sizeof(pb));
+        pb.params = k.track_params; pb.rows = at.nrows; pb.np = DMST_NUM_TRACK_PARAMS; pb.sr = (double)k.sr; pb.tab = w.track_etab;
+        for (int i = 0; i < DMST_NUM_TRACK_PARAMS; ++i) { pb.lo[i] = k.ranges->track_lo[i]; pb.hi[i] = k.ranges->track_hi[i]; }
+        DMST_LAUNCH(prepare_bwd_kernel, dim3(pb.rows), dim3(kNumRec * 32), 0, stream, pb);
+    }
+    {
+        auto kern = chain_bwd_kernel<2, kMasterBwdL, kMasterBwdNT, true>;
+        const size_t smem = bwd_smem_bytes(2, kMasterTile, k.la_m, kMasterBwdNT, true);
+        DMST_CHECK(DMST_SET_SMEM(kern, smem));
+        const int max_ctas = persistent_ctas(kern, kMasterBwdNT, smem);
+        if (max_ctas <= 0) return DMST_EINVAL;
+        int ctas = max_ctas;
+        if (params_only && overlap) {
+            ctas = kMasterBwdOverlapCtasPerBus * am.nrows;
+            if (ctas < kMasterBwdOverlapMinCtas) ctas = kMasterBwdOverlapMinCtas;
+            if (ctas > max_ctas) ctas = max_ctas;
+        }
+        if (const char* e = getenv("DMST_MASTER_BWD_CTAS")) { const int c = atoi(e); if (c > 0) ctas = c < max_ctas ? c : max_ctas; }  // tuning aid
+        if (ctas > fm.total) ctas = fm.total;
+        ScopedTimer tm(2, stream);
+        DMST_LAUNCH(kern, dim3(ctas), dim3(kMasterBwdNT), smem, stream, fm);
+    }
     int epilogue_tiles = w.nt_track;
-    if (!(k.flags & DMST_WANT_GRAD_TRACKS)) {
-        // parameter gradients only (training): commuting-sections formulation, needs only the EQ-output checkpoint
+    if (params_only) {
+        // commuting-sections formulation, needs only the EQ-output checkpoint
         Bwd2Args f2;
         memset(&f2, 0, sizeof(f2));
         f2.b = ft;
@@ -396,14 +431,8 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
         f2.etab = w.track_etab;
         f2.fwd_ntiles = w.nt_track;
         f2.fwd_ratio = kTrackTile / kTrackBwd2Tile;
+        f2.mflag = w.m_bflag; f2.m_ntiles = w.nt_master; f2.m_tile_shift = kMasterTileShift;
         epilogue_tiles = w.nt_track_b2;
-        if (at.flags & kChainEq) {
-            PrepareBwdArgs pb;
-            memset(&pb, 0, sizeof(pb));
-            pb.params = k.track_params; pb.rows = at.nrows; pb.np = DMST_NUM_TRACK_PARAMS; pb.sr = (double)k.sr; pb.tab = w.track_etab;
-            for (int i = 0; i < DMST_NUM_TRACK_PARAMS; ++i) { pb.lo[i] = k.ranges->track_lo[i]; pb.hi[i] = k.ranges->track_hi[i]; }
-            DMST_LAUNCH(prepare_bwd_kernel, dim3(pb.rows), dim3(kNumRec * 32), 0, stream, pb);
-        }
         auto kern = track_bwd2_kernel<kTrackBwd2L, kTrackBwd2NT>;
         const size_t smem = bwd_smem_bytes(1, kTrackBwd2Tile, k.la_t, kTrackBwd2NT, false);
         DMST_CHECK(DMST_SET_SMEM(kern, smem));
@@ -411,7 +440,8 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
         if (ctas <= 0) return DMST_EINVAL;
         if (ctas > f2.b.total) ctas = f2.b.total;
         ScopedTimer tm(3, stream);
-        DMST_LAUNCH(kern, dim3(ctas), dim3(kTrackBwd2NT), smem, stream, f2);
+        if (overlap) launch_dependent(kern, dim3(ctas), dim3(kTrackBwd2NT), smem, stream, f2);
+        else DMST_LAUNCH(kern, dim3(ctas), dim3(kTrackBwd2NT), smem, stream, f2);
     } else {
         auto kern = chain_bwd_kernel<1, kTrackBwdL, kTrackBwdNT, false>;
         const size_t smem = bwd_smem_bytes(1, kTrackTile, k.la_t, kTrackBwdNT, false);
@@ -421,6 +451,14 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
         if (ctas > ft.total) ctas = ft.total;
         ScopedTimer tm(3, stream);
         DMST_LAUNCH(kern, dim3(ctas), dim3(kTrackBwdNT), smem, stream, ft);
+    }
+    if (gmp && k.master_params) {
+        EpilogueArgs e;
+        memset(&e, 0, sizeof(e));
+        e.params = k.master_params; e.rows = k.B; e.np = DMST_NUM_MASTER_PARAMS; e.kind = 2;
+        for (int i = 0; i < DMST_NUM_MASTER_PARAMS; ++i) { e.lo[i] = k.ranges->master_lo[i]; e.hi[i] = k.ranges->master_hi[i]; }
+        e.sr = (double)k.sr; e.partial = w.m_partial; e.ntiles = w.nt_master; e.flags = am.flags; e.grad = gmp;
+        DMST_LAUNCH(grad_epilogue_kernel, dim3(e.rows), dim3(64), 0, stream, e);
     }
     {
         EpilogueArgs e;

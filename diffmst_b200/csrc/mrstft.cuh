@@ -15,7 +15,17 @@ namespace dmst {
 
 #ifndef DMST_EMULATE   // (cuFFT-fed: not part of the host-emulated build)
 constexpr int kMrBlock = 256;
-constexpr int kMrItemsPerBlock = 4096;  // spectrum elements per block
+constexpr int kMrLoadsInFlight = 4;      // independent 8-byte loads per thread and operand
+// Spectrum elements per block of the loss kernel: the (blocks_per_row, rows) grid is sized to ONE wave of
+// 148 SMs x 8 resident blocks (a second, partial wave cost 25 % of the kernel at the headline shape)
+inline int mr_items_per_block(int per_row, int rows) {
+    constexpr int kStep = kMrBlock * kMrLoadsInFlight;
+    int bpr = (148 * 8) / (rows > 0 ? rows : 1);
+    if (bpr < 1) bpr = 1;
+    int items = (per_row + bpr - 1) / bpr;
+    items = ((items + kStep - 1) / kStep) * kStep;
+    return items < 4 * kStep ? 4 * kStep : items;
+}
 
 // ---------------------------------------------------------------------------------
 // Framing with 128-bit accesses: thread g handles samples [4*i4, 4*i4+4) of frame f of one row.
@@ -59,24 +69,61 @@ __global__ void frame4_kernel(Frame4Args a) {
     *reinterpret_cast<float4*>(o) = make_float4(xv.x * wv.x, xv.y * wv.y, xv.z * wv.z, xv.w * wv.w);
 }
 
+// MUFU reciprocal square root and log2 (arguments here are clamped at eps > 0, never subnormal):
+// |X| = p * rsqrt(p) and 1/|X| = rsqrt(p) are good to 2 ulp, log2 to 2^-22 absolute near 1 (2 ulp elsewhere):
+// three orders of magnitude inside the 1e-4 of the loss, and these two kernels stay bound by HBM
+// instead of by the issue rate (the IEEE sqrtf / logf / division sequences cost ~80 instructions per bin)
+__device__ __forceinline__ float fast_rsqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_log2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Second stage of the reductions and the loss terms of one resolution (run by the block of mr_loss_kernel that
+// finishes last): warp w sums the block partials of rows w, w+nwarps, ... in float64 (fixed assignment of
+// partials to lanes + fixed shuffle tree => deterministic), then warp 0 forms the terms and the gradient coefficients.
+struct MrFinalArgs {
+    const float* partial;
+    int blocks_per_row;
+    double* rowsum;     // [rows][4] scratch
+    int rows, per_row;
+    float w_sc, w_log, w_lin;
+    int n_res;
+    float* res_loss;    // [4]: this resolution's contribution to the total, then its sc, log, lin terms
+    float* row_coef;    // [rows]: d(total)/d|X| coefficient of (|X|-|Y|) for the SC term
+    float* scal;        // [2]: coefficient of sign(log) / |X| and of sign(lin)
+};
 struct MrLossArgs {
     const float2* X;  // rows x frames x bins
     const float2* Y;
     int rows, per_row;   // per_row = frames * bins
-    int blocks_per_row;
+    int blocks_per_row, items_per_block;
     float eps;
     float* partial;      // [rows][blocks_per_row][4]: sum (|Y|-|X|)^2, sum |Y|^2, sum |log|, sum |lin|
+    unsigned* done;      // blocks finished (zero at launch; the last block resets it)
+    MrFinalArgs fin;
 };
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ void mr_final(const MrFinalArgs& a);
 
 // grid: (blocks_per_row, rows)
 __global__ void mr_loss_kernel(MrLossArgs a) {
-    DMST_SHARED_ARRAY(float, sh, 32);
+    DMST_SHARED_ARRAY(float, sh, 33);
     const int row = blockIdx.y;
     const long long base = (long long)row * a.per_row;
-    const int begin = blockIdx.x * kMrItemsPerBlock;
-    const int end = min(begin + kMrItemsPerBlock, a.per_row);
+    const int begin = blockIdx.x * a.items_per_block;
+    const int end = min(begin + a.items_per_block, a.per_row);
     float s_d2 = 0.f, s_y2 = 0.f, s_log = 0.f, s_lin = 0.f;
-    constexpr int U = 4;  // independent loads in flight per thread
+    constexpr int U = kMrLoadsInFlight;
     for (int i0 = begin + threadIdx.x; i0 < end; i0 += U * kMrBlock) {
         float2 x[U], y[U];
 #pragma unroll
@@ -89,47 +136,39 @@ __global__ void mr_loss_kernel(MrLossArgs a) {
             if (i0 + u * kMrBlock >= end) continue;
             const float px = fmaxf(fmaf(x[u].x, x[u].x, x[u].y * x[u].y), a.eps);
             const float py = fmaxf(fmaf(y[u].x, y[u].x, y[u].y * y[u].y), a.eps);
-            const float mx = sqrtf(px), my = sqrtf(py);
-            const float d = my - mx;
+            // (__fmul_rn: no contraction into an FMA, so that |Y| - |X| is exactly 0 for identical spectra)
+            const float d = __fmul_rn(py, fast_rsqrt(py)) - __fmul_rn(px, fast_rsqrt(px));   // |Y| - |X|
             s_d2 = fmaf(d, d, s_d2);
             s_y2 += py;
-            s_log += fabsf(0.5f * (logf(px) - logf(py)));
+            s_log += fabsf(fast_log2(px) - fast_log2(py));
             s_lin += fabsf(d);
         }
     }
+    s_log *= 0.5f * 0.6931471805599453f;   // log|X| - log|Y| = ln2 / 2 * (log2 px - log2 py)
     float* out = a.partial + ((long long)row * a.blocks_per_row + blockIdx.x) * 4;
     float r;
     r = block_sum(s_d2, sh); if (threadIdx.x == 0) out[0] = r;
     r = block_sum(s_y2, sh); if (threadIdx.x == 0) out[1] = r;
     r = block_sum(s_log, sh); if (threadIdx.x == 0) out[2] = r;
     r = block_sum(s_lin, sh); if (threadIdx.x == 0) out[3] = r;
+    // the block that finishes last reduces the partials (threadFenceReduction pattern)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned prev = atomicAdd(a.done, 1u);
+        sh[32] = (prev == total - 1) ? 1.0f : 0.0f;
+        if (prev == total - 1) { *a.done = 0u; __threadfence(); }   // ready for the next launch
+    }
+    __syncthreads();
+    if (sh[32] != 0.0f) mr_final(a.fin);
 }
 
-// Second stage of the reductions and the loss terms of one resolution, one block: warp w sums the
-// block partials of rows w, w+nwarps, ... in float64 (fixed assignment of partials to lanes + fixed
-// shuffle tree => deterministic), then thread 0 forms the terms and the gradient coefficients.
-struct MrFinalArgs {
-    const float* partial;
-    int blocks_per_row;
-    double* rowsum;     // [rows][4] scratch
-    int rows, per_row;
-    float w_sc, w_log, w_lin;
-    int n_res;
-    float* res_loss;    // [4]: this resolution's contribution to the total, then its sc, log, lin terms
-    float* row_coef;    // [rows]: d(total)/d|X| coefficient of (|X|-|Y|) for the SC term
-    float* scal;        // [2]: coefficient of sign(log) / |X| and of sign(lin)
-};
-__device__ __forceinline__ double warp_sum_f64(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__global__ void mr_final_kernel(MrFinalArgs a) {
+__device__ void mr_final(const MrFinalArgs& a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int row = warp; row < a.rows; row += nwarps) {
         double s[4] = {0.0, 0.0, 0.0, 0.0};
         for (int b = lane; b < a.blocks_per_row; b += 32) {
-            const float4 p = __ldg(reinterpret_cast<const float4*>(a.partial + ((long long)row * a.blocks_per_row + b) * 4));
+            const float4 p = __ldcg(reinterpret_cast<const float4*>(a.partial + ((long long)row * a.blocks_per_row + b) * 4));
             s[0] += p.x; s[1] += p.y; s[2] += p.z; s[3] += p.w;
         }
 #pragma unroll
@@ -178,37 +217,39 @@ __global__ void mr_grad_kernel(MrGradArgs a) {
     const int per_row = a.frames * a.bins;
     const long long base = (long long)row * per_row;
     const int i0 = blockIdx.x * (kMrBlock * kMrGradU) + threadIdx.x;
-    const float rc = __ldg(a.row_coef + row), c_log = __ldg(a.scal), c_lin = __ldg(a.scal + 1);
+    const float rc = __ldg(a.row_coef + row), c_log = a.use_log ? __ldg(a.scal) : 0.0f, c_lin = a.use_lin ? __ldg(a.scal + 1) : 0.0f;
     float2 x[kMrGradU], y[kMrGradU];
 #pragma unroll
     for (int u = 0; u < kMrGradU; ++u) {
         const int i = i0 + u * kMrBlock;
         if (i < per_row) { x[u] = a.X[base + i]; y[u] = __ldg(a.Y + base + i); }
     }
+    int bin = i0 % a.bins;   // one division per thread; the other elements step by the block size
 #pragma unroll
     for (int u = 0; u < kMrGradU; ++u) {
         const int i = i0 + u * kMrBlock;
-        if (i >= per_row) continue;
-        const int bin = i % a.bins;
-        const float px_raw = fmaf(x[u].x, x[u].x, x[u].y * x[u].y);
-        float2 z = make_float2(0.0f, 0.0f);
-        if (px_raw >= a.eps) {  // clamp passes gradient only where it is inactive
-            const float py = fmaxf(fmaf(y[u].x, y[u].x, y[u].y * y[u].y), a.eps);
-            const float mx = sqrtf(px_raw), my = sqrtf(py);
-            float g = rc * (mx - my);
-            if (a.use_log) {
-                const float dl = logf(px_raw) - logf(py);
-                g += c_log * ((dl > 0.0f) - (dl < 0.0f)) / mx;
+        if (i < per_row) {
+            const float px_raw = fmaf(x[u].x, x[u].x, x[u].y * x[u].y);
+            float2 z = make_float2(0.0f, 0.0f);
+            if (px_raw >= a.eps) {  // clamp passes gradient only where it is inactive
+                const float py = fmaxf(fmaf(y[u].x, y[u].x, y[u].y * y[u].y), a.eps);
+                const float rx = fast_rsqrt(px_raw);            // 1 / |X|
+                const float d = __fmul_rn(px_raw, rx) - __fmul_rn(py, fast_rsqrt(py));   // |X| - |Y| (no FMA contraction)
+                // sign(log|X| - log|Y|) = sign(|X|^2 - |Y|^2) (monotone), so the gradient needs no logarithm
+                const float sg_log = (px_raw > py) ? 1.0f : ((px_raw < py) ? -1.0f : 0.0f);
+                const float sg_lin = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+                const float g = fmaf(rc, d, fmaf(c_log * sg_log, rx, c_lin * sg_lin));
+                const float s = g * rx;
+                z.x = s * x[u].x; z.y = s * x[u].y;
             }
-            if (a.use_lin) g += c_lin * ((mx > my) - (mx < my));
-            const float s = g / mx;
-            z.x = s * x[u].x; z.y = s * x[u].y;
+            // adjoint of the onesided real FFT expressed through an unnormalised C2R transform:
+            // DC and Nyquist keep their real part, interior bins are halved
+            if (bin == 0 || bin == a.bins - 1) z.y = 0.0f;
+            else { z.x *= 0.5f; z.y *= 0.5f; }
+            a.X[base + i] = z;
         }
-        // adjoint of the onesided real FFT expressed through an unnormalised C2R transform:
-        // DC and Nyquist keep their real part, interior bins are halved
-        if (bin == 0 || bin == a.bins - 1) z.y = 0.0f;
-        else { z.x *= 0.5f; z.y *= 0.5f; }
-        a.X[base + i] = z;
+        bin += kMrBlock;
+        while (bin >= a.bins) bin -= a.bins;
     }
 }
 
@@ -221,19 +262,24 @@ struct OlaMultiArgs {
     const float* dframes[DMST_MRSTFT_MAX_RES];   // rows x frames x n
     const float* window[DMST_MRSTFT_MAX_RES];
     int n[DMST_MRSTFT_MAX_RES], hop[DMST_MRSTFT_MAX_RES], win[DMST_MRSTFT_MAX_RES], frames[DMST_MRSTFT_MAX_RES];
+    int hop_shift[DMST_MRSTFT_MAX_RES];   // log2(hop) when hop is a power of two (the frame range needs no division), else -1
     float* gx;                 // rows x T (contiguous), or null
     int gx_vec_ok;
-    const float* res_loss;     // [n_res][4]
-    float* loss;               // [0] total, [1 + 3*r ...] sc, log, lin
+    const float* gscale;       // device scalar multiplying the gradient (the upstream gradient of the loss), or null
+    const float* res_loss;     // [n_res][4], or null (gradient-only launch)
+    float* loss;               // [0] total
+    float* terms;              // [3*r ...] sc, log, lin, or null
 };
 __global__ void ola_multi_kernel(OlaMultiArgs a) {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    if (a.res_loss && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         float tot = 0.0f;
         for (int r = 0; r < a.n_res; ++r) {
             tot += a.res_loss[4 * r];
-            a.loss[1 + 3 * r + 0] = a.res_loss[4 * r + 1];
-            a.loss[1 + 3 * r + 1] = a.res_loss[4 * r + 2];
-            a.loss[1 + 3 * r + 2] = a.res_loss[4 * r + 3];
+            if (a.terms) {
+                a.terms[3 * r + 0] = a.res_loss[4 * r + 1];
+                a.terms[3 * r + 1] = a.res_loss[4 * r + 2];
+                a.terms[3 * r + 2] = a.res_loss[4 * r + 3];
+            }
         }
         a.loss[0] = tot;
     }
@@ -251,10 +297,11 @@ __global__ void ola_multi_kernel(OlaMultiArgs a) {
         const bool fast = (a.win[r] == n) && ((hop & 3) == 0) && ((n & 7) == 0) && (t + 3 < a.T);
         if (fast) {
             const int j = t + pad;  // padded position of the first of the 4 samples (multiple of 4)
-            int f_hi = j / hop;
+            const int hs = a.hop_shift[r];
+            int f_hi = hs >= 0 ? (j >> hs) : j / hop;
             if (f_hi > frames - 1) f_hi = frames - 1;
-            int f_lo = (j + 3 - n + hop) / hop;
-            if (j + 3 - n + 1 <= 0) f_lo = 0;
+            int f_lo = 0;
+            if (j + 3 - n + 1 > 0) f_lo = hs >= 0 ? ((j + 3 - n + hop) >> hs) : (j + 3 - n + hop) / hop;   // (numerator >= hop here)
             for (int f = f_lo; f <= f_hi; ++f) {
                 const int i = j - f * hop;  // multiple of 4; the 4 samples lie in [0, n) by the choice of f_lo, f_hi
                 if (i < 0 || i + 3 >= n) {  // frame covers only part of the quad (cannot happen when 4 | hop, kept for safety)
@@ -286,6 +333,11 @@ __global__ void ola_multi_kernel(OlaMultiArgs a) {
             }
         }
     }
+    if (a.gscale) {
+        const float gs = __ldg(a.gscale);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] *= gs;
+    }
     float* g = a.gx + (long long)row * a.T + t;
     if (a.gx_vec_ok && t + 3 < a.T) {
         *reinterpret_cast<float4*>(g) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -305,6 +357,7 @@ struct MrResWs {
 struct MrWs {
     MrResWs res[DMST_MRSTFT_MAX_RES];
     float* res_loss;  // [n_res][4]
+    unsigned* done;   // [MAX_RES] finished-block counters of mr_loss_kernel (zeroed once per call)
     size_t total;
 };
 inline int mr_carve(void* base, const dmst_mrstft_cfg* c, int rows, int T, MrWs* w) {
@@ -312,11 +365,13 @@ inline int mr_carve(void* base, const dmst_mrstft_cfg* c, int rows, int T, MrWs*
     size_t off = 0;
     auto take = [&](size_t bytes) { off = (off + 255) & ~size_t(255); void* p = b ? b + off : nullptr; off += bytes; return p; };
     w->res_loss = (float*)take(sizeof(float) * 4 * DMST_MRSTFT_MAX_RES);
+    w->done = (unsigned*)take(sizeof(unsigned) * DMST_MRSTFT_MAX_RES);
     for (int r = 0; r < c->n_res; ++r) {
         const int n = c->fft_size[r], hop = c->hop_size[r], win = c->win_length[r];
         if (n <= 0 || hop <= 0 || win <= 0 || win > n || (n & 7) || n / 2 >= T) return DMST_EINVAL;
         const size_t frames = 1 + T / hop, bins = n / 2 + 1;
-        const size_t bpr = (frames * bins + kMrItemsPerBlock - 1) / kMrItemsPerBlock;
+        const size_t ipb = (size_t)mr_items_per_block((int)(frames * bins), rows);
+        const size_t bpr = (frames * bins + ipb - 1) / ipb;
         const size_t w1 = plan_work_bytes(n, 2 * rows * (int)frames), w2 = plan_work_bytes(n, rows * (int)frames);
         if (w1 == (size_t)-1 || w2 == (size_t)-1) return 1002;
         MrResWs& s = w->res[r];
@@ -356,9 +411,25 @@ inline MrStreams* mr_streams() {
     return &s;
 }
 
+// Launch of the overlap-add (+ loss totals) over the frame gradients the workspace holds
+inline int mr_launch_ola(OlaMultiArgs& oa, const dmst_mrstft_cfg* c, int rows, int T, float* grad_x, cudaStream_t stream) {
+    oa.n_res = c->n_res; oa.rows = rows; oa.T = T;
+    for (int r = 0; r < DMST_MRSTFT_MAX_RES; ++r) {
+        const int h = r < c->n_res ? c->hop_size[r] : 0;
+        oa.hop_shift[r] = -1;
+        if (h > 0 && (h & (h - 1)) == 0) { int sft = 0; while ((1 << sft) < h) ++sft; oa.hop_shift[r] = sft; }
+    }
+    oa.gx = grad_x; oa.gx_vec_ok = grad_x && ((reinterpret_cast<uintptr_t>(grad_x) & 15) == 0) && (T % 4 == 0);
+    const dim3 grid(grad_x ? ((T + 3) / 4 + 255) / 256 : 1, grad_x ? rows : 1);
+    ola_multi_kernel<<<grid, 256, 0, stream>>>(oa);
+    return (int)cudaGetLastError();
+}
+
+// keep_frames: compute the per-frame gradients and leave them in the workspace for mrstft_backward_run (the
+// two-call form an autograd node uses: the upstream gradient of the loss only exists at backward time)
 inline int mrstft_run(const float* x, long long xs, const float* y, long long ys, const float* windows,
-                      const dmst_mrstft_cfg* c, int rows, int T, float* loss, float* grad_x, void* ws,
-                      size_t ws_bytes, cudaStream_t stream) {
+                      const dmst_mrstft_cfg* c, int rows, int T, float* loss, float* terms, float* grad_x,
+                      bool keep_frames, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (!x || !y || !windows || !c || !loss || !ws || rows <= 0 || T <= 0) return DMST_EINVAL;
     if (c->n_res <= 0 || c->n_res > DMST_MRSTFT_MAX_RES) return DMST_EINVAL;
     MrWs w;
@@ -368,6 +439,7 @@ inline int mrstft_run(const float* x, long long xs, const float* y, long long ys
     MrStreams* st = mr_streams();
     if (!st) return (int)cudaGetLastError();
     static const bool serial = getenv("DMST_MRSTFT_SERIAL") && getenv("DMST_MRSTFT_SERIAL")[0] == '1';  // tuning aid
+    if (cudaMemsetAsync(w.done, 0, sizeof(unsigned) * DMST_MRSTFT_MAX_RES, stream) != cudaSuccess) return (int)cudaGetLastError();
     // fork: resolution 0 stays on the caller's stream, the others run on side streams
     if (c->n_res > 1 && !serial && cudaEventRecord(st->start, stream) != cudaSuccess) return (int)cudaGetLastError();
     OlaMultiArgs oa;
@@ -393,13 +465,13 @@ inline int mrstft_run(const float* x, long long xs, const float* y, long long ys
         if (e) return e;
         float2* X = q.spec;
         float2* Y = q.spec + (size_t)rows * per_row;
-        const int bpr = (per_row + kMrItemsPerBlock - 1) / kMrItemsPerBlock;
-        MrLossArgs la{X, Y, rows, per_row, bpr, c->eps, q.partial};
-        mr_loss_kernel<<<dim3(bpr, rows), kMrBlock, 0, s>>>(la);
+        const int ipb = mr_items_per_block(per_row, rows);
+        const int bpr = (per_row + ipb - 1) / ipb;
         MrFinalArgs fa2{q.partial, bpr, q.rowsum, rows, per_row, c->w_sc, c->w_log_mag, c->w_lin_mag, c->n_res,
                         w.res_loss + 4 * r, q.row_coef, q.scal};
-        mr_final_kernel<<<1, 512, 0, s>>>(fa2);
-        if (grad_x) {
+        MrLossArgs la{X, Y, rows, per_row, bpr, ipb, c->eps, q.partial, w.done + r, fa2};
+        mr_loss_kernel<<<dim3(bpr, rows), kMrBlock, 0, s>>>(la);
+        if (grad_x || keep_frames) {
             MrGradArgs ga{X, Y, rows, frames, bins, c->eps, q.row_coef, q.scal, c->w_log_mag != 0.0f,
                           c->w_lin_mag != 0.0f};
             mr_grad_kernel<<<dim3((per_row + kMrBlock * kMrGradU - 1) / (kMrBlock * kMrGradU), rows), kMrBlock, 0, s>>>(ga);
@@ -414,12 +486,29 @@ inline int mrstft_run(const float* x, long long xs, const float* y, long long ys
         win += wl;
     }
     // join: overlap-add of every resolution's frame gradients + the total loss, one pass
-    oa.n_res = c->n_res; oa.rows = rows; oa.T = T;
-    oa.gx = grad_x; oa.gx_vec_ok = grad_x && ((reinterpret_cast<uintptr_t>(grad_x) & 15) == 0) && (T % 4 == 0);
-    oa.res_loss = w.res_loss; oa.loss = loss;
-    const dim3 grid(grad_x ? ((T + 3) / 4 + 255) / 256 : 1, grad_x ? rows : 1);
-    ola_multi_kernel<<<grid, 256, 0, stream>>>(oa);
-    return (int)cudaGetLastError();
+    oa.res_loss = w.res_loss; oa.loss = loss; oa.terms = terms;
+    return mr_launch_ola(oa, c, rows, T, grad_x, stream);
+}
+
+// Second call of the two-call form: grad_x = grad_loss * d loss / d x from the frame gradients mrstft_run left
+inline int mrstft_backward_run(const float* windows, const dmst_mrstft_cfg* c, int rows, int T, const float* grad_loss,
+                               float* grad_x, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (!windows || !c || !grad_x || !ws || rows <= 0 || T <= 0) return DMST_EINVAL;
+    if (c->n_res <= 0 || c->n_res > DMST_MRSTFT_MAX_RES) return DMST_EINVAL;
+    MrWs w;
+    int e = mr_carve(ws, c, rows, T, &w);
+    if (e) return e;
+    if (ws_bytes < w.total) return DMST_EINVAL;
+    OlaMultiArgs oa;
+    memset(&oa, 0, sizeof(oa));
+    const float* win = windows;
+    for (int r = 0; r < c->n_res; ++r) {
+        oa.dframes[r] = w.res[r].frames; oa.window[r] = win; oa.n[r] = c->fft_size[r]; oa.hop[r] = c->hop_size[r];
+        oa.win[r] = c->win_length[r]; oa.frames[r] = 1 + T / c->hop_size[r];
+        win += c->win_length[r];
+    }
+    oa.gscale = grad_loss;
+    return mr_launch_ola(oa, c, rows, T, grad_x, stream);
 }
 #endif
 

@@ -55,22 +55,42 @@ class _MrstftFunction(torch.autograd.Function):
                 raise ValueError("MultiResolutionSTFTLoss: invalid configuration for this input length "
                                  "(each fft_size must be even, >= win_length and < 2 * samples)")
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            out = torch.empty(1 + 3 * cfg.n_res, dtype=torch.float32, device=dev)
-            gx = torch.empty(rows, T, dtype=torch.float32, device=dev) if need_grad else None
-            rc = lib.dmst_mrstft_forward(_ptr(xv), xs, _ptr(yv), ys, _ptr(windows), ctypes.byref(cfg), rows, T,
-                                         _ptr(out), _ptr(gx), _ptr(ws), nbytes,
-                                         ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            terms = torch.empty(3 * cfg.n_res, dtype=torch.float32, device=dev)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if need_grad:
+                # the per-frame gradients stay in the workspace; backward overlap-adds them scaled by the upstream
+                # gradient of the loss (no separate multiply over the (rows, T) gradient)
+                rc = lib.dmst_mrstft_forward_keep(_ptr(xv), xs, _ptr(yv), ys, _ptr(windows), ctypes.byref(cfg), rows, T,
+                                                  _ptr(loss), _ptr(terms), _ptr(ws), nbytes, stream)
+            else:
+                out = torch.empty(1 + 3 * cfg.n_res, dtype=torch.float32, device=dev)
+                rc = lib.dmst_mrstft_forward(_ptr(xv), xs, _ptr(yv), ys, _ptr(windows), ctypes.byref(cfg), rows, T,
+                                             _ptr(out), None, _ptr(ws), nbytes, stream)
+                loss, terms = out[0], out[1:]
         _lib.check(rc, "dmst_mrstft_forward")
-        ctx.gx = gx
+        if need_grad:
+            ctx.ws, ctx.nbytes, ctx.cfg, ctx.windows, ctx.rows, ctx.T = ws, nbytes, cfg, windows, rows, T
+        else:
+            ctx.ws = None
         ctx.shape = x.shape
-        ctx.mark_non_differentiable(out)
-        return out[0].clone(), out
+        ctx.mark_non_differentiable(terms)
+        return loss, terms
 
     @staticmethod
     def backward(ctx, gloss, _gterms):
-        if ctx.gx is None:
+        if ctx.ws is None:
             return None, None, None, None, None
-        return (ctx.gx.view(ctx.shape) * gloss), None, None, None, None
+        lib = _lib.lib()
+        dev = ctx.ws.device
+        g = gloss.detach().to(dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            gx = torch.empty(ctx.rows, ctx.T, dtype=torch.float32, device=dev)
+            rc = lib.dmst_mrstft_backward(_ptr(ctx.windows), ctypes.byref(ctx.cfg), ctx.rows, ctx.T, _ptr(g), _ptr(gx),
+                                          _ptr(ctx.ws), ctx.nbytes,
+                                          ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "dmst_mrstft_backward")
+        return gx.view(ctx.shape), None, None, None, None
 
 
 class MultiResolutionSTFTLoss(torch.nn.Module):
@@ -133,7 +153,7 @@ class MultiResolutionSTFTLoss(torch.nn.Module):
 
     def forward(self, x: torch.Tensor, y: torch.Tensor):
         loss, terms = _MrstftFunction.apply(x, y, self._windows_on(x.device), self._cfg(), torch.is_grad_enabled())
-        self.last_terms = terms[1:].view(-1, 3)
+        self.last_terms = terms.view(-1, 3)
         return loss
 
 

@@ -152,6 +152,21 @@ int dmst_mrstft_forward(const float* x, long long x_row_stride, const float* y,
                         long long y_row_stride, const float* windows,
                         const dmst_mrstft_cfg* cfg_host, int rows, int T, float* loss,
                         float* grad_x, void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * Two-call form for an autograd node (the loss's upstream gradient only exists at backward time, which is how
+ * torch differentiates auraloss's forward at mst/system.py:332 + Lightning's loss.backward()):
+ * dmst_mrstft_forward_keep computes the loss (loss: float32[1], terms: float32[3*n_res] or NULL) and leaves the
+ * per-frame gradients of every resolution in the workspace; dmst_mrstft_backward overlap-adds them into
+ * grad_x = grad_loss[0] * d loss / d x ((rows, T) contiguous; grad_loss: device scalar, NULL means 1).  The
+ * workspace must be kept untouched between the two calls.
+ */
+int dmst_mrstft_forward_keep(const float* x, long long x_row_stride, const float* y,
+                             long long y_row_stride, const float* windows,
+                             const dmst_mrstft_cfg* cfg_host, int rows, int T, float* loss,
+                             float* terms, void* workspace, size_t workspace_bytes, void* stream);
+int dmst_mrstft_backward(const float* windows, const dmst_mrstft_cfg* cfg_host, int rows, int T,
+                         const float* grad_loss, float* grad_x, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ---- audio feature loss: replaces mst.loss.AudioFeatureLoss.forward (mst/loss.py:238-260)
  *      and the compute_* transforms (mst/loss.py:62-195) ---- */
