@@ -388,4 +388,21 @@ int dmst_conv_round_tf32(const float*, float*, long long, int, int, int, int, vo
 int dmst_conv_avgpool(const float*, float*, int, int, int, int, int, int, int, void*) { return DMST_EINVAL; }
 #endif
 
-}  // extern "C"
+
+#ifdef DMST_EMULATE
+// TEST INFRASTRUCTURE (host-emulated build only, not declared in include/): the fused STFT + loss-sum kernel on
+// host buffers; twiddle tables supplied by the caller
+int dmst_emul_stft_loss(const float* x, const float* y, int rows, int T, int n, int hop, int win, const float* window,
+                        const float* tw_m, const float* tw_n, float* X, float* PY, float eps, float* partial) {
+    dmst::SfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x[0] = x; a.x[1] = y; a.row_stride[0] = T; a.row_stride[1] = T;
+    a.vec_ok[0] = a.vec_ok[1] = (T % 2 == 0) && (hop % 2 == 0);
+    a.rows = rows; a.T = T; a.n = n; a.hop = hop; a.win = win; a.frames = 1 + T / hop;
+    a.window = window; a.win_vec_ok = (win == n);
+    a.tw_m = reinterpret_cast<const float2*>(tw_m); a.tw_n = reinterpret_cast<const float2*>(tw_n);
+    a.X = reinterpret_cast<float2*>(X); a.PY = PY; a.eps = eps; a.partial = partial; a.done = nullptr;
+    return dmst::sf_launch(a, nullptr) ? 0 : DMST_EINVAL;
+}
+#endif
+}

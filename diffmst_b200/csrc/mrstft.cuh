@@ -10,6 +10,10 @@
 #pragma once
 #include "../../include/diffmst_b200.h"
 #include "stft.cuh"
+#include "stft_fused.cuh"
+#ifndef DMST_EMULATE
+#include <vector>
+#endif
 
 namespace dmst {
 
@@ -84,20 +88,6 @@ __device__ __forceinline__ float fast_log2(float x) {
     return y;
 }
 
-// Second stage of the reductions and the loss terms of one resolution (run by the block of mr_loss_kernel that
-// finishes last): warp w sums the block partials of rows w, w+nwarps, ... in float64 (fixed assignment of
-// partials to lanes + fixed shuffle tree => deterministic), then warp 0 forms the terms and the gradient coefficients.
-struct MrFinalArgs {
-    const float* partial;
-    int blocks_per_row;
-    double* rowsum;     // [rows][4] scratch
-    int rows, per_row;
-    float w_sc, w_log, w_lin;
-    int n_res;
-    float* res_loss;    // [4]: this resolution's contribution to the total, then its sc, log, lin terms
-    float* row_coef;    // [rows]: d(total)/d|X| coefficient of (|X|-|Y|) for the SC term
-    float* scal;        // [2]: coefficient of sign(log) / |X| and of sign(lin)
-};
 struct MrLossArgs {
     const float2* X;  // rows x frames x bins
     const float2* Y;
@@ -113,7 +103,6 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ void mr_final(const MrFinalArgs& a);
 
 // grid: (blocks_per_row, rows)
 __global__ void mr_loss_kernel(MrLossArgs a) {
@@ -202,7 +191,8 @@ __device__ void mr_final(const MrFinalArgs& a) {
 
 struct MrGradArgs {
     float2* X;        // in: spectrum of x; out: Z, the C2R-ready half-spectrum gradient
-    const float2* Y;
+    const float2* Y;  // spectrum of y, or null when PY is given
+    const float* PY;  // max(|Y|^2, eps) (the fused front end keeps only this of the target), or null
     int rows, frames, bins;
     float eps;
     const float* row_coef;
@@ -222,7 +212,11 @@ __global__ void mr_grad_kernel(MrGradArgs a) {
 #pragma unroll
     for (int u = 0; u < kMrGradU; ++u) {
         const int i = i0 + u * kMrBlock;
-        if (i < per_row) { x[u] = a.X[base + i]; y[u] = __ldg(a.Y + base + i); }
+        if (i < per_row) {
+            x[u] = a.X[base + i];
+            if (a.PY) y[u] = make_float2(__ldg(a.PY + base + i), 0.0f);
+            else y[u] = __ldg(a.Y + base + i);
+        }
     }
     int bin = i0 % a.bins;   // one division per thread; the other elements step by the block size
 #pragma unroll
@@ -232,7 +226,7 @@ __global__ void mr_grad_kernel(MrGradArgs a) {
             const float px_raw = fmaf(x[u].x, x[u].x, x[u].y * x[u].y);
             float2 z = make_float2(0.0f, 0.0f);
             if (px_raw >= a.eps) {  // clamp passes gradient only where it is inactive
-                const float py = fmaxf(fmaf(y[u].x, y[u].x, y[u].y * y[u].y), a.eps);
+                const float py = a.PY ? y[u].x : fmaxf(fmaf(y[u].x, y[u].x, y[u].y * y[u].y), a.eps);
                 const float rx = fast_rsqrt(px_raw);            // 1 / |X|
                 const float d = __fmul_rn(px_raw, rx) - __fmul_rn(py, fast_rsqrt(py));   // |X| - |Y| (no FMA contraction)
                 // sign(log|X| - log|Y|) = sign(|X|^2 - |Y|^2) (monotone), so the gradient needs no logarithm
@@ -348,6 +342,36 @@ __global__ void ola_multi_kernel(OlaMultiArgs a) {
     }
 }
 
+// Twiddle tables of the fused front end, built in float64 on the host once per (device, fft size)
+struct SfTables { float2* tw_m; float2* tw_n; };
+inline bool sf_tables(int n, SfTables* out) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, SfTables> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(dev, n);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        const int M = n / 2, K = M / 2 + 1;
+        std::vector<float2> h(M + K);
+        const double pi = 3.14159265358979323846;
+        for (int j = 0; j < M; ++j) h[j] = make_float2((float)cos(2.0 * pi * j / M), (float)-sin(2.0 * pi * j / M));
+        for (int k = 0; k < K; ++k) h[M + k] = make_float2((float)cos(2.0 * pi * k / n), (float)-sin(2.0 * pi * k / n));
+        float2* d = nullptr;
+        if (cudaMalloc(&d, sizeof(float2) * (M + K)) != cudaSuccess) return false;
+        if (cudaMemcpy(d, h.data(), sizeof(float2) * (M + K), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return false; }
+        it = cache.emplace(key, SfTables{d, d + M}).first;
+    }
+    *out = it->second;
+    return true;
+}
+// The fused front end serves power-of-two FFT sizes (DMST_MRSTFT_FUSED=0: framing + cuFFT + loss kernels, tuning aid)
+inline bool mr_use_fused(int n) {
+    static const bool off = getenv("DMST_MRSTFT_FUSED") && getenv("DMST_MRSTFT_FUSED")[0] == '0';
+    return !off && sf_supported(n);
+}
+
 // Per-resolution slice of the workspace: the resolutions run concurrently on side streams
 struct MrResWs {
     float* frames;    // 2*rows*frames*n
@@ -371,7 +395,12 @@ inline int mr_carve(void* base, const dmst_mrstft_cfg* c, int rows, int T, MrWs*
         if (n <= 0 || hop <= 0 || win <= 0 || win > n || (n & 7) || n / 2 >= T) return DMST_EINVAL;
         const size_t frames = 1 + T / hop, bins = n / 2 + 1;
         const size_t ipb = (size_t)mr_items_per_block((int)(frames * bins), rows);
-        const size_t bpr = (frames * bins + ipb - 1) / ipb;
+        size_t bpr = (frames * bins + ipb - 1) / ipb;
+        if (mr_use_fused(n)) {
+            bpr = max(bpr, (size_t)sf_blocks_per_row(n, (int)frames));
+            SfTables tb;
+            if (!sf_tables(n, &tb)) return 1003;
+        }
         const size_t w1 = plan_work_bytes(n, 2 * rows * (int)frames), w2 = plan_work_bytes(n, rows * (int)frames);
         if (w1 == (size_t)-1 || w2 == (size_t)-1) return 1002;
         MrResWs& s = w->res[r];
@@ -454,25 +483,47 @@ inline int mrstft_run(const float* x, long long xs, const float* y, long long ys
         MrResWs& q = w.res[r];
         float* fx = q.frames;
         float* fy = q.frames + (size_t)rows * frames * n;
-        Frame4Args fa;
-        fa.x[0] = x; fa.x[1] = y; fa.row_stride[0] = xs; fa.row_stride[1] = ys;
-        fa.vec_ok[0] = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (xs % 4 == 0) && (hop % 4 == 0);
-        fa.vec_ok[1] = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && (ys % 4 == 0) && (hop % 4 == 0);
-        fa.out[0] = fx; fa.out[1] = fy;
-        fa.rows = rows; fa.T = T; fa.n = n; fa.hop = hop; fa.win = wl; fa.frames = frames; fa.window = win;
-        frame4_kernel<<<dim3((frames * (n / 4) + 255) / 256, rows, 2), 256, 0, s>>>(fa);
-        e = exec_r2c(n, 2 * rows * frames, q.frames, q.spec, q.fft_work, s);
-        if (e) return e;
         float2* X = q.spec;
         float2* Y = q.spec + (size_t)rows * per_row;
-        const int ipb = mr_items_per_block(per_row, rows);
-        const int bpr = (per_row + ipb - 1) / ipb;
-        MrFinalArgs fa2{q.partial, bpr, q.rowsum, rows, per_row, c->w_sc, c->w_log_mag, c->w_lin_mag, c->n_res,
-                        w.res_loss + 4 * r, q.row_coef, q.scal};
-        MrLossArgs la{X, Y, rows, per_row, bpr, ipb, c->eps, q.partial, w.done + r, fa2};
-        mr_loss_kernel<<<dim3(bpr, rows), kMrBlock, 0, s>>>(la);
+        const bool fused = mr_use_fused(n);
+        const bool want_spectra = grad_x || keep_frames;
+        if (fused) {
+            SfTables tb;
+            if (!sf_tables(n, &tb)) return 1003;
+            SfArgs sa;
+            memset(&sa, 0, sizeof(sa));
+            sa.x[0] = x; sa.x[1] = y; sa.row_stride[0] = xs; sa.row_stride[1] = ys;
+            sa.vec_ok[0] = ((reinterpret_cast<uintptr_t>(x) & 7) == 0) && (xs % 2 == 0) && (hop % 2 == 0);
+            sa.vec_ok[1] = ((reinterpret_cast<uintptr_t>(y) & 7) == 0) && (ys % 2 == 0) && (hop % 2 == 0);
+            sa.rows = rows; sa.T = T; sa.n = n; sa.hop = hop; sa.win = wl; sa.frames = frames;
+            sa.window = win; sa.win_vec_ok = (wl == n) && ((reinterpret_cast<uintptr_t>(win) & 7) == 0);
+            sa.tw_m = tb.tw_m; sa.tw_n = tb.tw_n;
+            sa.X = want_spectra ? X : nullptr;
+            sa.PY = want_spectra ? reinterpret_cast<float*>(Y) : nullptr;   // (the target's slot of the spectrum area)
+            sa.eps = c->eps; sa.partial = q.partial; sa.done = w.done + r;
+            const int bpr = sf_blocks_per_row(n, frames);
+            sa.fin = MrFinalArgs{q.partial, bpr, q.rowsum, rows, per_row, c->w_sc, c->w_log_mag, c->w_lin_mag, c->n_res,
+                                 w.res_loss + 4 * r, q.row_coef, q.scal};
+            if (!sf_launch(sa, s)) return DMST_EINVAL;
+        } else {
+            Frame4Args fa;
+            fa.x[0] = x; fa.x[1] = y; fa.row_stride[0] = xs; fa.row_stride[1] = ys;
+            fa.vec_ok[0] = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (xs % 4 == 0) && (hop % 4 == 0);
+            fa.vec_ok[1] = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && (ys % 4 == 0) && (hop % 4 == 0);
+            fa.out[0] = fx; fa.out[1] = fy;
+            fa.rows = rows; fa.T = T; fa.n = n; fa.hop = hop; fa.win = wl; fa.frames = frames; fa.window = win;
+            frame4_kernel<<<dim3((frames * (n / 4) + 255) / 256, rows, 2), 256, 0, s>>>(fa);
+            e = exec_r2c(n, 2 * rows * frames, q.frames, q.spec, q.fft_work, s);
+            if (e) return e;
+            const int ipb = mr_items_per_block(per_row, rows);
+            const int bpr = (per_row + ipb - 1) / ipb;
+            MrFinalArgs fa2{q.partial, bpr, q.rowsum, rows, per_row, c->w_sc, c->w_log_mag, c->w_lin_mag, c->n_res,
+                            w.res_loss + 4 * r, q.row_coef, q.scal};
+            MrLossArgs la{X, Y, rows, per_row, bpr, ipb, c->eps, q.partial, w.done + r, fa2};
+            mr_loss_kernel<<<dim3(bpr, rows), kMrBlock, 0, s>>>(la);
+        }
         if (grad_x || keep_frames) {
-            MrGradArgs ga{X, Y, rows, frames, bins, c->eps, q.row_coef, q.scal, c->w_log_mag != 0.0f,
+            MrGradArgs ga{X, fused ? nullptr : Y, fused ? reinterpret_cast<const float*>(Y) : nullptr, rows, frames, bins, c->eps, q.row_coef, q.scal, c->w_log_mag != 0.0f,
                           c->w_lin_mag != 0.0f};
             mr_grad_kernel<<<dim3((per_row + kMrBlock * kMrGradU - 1) / (kMrBlock * kMrGradU), rows), kMrBlock, 0, s>>>(ga);
             e = exec_c2r(n, rows * frames, X, fx, q.fft_work, s);
