@@ -458,11 +458,11 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# our kernels per step: console forward 4 (2 x prepare, fused chain kernel, fx-bus range check), MRSTFT 11 (per
-# resolution framing, fused loss + reduction, gradient; the loss totals; one overlap-add for all at backward),
-# console backward 5 (master chain kernel + epilogue, recursion-table prepare, track chain kernel + epilogue);
-# cuFFT's 6 kernels and torch's glue kernels are not counted
-GPU_LAUNCHES_PER_STEP = 20
+# our kernels per step: console forward 4 (2 x prepare, fused chain kernel, fx-bus range check), MRSTFT 8 (per
+# resolution the fused STFT + loss kernel and the gradient kernel; the loss totals; one overlap-add for all at
+# backward), console backward 5 (recursion-table prepare, master chain kernel, track chain kernel beside it, two
+# epilogues); cuFFT's 3 inverse transforms and torch's glue kernels are not counted
+GPU_LAUNCHES_PER_STEP = 17
 
 
 def main():

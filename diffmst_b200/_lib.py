@@ -58,6 +58,8 @@ def lib():
                                         vp, vp, vp, vp, vp, vp, sz, vp]
     l.dmst_console_check_ranges.restype = i
     l.dmst_console_check_ranges.argtypes = [vp, i, i, i, vp, vp]
+    l.dmst_console_report_ranges.restype = i
+    l.dmst_console_report_ranges.argtypes = [vp, ll, i, i, i, vp, vp, vp]
     l.dmst_ola_hann_add.restype = i
     l.dmst_ola_hann_add.argtypes = [vp, ll, vp, ll, i, i, i, i, vp]
     l.dmst_mrstft_workspace_bytes.restype = sz

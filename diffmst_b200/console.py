@@ -325,12 +325,6 @@ class AdvancedMixConsole(torch.nn.Module):
         dev = status.device
         capturing = torch.cuda.is_current_stream_capturing()
         with torch.cuda.device(dev):
-            if fx_bus_params is not None and fx_bus_params.numel():
-                # 24 tested columns: upstream forces "mix" (column 24) to ones before the test (mst/modules.py:420)
-                fx = fx_bus_params.detach().reshape(-1, fx_bus_params.shape[-1])[:, :24].contiguous()
-                _lib.check(lib.dmst_console_check_ranges(_ptr(fx), fx.shape[0], fx.shape[1], 500, _ptr(status),
-                                                         ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
-                           "dmst_console_check_ranges")
             if capturing:
                 # pinned memory cannot be allocated while a stream is capturing: take a slot reserved beforehand
                 if not self._capture_slots:
@@ -340,7 +334,18 @@ class AdvancedMixConsole(torch.nn.Module):
             else:
                 host = torch.empty(1, dtype=torch.int32, pin_memory=True)
             host.fill_(_lib.STATUS_OK)
-            host.copy_(status[:1], non_blocking=True)
+            fx, rows, np_ = None, 0, 0
+            if fx_bus_params is not None and fx_bus_params.numel():
+                # 24 tested columns: upstream forces "mix" (column 24) to ones before the test (mst/modules.py:420)
+                fx = fx_bus_params.detach().reshape(-1, fx_bus_params.shape[-1])
+                if fx.stride(1) != 1 or fx.dtype != torch.float32:
+                    fx = fx.float().contiguous()
+                rows, np_ = fx.shape[0], min(24, fx.shape[1])
+            # one kernel: the fx-bus test and the verdict stored straight into the pinned host word
+            _lib.check(lib.dmst_console_report_ranges(_ptr(fx), fx.stride(0) if fx is not None else 0, rows, np_, 500,
+                                                      _ptr(status), ctypes.c_void_p(host.data_ptr()),
+                                                      ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                       "dmst_console_report_ranges")
             ev = None
             if not capturing:
                 ev = torch.cuda.Event()

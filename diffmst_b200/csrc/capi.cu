@@ -60,6 +60,43 @@ int dmst_console_check_ranges(const float* params, int rows, int np, int base, i
     return DMST_LAST_ERROR();
 }
 
+// Same test over a strided (rows x np) view (or nothing when params is NULL), then the verdict status[0] (which the
+// forward call's own test has already updated, earlier on the stream) is stored to host_status: a word of pinned
+// host memory, device-visible under unified addressing.  One kernel instead of a copy kernel, the test and a
+// device-to-host copy node.
+#ifndef DMST_EMULATE
+__global__ void range_report_kernel(const float* params, long long row_stride, int rows, int np, int base, int* status,
+                                    int* host_status) {
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0x7fffffff;
+    __syncthreads();
+    int bad = 0x7fffffff;
+    if (params)
+        for (int i = threadIdx.x; i < rows * np; i += blockDim.x) {
+            const int r = i / np, c = i - r * np;
+            const float v = params[(long long)r * row_stride + c];
+            if (v < 0.0f || v > 1.0f) bad = min(bad, base + 1 + c);
+        }
+    if (bad != 0x7fffffff) atomicMin(&s_bad, bad);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int v = *reinterpret_cast<volatile int*>(status);
+        if (s_bad < v) { v = s_bad; *status = v; }
+        *reinterpret_cast<volatile int*>(host_status) = v;
+    }
+}
+#endif
+int dmst_console_report_ranges(const float* params, long long row_stride, int rows, int np, int base, int* status,
+                               int* host_status, void* stream) {
+    if (!status || !host_status || (params && (rows <= 0 || np <= 0))) return DMST_EINVAL;
+#ifndef DMST_EMULATE
+    range_report_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(params, row_stride, rows, np, base, status, host_status);
+    return DMST_LAST_ERROR();
+#else
+    return DMST_EINVAL;
+#endif
+}
+
 // Hann-weighted overlap-add of one console window into the running mix (mst/utils.py:151-163): out[r, off + t] +=
 // win[r, t] * w(t), w = periodic Hann of length W (torch.hann_window), with the first half forced to 1 for the first window.
 __global__ void ola_hann_add_kernel(const float* win, long long win_stride, float* out, long long out_stride, int rows,

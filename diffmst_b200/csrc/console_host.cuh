@@ -318,12 +318,15 @@ inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* 
     ConsoleWs w = carve_console(ws, k.B, k.N, k.T, k.la_t, k.la_m, k.flags);
     if (ws_bytes < w.total || !aligned16(ws)) return DMST_EINVAL;
     unsigned char* base = reinterpret_cast<unsigned char*>(ws);
-    DMST_CHECK(DMST_MEMSET_ASYNC(w.header, 0, 64 * sizeof(int), stream));
-    DMST_CHECK(DMST_MEMSET_ASYNC(base + w.flags_begin, 0, w.flags_end - w.flags_begin, stream));
     DMST_CHECK(DMST_MEMSET_ASYNC(status, 0x7f, 4, stream));  // 0x7f7f7f7f = "no offender yet"
 
     PrepareArgs pt, pm;
     fill_prepare(pt, k, false, w, status);
+    // the track prepare kernel also clears the tickets and the chain flags / mailboxes of forward AND backward
+    // (contiguous in the workspace): no memset nodes in front of the chain kernels
+    pt.zero[0] = reinterpret_cast<int4*>(w.header); pt.zero_n16[0] = 64 * sizeof(int) / 16;
+    const size_t zend = w.bflags_end > w.flags_end ? w.bflags_end : w.flags_end;
+    pt.zero[1] = reinterpret_cast<int4*>(base + w.flags_begin); pt.zero_n16[1] = (long long)((zend - w.flags_begin + 15) / 16);
     DMST_LAUNCH(prepare_kernel, dim3(pt.rows), dim3(256), 0, stream, pt);
     fill_prepare(pm, k, true, w, status);
     if (!k.master_params) { pm.kind = 3; pm.np = 0; }
@@ -369,9 +372,6 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
     ConsoleWs w = carve_console(ws, k.B, k.N, k.T, k.la_t, k.la_m, k.flags);
     if (ws_bytes < w.total || !aligned16(ws)) return DMST_EINVAL;
     unsigned char* base = reinterpret_cast<unsigned char*>(ws);
-    DMST_CHECK(DMST_MEMSET_ASYNC(w.header, 0, 64 * sizeof(int), stream));
-    DMST_CHECK(DMST_MEMSET_ASYNC(base + w.bflags_begin, 0, w.bflags_end - w.bflags_begin, stream));
-
     BwdArgs fm, ft;
     memset(&fm, 0, sizeof(fm));
     memset(&ft, 0, sizeof(ft));
@@ -391,6 +391,12 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
     ft.total = at.nrows * at.ntiles; ft.ticket = w.header + 3;
     ft.area = bwd_area_floats(1, kTrackTile, k.la_t);
     const bool params_only = !(k.flags & DMST_WANT_GRAD_TRACKS);
+    // tickets and reverse-chain flags / mailboxes: cleared by the recursion-table kernel when it runs (first kernel
+    // of the parameter-gradient path), else by memsets
+    if (!(params_only && (at.flags & kChainEq))) {
+        DMST_CHECK(DMST_MEMSET_ASYNC(w.header, 0, 64 * sizeof(int), stream));
+        DMST_CHECK(DMST_MEMSET_ASYNC(base + w.bflags_begin, 0, w.bflags_end - w.bflags_begin, stream));
+    }
     // Parameter gradients only (training): the track kernel is launched as a programmatic dependent of the master
     // kernel.  The master chain is latency bound (B chains of tiles, each hop a round trip through L2): it gets a
     // fraction of the SMs, the track kernel starts on the others at once and follows the master's per-tile flags.
@@ -401,6 +407,8 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
         memset(&pb, 0, sizeof(pb));
         pb.params = k.track_params; pb.rows = at.nrows; pb.np = DMST_NUM_TRACK_PARAMS; pb.sr = (double)k.sr; pb.tab = w.track_etab;
         for (int i = 0; i < DMST_NUM_TRACK_PARAMS; ++i) { pb.lo[i] = k.ranges->track_lo[i]; pb.hi[i] = k.ranges->track_hi[i]; }
+        pb.zero[0] = reinterpret_cast<int4*>(w.header); pb.zero_n16[0] = 64 * sizeof(int) / 16;
+        pb.zero[1] = reinterpret_cast<int4*>(base + w.bflags_begin); pb.zero_n16[1] = (long long)((w.bflags_end - w.bflags_begin + 15) / 16);
         DMST_LAUNCH(prepare_bwd_kernel, dim3(pb.rows), dim3(kNumRec * 32), 0, stream, pb);
     }
     {

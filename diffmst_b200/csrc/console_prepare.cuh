@@ -89,7 +89,23 @@ struct PrepareArgs {
     RowTab* tab[2];        // [rows] each; tab[1] may be null
     int* status;
     int status_base;       // added to the flat index reported in status[0]
+    // chain workspace to clear before the chain kernels run (tickets, flags, mailboxes): 16-byte units, or null
+    int4* zero[2];
+    long long zero_n16[2];
 };
+
+// Cooperative clear of up to two workspace regions by a whole grid (replaces cudaMemsetAsync nodes in front of the
+// chain kernels: in a replayed CUDA graph each memset node costs 3-4 us of latency on the critical path)
+__device__ __forceinline__ void grid_zero(int4* const (&ptr)[2], const long long (&n16)[2]) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        int4* p = r ? ptr[1] : ptr[0];
+        const long long n = r ? n16[1] : n16[0];
+        if (!p) continue;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = make_int4(0, 0, 0, 0);
+    }
+}
 
 // index maps into the normalised parameter vector (mst/modules.py:353-460)
 struct ParamMap { int gain_in, eq0, comp0, pan, gain_out; };
@@ -117,6 +133,7 @@ __device__ __forceinline__ M2 mpow_from_squares(const M2* sq, int e) {
 // range check.  Lanes split the table entries (lane l builds P^l), everything in float64.
 // grid: rows blocks of 256 threads.
 __global__ void prepare_kernel(PrepareArgs a) {
+    grid_zero(a.zero, a.zero_n16);
     const int row = blockIdx.x;
     const int job = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* p = a.params + (long long)row * a.np;
@@ -205,9 +222,12 @@ struct PrepareBwdArgs {
     float lo[32], hi[32];
     double sr;
     EqBwdTab* tab;         // [rows]
+    int4* zero[2];         // backward chain workspace to clear (see grid_zero), or null
+    long long zero_n16[2];
 };
 // grid: rows blocks of kNumRec warps; warp r builds recursion r = 2 * section + type, lane l builds P^l
 __global__ void prepare_bwd_kernel(PrepareBwdArgs a) {
+    grid_zero(a.zero, a.zero_n16);
     const int row = blockIdx.x;
     const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (r >= kNumRec) return;

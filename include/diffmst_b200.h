@@ -109,6 +109,11 @@ int dmst_console_backward(const float* tracks, long long tracks_batch_stride,
  * of the same call (or hold 0x7f7f7f7f).  Convention: fx-bus block base = 500 (track 0, master 1000), so that the
  * smallest code is the reference's first offender in its traversal order (track, fx bus, master bus). */
 int dmst_console_check_ranges(const float* params, int rows, int np, int base, int* status, void* stream);
+/* The same test over a strided (rows, np) view (params may be NULL: no test), after which the verdict status[0] is
+ * stored to host_status, one int of PINNED host memory (device-visible under unified addressing): the asynchronous
+ * form of the reference's range test (mst/modules.py:86-89) costs one small kernel and no copy node. */
+int dmst_console_report_ranges(const float* params, long long row_stride, int rows, int np, int base, int* status,
+                               int* host_status, void* stream);
 
 /* Sliding-window inference (mst/utils.py:121-166, run_diffmst): Hann-weighted overlap-add of one console window
  * into the running mix on the device.  out[r, t] += window_mix[r, t] * w(t) for t < n <= window_length, rows = bs * 2;

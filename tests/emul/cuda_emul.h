@@ -39,6 +39,8 @@ struct uint3_ { unsigned x, y, z; };
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct double2 { double x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+static inline int4 make_int4(int a, int b, int c, int d) { return {a, b, c, d}; }
 static inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
 static inline float2 make_float2(float a, float b) { return {a, b}; }
 
