@@ -282,6 +282,28 @@ __global__ void ola_multi_kernel(OlaMultiArgs a) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) << 2;
     if (t >= a.T) return;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // Half-overlapping frames (the configurations of the reference): exactly the frames f1 = j / hop and f1 - 1 cover the
+    // quad.  The frame-gradient loads of the first resolutions are all issued before the first use (one DRAM latency
+    // per thread instead of one per frame).
+    constexpr int kBatched = 4;
+    float4 da[kBatched], db[kBatched];
+    bool batched[kBatched];
+#pragma unroll
+    for (int r = 0; r < kBatched; ++r) {
+        batched[r] = false;
+        da[r] = make_float4(0.f, 0.f, 0.f, 0.f); db[r] = da[r];
+        if (r < a.n_res) {
+            const int n = a.n[r], hop = a.hop[r], frames = a.frames[r], hs = a.hop_shift[r];
+            if ((a.win[r] == n) && hs >= 2 && n == 2 * hop && (t + 3 < a.T)) {
+                batched[r] = true;
+                const float* df = a.dframes[r] + (long long)row * frames * n;
+                const int j = t + (n >> 1);
+                const int f1 = j >> hs, i1 = j - (f1 << hs);   // i1 in [0, hop), a multiple of 4
+                if (f1 < frames) da[r] = __ldg(reinterpret_cast<const float4*>(df + (long long)f1 * n + i1));
+                if (f1 >= 1 && f1 - 1 < frames) db[r] = __ldg(reinterpret_cast<const float4*>(df + (long long)(f1 - 1) * n + i1 + hop));
+            }
+        }
+    }
 #pragma unroll
     for (int r = 0; r < DMST_MRSTFT_MAX_RES; ++r) {  // fully unrolled: kernel-parameter arrays indexed with constants
         if (r >= a.n_res) break;
@@ -289,9 +311,37 @@ __global__ void ola_multi_kernel(OlaMultiArgs a) {
         const float* df = a.dframes[r] + (long long)row * frames * n;
         OlaArgs oa{df, a.rows, a.T, n, hop, a.win[r], frames, a.window[r], nullptr, 0, 1.0f};
         const bool fast = (a.win[r] == n) && ((hop & 3) == 0) && ((n & 7) == 0) && (t + 3 < a.T);
-        if (fast) {
+        const int hs = a.hop_shift[r];
+        if (r < kBatched && batched[r < kBatched ? r : 0]) {
+            const int j = t + pad;
+            const int i1 = j & (hop - 1);
+            const float4 wa = __ldg(reinterpret_cast<const float4*>(a.window[r] + i1));
+            const float4 wb = __ldg(reinterpret_cast<const float4*>(a.window[r] + i1 + hop));
+            const float4 d0 = da[r < kBatched ? r : 0], d1 = db[r < kBatched ? r : 0];   // (zero where the frame does not exist)
+            acc[0] = fmaf(d0.x, wa.x, acc[0]); acc[1] = fmaf(d0.y, wa.y, acc[1]);
+            acc[2] = fmaf(d0.z, wa.z, acc[2]); acc[3] = fmaf(d0.w, wa.w, acc[3]);
+            acc[0] = fmaf(d1.x, wb.x, acc[0]); acc[1] = fmaf(d1.y, wb.y, acc[1]);
+            acc[2] = fmaf(d1.z, wb.z, acc[2]); acc[3] = fmaf(d1.w, wb.w, acc[3]);
+        } else if (fast && hs >= 0 && n == 2 * hop) {
+            // half-overlapping frames (the configurations of the reference): exactly the frames f1 = j / hop and f1 - 1
+            // cover the quad, straight-line code
+            const int j = t + pad;
+            const int f1 = j >> hs, i1 = j - (f1 << hs);   // i1 in [0, hop), a multiple of 4
+            const float* wv = a.window[r];
+            if (f1 < frames) {
+                const float4 d = __ldg(reinterpret_cast<const float4*>(df + (long long)f1 * n + i1));
+                const float4 w = __ldg(reinterpret_cast<const float4*>(wv + i1));
+                acc[0] = fmaf(d.x, w.x, acc[0]); acc[1] = fmaf(d.y, w.y, acc[1]);
+                acc[2] = fmaf(d.z, w.z, acc[2]); acc[3] = fmaf(d.w, w.w, acc[3]);
+            }
+            if (f1 >= 1 && f1 - 1 < frames) {
+                const float4 d = __ldg(reinterpret_cast<const float4*>(df + (long long)(f1 - 1) * n + i1 + hop));
+                const float4 w = __ldg(reinterpret_cast<const float4*>(wv + i1 + hop));
+                acc[0] = fmaf(d.x, w.x, acc[0]); acc[1] = fmaf(d.y, w.y, acc[1]);
+                acc[2] = fmaf(d.z, w.z, acc[2]); acc[3] = fmaf(d.w, w.w, acc[3]);
+            }
+        } else if (fast) {
             const int j = t + pad;  // padded position of the first of the 4 samples (multiple of 4)
-            const int hs = a.hop_shift[r];
             int f_hi = hs >= 0 ? (j >> hs) : j / hop;
             if (f_hi > frames - 1) f_hi = frames - 1;
             int f_lo = 0;

@@ -10,12 +10,19 @@ want = [('gpu__time_duration.sum', 'duration_us'), ('launch__registers_per_threa
         ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram_throughput_pct'),
         ('dram__bytes_read.sum', 'dram_read_MB'), ('dram__bytes_write.sum', 'dram_write_MB'),
         ('smsp__inst_executed.sum', 'warp_instructions'), ('launch__waves_per_multiprocessor', 'waves')]
-kern = []
-for r in rows[2:]:
-    d = {'kernel': r[idx['Kernel Name']]}
-    for m, n in want:
-        d[n] = r[idx[m]] if m in idx else None
-    kern.append(d)
+def table(rows):
+    hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
+    out = []
+    for r in rows[2:]:
+        d = {'kernel': r[idx['Kernel Name']]}
+        for m, n in want:
+            d[n] = r[idx[m]] if m in idx else None
+        out.append(d)
+    return out
+kern = table(rows)
+import os
+mr_path = f'gpurun_out/prof_mr_{tag}_raw.csv'
+mr = table(list(csv.reader(open(mr_path)))) if os.path.exists(mr_path) else []
 lr = [r for r in csv.reader(open(f'gpurun_out/launches_step_{tag}.csv')) if len(r) > 5]
 h2 = lr[0]; ki = h2.index('Kernel Name'); vi = h2.index('Metric Value')
 names = [(r[ki], float(r[vi].replace(',', ''))) for r in lr[1:]]
@@ -27,6 +34,8 @@ md = [f'# profiles/ - round {tag} (B200, ncu, `--clock-control none`)\n',
       'Commands (under gpurun):\n```\n'
       f'ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step_{tag}.csv python scripts/prof_step.py 3\n'
       f'ncu --set full --clock-control none --import-source on -k regex:"console_fwd|chain_bwd|track_bwd2" -s 3 -c 3 -o gpurun_out/prof_{tag} python scripts/prof_once.py 8 16 262144 2\n'
+      f'ncu --set full --clock-control none --import-source on -k regex:"stft_loss|mr_grad|ola_multi" -s 8 -c 8 -o gpurun_out/prof_mr_{tag} python scripts/prof_mrstft.py 2\n'
+      'python scripts/timeline_step.py   # torch.profiler / CUPTI timeline of the graph-replayed step: what overlaps\n'
       'python scripts/sweep_eq_comp.py ; python tests/tools/conv_bench.py\npython bench.py --steps 50 --warmup 5 ; python bench.py --impl reference --steps 3 --warmup 1\n```\n',
       '## 1. Launch list of one step (ncu per-launch times are cold-cache and serialised: compare shares)\n',
       '| us | share | kernel |\n|---:|---:|---|']
@@ -38,6 +47,15 @@ md.append('| kernel | us | regs | warps active % | SM throughput % | FMA pipe % 
 for d in kern:
     f = lambda k: float(str(d[k]).replace(',', ''))
     md.append(f"| `{d['kernel'][:60]}` | {f('duration_us'):.1f} | {d['regs']} | {f('warps_active_pct'):.1f} | {f('sm_throughput_pct'):.1f} | {f('fma_pipe_pct'):.1f} | {f('dram_throughput_pct'):.1f} | {f('dram_read_MB'):.1f} | {f('dram_write_MB'):.1f} | {f('warp_instructions'):.0f} |")
+def rowfmt(d):
+    f = lambda k: float(str(d[k]).replace(',', ''))
+    return (f"| `{d['kernel'][:60]}` | {f('duration_us'):.1f} | {d['regs']} | {f('warps_active_pct'):.1f} | {f('sm_throughput_pct'):.1f} | "
+            f"{f('fma_pipe_pct'):.1f} | {f('dram_throughput_pct'):.1f} | {f('dram_read_MB'):.1f} | {f('dram_write_MB'):.1f} | {f('warp_instructions'):.0f} |")
+if mr:
+    md.append('\n## 3. `ncu --set full` of the MRSTFT kernels (one resolution each; run alone, cold cache)\n')
+    md.append('| kernel | us | regs | warps active % | SM throughput % | FMA pipe % | DRAM throughput % | DRAM read MB | DRAM write MB | warp-instructions |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|')
+    for d in mr:
+        md.append(rowfmt(d))
 open(f'profiles/ncu_{tag}_summary.md', 'w').write('\n'.join(md) + '\n')
-json.dump({'kernels': kern, 'step_launches_us': [(n, v / 1000) for n, v in step]}, open(f'profiles/ncu_{tag}_summary.json', 'w'), indent=1)
+json.dump({'kernels': kern, 'mrstft_kernels': mr, 'step_launches_us': [(n, v / 1000) for n, v in step]}, open(f'profiles/ncu_{tag}_summary.json', 'w'), indent=1)
 print('\n'.join(md[-7:]))
