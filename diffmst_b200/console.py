@@ -16,6 +16,7 @@ the autograd graph.  The denormalised parameter dictionaries returned to the cal
 produced with the same torch expressions as upstream (they are tiny and callers may
 differentiate through them).
 """
+import contextlib
 import ctypes
 from typing import Optional
 
@@ -210,6 +211,8 @@ class AdvancedMixConsole(torch.nn.Module):
         self.check_ranges = True
         self._pending_ranges = []   # [(pinned int32 host tensor, event or None)]
         self._capture_slots = []    # pinned words reserved for calls made during a CUDA-graph capture
+        self._side_streams = {}     # device -> stream the returned parameter dictionaries are computed on
+        self.side_stream_dicts = True
 
     # ---- parameter plumbing (mst/modules.py:353-466) ----
     def _track_ranges(self):
@@ -458,15 +461,37 @@ class AdvancedMixConsole(torch.nn.Module):
                 self.check_pending_ranges(wait=False)          # verdicts of earlier calls that have landed
         elif self.check_ranges:
             self._raise_if_out_of_range(track_params, fx_bus_params, master_bus_params)
-        # two elementwise kernels per tensor instead of two per dictionary entry (156 upstream)
-        track_param_dict = self._denormalize_batched(track_params, self._track_ranges(), self._split_track)
+        # The returned dictionaries of denormalised values (two elementwise kernels per tensor instead of two per
+        # dictionary entry, 156 upstream) do not feed the audio path: they are computed on a side stream, beside the
+        # console kernels, and joined before this call returns (in a captured CUDA graph: a parallel branch).
         fx_ranges = [self.param_ranges["reverberation"][f"band{i}_gain"] for i in range(12)] + \
             [self.param_ranges["reverberation"][f"band{i}_decay"] for i in range(12)] + \
             [self.param_ranges["reverberation"]["mix"]]
-        fx_bus_param_dict = self._denormalize_batched(fx_bus_params, fx_ranges, self._split_fx)
-        master_bus_param_dict = self._denormalize_batched(master_bus_params, self._master_ranges(),
-                                                          self._split_master)
+        side = cur = None
+        if tracks.is_cuda and self.side_stream_dicts:
+            cur = torch.cuda.current_stream(tracks.device)
+            side = self._side_streams.get(tracks.device)
+            if side is None:
+                side = self._side_streams[tracks.device] = torch.cuda.Stream(tracks.device)
+            side.wait_stream(cur)
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            track_param_dict = self._denormalize_batched(track_params, self._track_ranges(), self._split_track)
+            fx_bus_param_dict = self._denormalize_batched(fx_bus_params, fx_ranges, self._split_fx)
+            master_bus_param_dict = self._denormalize_batched(master_bus_params, self._master_ranges(),
+                                                              self._split_master)
+            if side is not None:   # allocated on the side stream, consumed on the caller's (the entries of a dictionary
+                for d in (track_param_dict, fx_bus_param_dict, master_bus_param_dict):   # are views of one tensor)
+                    seen = set()
+                    for effect in d.values():
+                        for v in effect.values():
+                            if torch.is_tensor(v):
+                                base = v._base if v._base is not None else v
+                                if id(base) not in seen:
+                                    seen.add(id(base))
+                                    base.record_stream(cur)
         mixed_tracks, mix = self._run(tracks, track_params, master_bus_params, flags, fx_bus_params=fx_bus_params)
+        if side is not None:
+            cur.wait_stream(side)
         return mixed_tracks, mix, track_param_dict, fx_bus_param_dict, master_bus_param_dict
 
 
