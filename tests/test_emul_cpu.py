@@ -143,3 +143,52 @@ def test_emulated_parameter_only_backward_matches_float64_oracle(emul_console, s
     assert np.isfinite(gtp).all()
     assert rel_l2(gtp, tpd.grad.numpy()) <= 1e-3, (rel_l2(gtp, tpd.grad.numpy()), np.abs(gtp - tpd.grad.numpy()).max(axis=(0, 1)))
     assert rel_l2(gmp, mpd.grad.numpy()) <= 1e-3
+
+
+# (fft size, hop, window, rows, samples): every radix plan of the fused STFT front end (complex lengths 32 .. 4096:
+# 16x2, 16x4, 16x8, 16x16, 16x16x2, 16x16x4, 16x16x8, 16x16x16), half-overlapping and auraloss-default framing, windows
+# shorter than the FFT, odd lengths (reflect padding and the scalar load path), several frames per block
+@pytest.mark.parametrize("cfg", [(512, 256, 512, 2, 5000), (2048, 1024, 2048, 2, 9000), (8192, 4096, 8192, 1, 20000),
+                                 (1024, 120, 600, 1, 3001), (64, 16, 64, 1, 700), (128, 64, 100, 1, 1000),
+                                 (256, 128, 256, 1, 1500), (4096, 1024, 4096, 1, 9001)])
+def test_emulated_fused_stft_front_end_matches_numpy(emul_console, cfg):
+    """stft_fused.cuh (framing + real FFT of both signals + loss sums) on the host emulator against numpy float64:
+    spectrum of the prediction, clamped power of the target, the four sums the loss terms are made of."""
+    import ctypes
+    n, hop, win, rows, T = cfg
+    lib = emul_console.load()
+    rng = np.random.default_rng(n + T)
+    x = (rng.standard_normal((rows, T)) * 0.1).astype(np.float32)
+    y = (rng.standard_normal((rows, T)) * 0.1 + 0.3 * x).astype(np.float32)
+    M = n // 2
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(win) / win)).astype(np.float32)   # torch.hann_window (periodic)
+    j = np.arange(M)
+    twm = np.stack([np.cos(2 * np.pi * j / M), -np.sin(2 * np.pi * j / M)], -1).astype(np.float32)
+    k = np.arange(M // 2 + 1)
+    twn = np.stack([np.cos(2 * np.pi * k / n), -np.sin(2 * np.pi * k / n)], -1).astype(np.float32)
+    frames, bins = 1 + T // hop, M + 1
+    X = np.zeros((rows, frames, bins, 2), np.float32)
+    PY = np.zeros((rows, frames, bins), np.float32)
+    fpb = 4096 // M
+    partial = np.zeros((rows, (frames + fpb - 1) // fpb, 4), np.float32)
+    eps = 1e-8
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.dmst_emul_stft_loss(p(x), p(y), rows, T, n, hop, win, p(w), p(twm), p(twn), p(X), p(PY),
+                                 ctypes.c_float(eps), p(partial))
+    assert rc == 0
+    wp = np.zeros(n)
+    wl = (n - win) // 2
+    wp[wl:wl + win] = w
+
+    def stft(s):   # torch.stft(center=True, pad_mode="reflect", onesided) as auraloss calls it
+        sp = np.pad(s.astype(np.float64), ((0, 0), (n // 2, n // 2)), mode="reflect")
+        return np.fft.rfft(np.stack([sp[:, f * hop:f * hop + n] * wp for f in range(frames)], 1), axis=-1)
+
+    Xr, Yr = stft(x), stft(y)
+    assert np.abs((X[..., 0] + 1j * X[..., 1]) - Xr).max() <= 5e-7 * np.abs(Xr).max()
+    pyr, pxr = np.maximum(np.abs(Yr) ** 2, eps), np.maximum(np.abs(Xr) ** 2, eps)
+    assert np.abs(PY - pyr).max() <= 2e-6 * pyr.max()
+    d = np.sqrt(pyr) - np.sqrt(pxr)
+    ref = np.array([(d ** 2).sum(), pyr.sum(), np.abs(0.5 * (np.log(pxr) - np.log(pyr))).sum(), np.abs(d).sum()])
+    got = partial.astype(np.float64).sum((0, 1))
+    assert (np.abs(got - ref) / ref).max() <= 2e-6
