@@ -467,13 +467,18 @@ class AdvancedMixConsole(torch.nn.Module):
         fx_ranges = [self.param_ranges["reverberation"][f"band{i}_gain"] for i in range(12)] + \
             [self.param_ranges["reverberation"][f"band{i}_decay"] for i in range(12)] + \
             [self.param_ranges["reverberation"]["mix"]]
-        side = cur = None
+        side = cur = ready = None
         if tracks.is_cuda and self.side_stream_dicts:
             cur = torch.cuda.current_stream(tracks.device)
             side = self._side_streams.get(tracks.device)
             if side is None:
                 side = self._side_streams[tracks.device] = torch.cuda.Stream(tracks.device)
-            side.wait_stream(cur)
+            ready = cur.record_event()   # the parameters are ready here; the side stream need not wait for the console
+        # (the console call comes first: the parameters' first differentiable use, hence their gradient accumulation,
+        # stays on the caller's stream)
+        mixed_tracks, mix = self._run(tracks, track_params, master_bus_params, flags, fx_bus_params=fx_bus_params)
+        if side is not None:
+            side.wait_event(ready)
         with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
             track_param_dict = self._denormalize_batched(track_params, self._track_ranges(), self._split_track)
             fx_bus_param_dict = self._denormalize_batched(fx_bus_params, fx_ranges, self._split_fx)
@@ -489,7 +494,6 @@ class AdvancedMixConsole(torch.nn.Module):
                                 if id(base) not in seen:
                                     seen.add(id(base))
                                     base.record_stream(cur)
-        mixed_tracks, mix = self._run(tracks, track_params, master_bus_params, flags, fx_bus_params=fx_bus_params)
         if side is not None:
             cur.wait_stream(side)
         return mixed_tracks, mix, track_param_dict, fx_bus_param_dict, master_bus_param_dict

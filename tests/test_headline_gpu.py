@@ -258,3 +258,32 @@ def test_sliding_window_inference_matches_reference_loop():
     want, want32 = reference_loop(torch.float64), reference_loop(torch.float32)
     b = 1.5 * max(1e-4, relmax(want32, want))
     assert relmax(got.cpu().numpy(), want) <= b, (relmax(got.cpu().numpy(), want), b)
+
+
+def test_backward_twice_over_a_retained_graph_is_bit_identical():
+    """The backward kernels clear their own tickets / flags / mailboxes and the loss keeps its per-frame gradients in
+    the workspace: a second backward over a retained graph (and one with another upstream gradient) must reproduce the
+    first bit for bit (scaled), for the training path (parameter gradients: track kernel beside the master kernel)
+    and for the audio-gradient path (classic adjoint)."""
+    from diffmst_b200 import AdvancedMixConsole, MRSTFTLoss
+    g = torch.Generator().manual_seed(31)
+    B, N, T = 2, 3, 40000
+    tracks = (torch.randn(B, N, T, generator=g) * 0.1).cuda()
+    fp = torch.rand(B, 25, generator=g).cuda()
+    target = (torch.randn(B, 2, T, generator=g) * 0.1).cuda()
+    con = AdvancedMixConsole(SR).cuda()
+    con.materialize_tracks = False
+    loss_fn = MRSTFTLoss(**RES)
+    for want_audio_grad in (False, True):
+        tp = torch.rand(B, N, 27, generator=g).cuda().requires_grad_(True)
+        mp = torch.rand(B, 26, generator=g).cuda().requires_grad_(True)
+        x = tracks.clone().requires_grad_(want_audio_grad)
+        loss = loss_fn(con(x, tp, fp, mp, **FLAGS)[1], target)
+        leaves = [tp, mp] + ([x] if want_audio_grad else [])
+        first = torch.autograd.grad(loss, leaves, retain_graph=True)
+        second = torch.autograd.grad(loss, leaves, retain_graph=True)
+        scaled = torch.autograd.grad(2.0 * loss, leaves)
+        for a, b, c in zip(first, second, scaled):
+            assert torch.isfinite(a).all()
+            assert torch.equal(a, b)
+            assert torch.equal(2.0 * a, c)
