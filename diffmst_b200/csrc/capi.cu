@@ -441,5 +441,14 @@ int dmst_emul_stft_loss(const float* x, const float* y, int rows, int T, int n, 
     a.X = reinterpret_cast<float2*>(X); a.PY = PY; a.eps = eps; a.partial = partial; a.done = nullptr;
     return dmst::sf_launch(a, nullptr) ? 0 : DMST_EINVAL;
 }
+int dmst_emul_istft_grad(const float* X, const float* PY, float* dframes, int rows, int n, int frames, const float* tw_m,
+                         const float* tw_n, float eps, const float* row_coef, const float* scal, int use_log, int use_lin) {
+    dmst::SfGradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = reinterpret_cast<const float2*>(X); a.PY = PY; a.dframes = dframes; a.rows = rows; a.n = n; a.frames = frames;
+    a.tw_m = reinterpret_cast<const float2*>(tw_m); a.tw_n = reinterpret_cast<const float2*>(tw_n);
+    a.eps = eps; a.row_coef = row_coef; a.scal = scal; a.use_log = use_log; a.use_lin = use_lin;
+    return dmst::sf_grad_launch(a, nullptr) ? 0 : DMST_EINVAL;
+}
 #endif
 }

@@ -451,8 +451,11 @@ inline int mr_carve(void* base, const dmst_mrstft_cfg* c, int rows, int T, MrWs*
             SfTables tb;
             if (!sf_tables(n, &tb)) return 1003;
         }
-        const size_t w1 = plan_work_bytes(n, 2 * rows * (int)frames), w2 = plan_work_bytes(n, rows * (int)frames);
-        if (w1 == (size_t)-1 || w2 == (size_t)-1) return 1002;
+        size_t w1 = 0, w2 = 0;   // (the fused kernels need no cuFFT plan)
+        if (!mr_use_fused(n)) {
+            w1 = plan_work_bytes(n, 2 * rows * (int)frames); w2 = plan_work_bytes(n, rows * (int)frames);
+            if (w1 == (size_t)-1 || w2 == (size_t)-1) return 1002;
+        }
         MrResWs& s = w->res[r];
         s.frames = (float*)take((size_t)2 * rows * frames * n * 4);
         s.spec = (float2*)take((size_t)2 * rows * frames * bins * 8);
@@ -572,8 +575,18 @@ inline int mrstft_run(const float* x, long long xs, const float* y, long long ys
             MrLossArgs la{X, Y, rows, per_row, bpr, ipb, c->eps, q.partial, w.done + r, fa2};
             mr_loss_kernel<<<dim3(bpr, rows), kMrBlock, 0, s>>>(la);
         }
-        if (grad_x || keep_frames) {
-            MrGradArgs ga{X, fused ? nullptr : Y, fused ? reinterpret_cast<const float*>(Y) : nullptr, rows, frames, bins, c->eps, q.row_coef, q.scal, c->w_log_mag != 0.0f,
+        if (want_spectra && fused) {
+            // spectrum -> half-spectrum gradient -> inverse real FFT of every frame, one kernel
+            SfTables tb;
+            if (!sf_tables(n, &tb)) return 1003;
+            SfGradArgs ga;
+            memset(&ga, 0, sizeof(ga));
+            ga.X = X; ga.PY = reinterpret_cast<const float*>(Y); ga.dframes = fx;
+            ga.rows = rows; ga.n = n; ga.frames = frames; ga.tw_m = tb.tw_m; ga.tw_n = tb.tw_n; ga.eps = c->eps;
+            ga.row_coef = q.row_coef; ga.scal = q.scal; ga.use_log = c->w_log_mag != 0.0f; ga.use_lin = c->w_lin_mag != 0.0f;
+            if (!sf_grad_launch(ga, s)) return DMST_EINVAL;
+        } else if (want_spectra) {
+            MrGradArgs ga{X, Y, nullptr, rows, frames, bins, c->eps, q.row_coef, q.scal, c->w_log_mag != 0.0f,
                           c->w_lin_mag != 0.0f};
             mr_grad_kernel<<<dim3((per_row + kMrBlock * kMrGradU - 1) / (kMrBlock * kMrGradU), rows), kMrBlock, 0, s>>>(ga);
             e = exec_c2r(n, rows * frames, X, fx, q.fft_work, s);

@@ -125,7 +125,7 @@ template <int M> struct SfPlan {
 // One in-place shared-memory stage over both signals (sm0: prediction, sm1: target): sub-FFTs of length L = R * S;
 // every thread does 16 / R butterflies per signal.  Output k is multiplied by w_L^(n_low k) = tw[(M / L) n_low k]
 // (loaded once, ahead of the butterflies, and used for both signals).
-template <int M, int R, int L>
+template <int M, int R, int L, int NSIG = 2>
 __device__ __forceinline__ void sf_stage(float2* sm0, float2* sm1, const float2* tw, int tid) {
     constexpr int S = L / R, G = 16 / R;
 #pragma unroll
@@ -139,7 +139,7 @@ __device__ __forceinline__ void sf_stage(float2* sm0, float2* sm1, const float2*
             for (int k = 1; k < R; ++k) w[k] = sf_ldg2(tw + (M / L) * n_low * k);
         }
 #pragma unroll
-        for (int sig = 0; sig < 2; ++sig) {
+        for (int sig = 0; sig < NSIG; ++sig) {
             float2* sm = sig ? sm1 : sm0;
             float2 v[R];
 #pragma unroll
@@ -378,6 +378,120 @@ __global__ void __launch_bounds__(kSfThreads, 2) stft_loss_kernel(SfArgs a) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Gradient side: spectrum of the prediction + max(|Y|^2, eps) -> half-spectrum gradient -> inverse real FFT of every
+// frame, in one kernel (replaces mr_grad_kernel + cuFFT C2R for the same FFT sizes).  The loss's derivative w.r.t. the
+// frame is r[n] = Re sum_{k=0..n/2} g[k] e^{+2 pi i k n / N}, g = dL/dRe X + i dL/dIm X; with H = g/2 on interior bins
+// (real part of g at DC and Nyquist) r is the unnormalised inverse DFT of H's Hermitian extension, which a complex
+// inverse FFT of length M = N/2 delivers as z'[m] = r[2m] + i r[2m+1] from
+//     Z'[k] = (H[k] + conj(H[M-k])) + i conj(w_N^k) (H[k] - conj(H[M-k])),      k = 0 .. M-1   (H[M]: Nyquist)
+// and the inverse FFT is the forward machinery on conj(Z') with the result conjugated.
+// ---------------------------------------------------------------------------------------------------------------
+struct SfGradArgs {
+    const float2* X;            // rows x frames x (M+1) spectrum of the prediction
+    const float* PY;            // rows x frames x (M+1) max(|Y|^2, eps)
+    float* dframes;             // rows x frames x n: d loss / d frame (before the window; the overlap-add applies it)
+    int rows, n, frames;
+    const float2* tw_m;
+    const float2* tw_n;
+    float eps;
+    const float* row_coef;      // [rows]
+    const float* scal;          // [2]
+    int use_log, use_lin;
+};
+
+// g/2 (interior) of one bin: x = X[bin], py = max(|Y|^2, eps)
+__device__ __forceinline__ float2 sf_bin_gradient(float2 x, float py, float rc, float c_log, float c_lin, float eps) {
+    const float px = fmaf(x.x, x.x, x.y * x.y);
+    if (!(px >= eps)) return make_float2(0.0f, 0.0f);   // the clamp passes gradient only where it is inactive
+    const float rx = sf_rsqrt(px);
+    const float d = __fmul_rn(px, rx) - __fmul_rn(py, sf_rsqrt(py));   // |X| - |Y|
+    const float sg_log = (px > py) ? 1.0f : ((px < py) ? -1.0f : 0.0f);
+    const float sg_lin = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+    const float s = fmaf(rc, d, fmaf(c_log * sg_log, rx, c_lin * sg_lin)) * rx;
+    return make_float2(s * x.x, s * x.y);
+}
+
+// grid: (ceil(frames / FPB), rows); block 256; one exchange buffer
+template <int M>
+__global__ void __launch_bounds__(kSfThreads, 4) istft_grad_kernel(SfGradArgs a) {
+    typedef SfPlan<M> P;
+    constexpr int FPB = P::FPB, HALF = M / 2, SLOTS = FPB * HALF, J = SLOTS / kSfThreads, BINS = M + 1, S = M / 16;
+    DMST_DYN_SMEM(smem_raw);
+    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    const int tid = threadIdx.x, row = blockIdx.y;
+    const int frame0 = blockIdx.x * FPB;
+    const float rc = __ldg(a.row_coef + row), c_log = a.use_log ? __ldg(a.scal) : 0.0f, c_lin = a.use_lin ? __ldg(a.scal + 1) : 0.0f;
+    // ---- conj(Z') of every frame into shared memory, natural order ----
+    // (all global loads of the thread's slots are issued before the first use: one memory latency, not one per slot)
+    float2 xa[J], xb[J];
+    float pa[J], pb[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int slot = tid + kSfThreads * j;
+        const int p = slot / HALF, k = slot - p * HALF;
+        const int f = frame0 + p;
+        xa[j] = make_float2(0.0f, 0.0f); xb[j] = xa[j]; pa[j] = 1.0f; pb[j] = 1.0f;
+        if (f < a.frames) {   // (k = 0: bins 0 and M, the same addresses as the pair (k, M - k))
+            const long long o = ((long long)row * a.frames + f) * BINS;
+            xa[j] = sf_ldg2(a.X + o + k); xb[j] = sf_ldg2(a.X + o + M - k);
+            pa[j] = __ldg(a.PY + o + k); pb[j] = __ldg(a.PY + o + M - k);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int slot = tid + kSfThreads * j;
+        const int p = slot / HALF, k = slot - p * HALF;
+        const int f = frame0 + p;
+        float2* zf = sm + sf_pad(p * M);
+        // (frames beyond the end: x = 0 gives zero gradients, so zeros are stored)
+        const float2 ga = sf_bin_gradient(xa[j], pa[j], rc, c_log, c_lin, a.eps);
+        const float2 gb = sf_bin_gradient(xb[j], pb[j], rc, c_log, c_lin, a.eps);
+        if (k == 0) {
+            // DC and Nyquist keep the real part of g; bin M/2 is an interior bin paired with itself
+            float2 gh = make_float2(0.0f, 0.0f);
+            if (f < a.frames) {
+                const long long o = ((long long)row * a.frames + f) * BINS;
+                gh = sf_bin_gradient(sf_ldg2(a.X + o + HALF), __ldg(a.PY + o + HALF), rc, c_log, c_lin, a.eps);
+            }
+            zf[sf_pad(0)] = make_float2(ga.x + gb.x, -(ga.x - gb.x));   // conj((h0 + hm) + i (h0 - hm))
+            zf[sf_pad(HALF)] = gh;                                       // conj(2 conj(H)) with H = g / 2
+        } else {
+            const float2 A = make_float2(0.5f * ga.x, 0.5f * ga.y), B = make_float2(0.5f * gb.x, -0.5f * gb.y);   // H[k], conj(H[M-k])
+            const float2 sum = make_float2(A.x + B.x, A.y + B.y), dif = make_float2(A.x - B.x, A.y - B.y);
+            const float2 w = sf_ldg2(a.tw_n + k);                       // w_N^k
+            // i conj(w) dif  and  i w conj(dif)
+            const float2 cw = sf_cmul(make_float2(w.x, -w.y), dif), wc = sf_cmul(w, make_float2(dif.x, -dif.y));
+            const float2 zk = make_float2(sum.x - cw.y, sum.y + cw.x);         // Z'[k]
+            const float2 zm = make_float2(sum.x - wc.y, -sum.y + wc.x);        // Z'[M-k] = conj(sum) + i w conj(dif)
+            zf[sf_pad(k)] = make_float2(zk.x, -zk.y);
+            zf[sf_pad(M - k)] = make_float2(zm.x, -zm.y);
+        }
+    }
+    __syncthreads();
+    // ---- forward FFT machinery on conj(Z'), in place ----
+    sf_stage<M, 16, M, 1>(sm, sm, a.tw_m, tid);
+    __syncthreads();
+    sf_stage<M, P::R2, P::L2, 1>(sm, sm, a.tw_m, tid);
+    __syncthreads();
+    if (P::L3 > 1) {
+        sf_stage<M, (P::R3 > 1 ? P::R3 : 2), (P::L3 > 1 ? P::L3 : 2), 1>(sm, sm, a.tw_m, tid);
+        __syncthreads();
+    }
+    // ---- r[2m] + i r[2m+1] = conj(out[m]): coalesced float2 stores ----
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int idx = tid + kSfThreads * j;
+        const int p = idx / M, m = idx - p * M;
+        const int f = frame0 + p;
+        if (f < a.frames) {
+            const float2 o = sm[sf_pad(p * M) + sf_pad(P::pos(m))];
+            *reinterpret_cast<float2*>(a.dframes + ((long long)row * a.frames + f) * a.n + 2 * m) = make_float2(o.x, -o.y);
+        }
+    }
+    (void)S;
+}
+
 constexpr size_t kSfSmemBytes = 2 * sizeof(float2) * kSfSmemFloat2;
 #ifdef DMST_EMULATE
 #define DMST_SF_SET_SMEM(kernel) 0
@@ -394,6 +508,22 @@ inline bool sf_launch(const SfArgs& a, cudaStream_t stream) {
         const dim3 grid((a.frames + SfPlan<MM>::FPB - 1) / SfPlan<MM>::FPB, a.rows);                       \
         if (DMST_SF_SET_SMEM(stft_loss_kernel<MM>) != 0) return false;                                     \
         DMST_LAUNCH(stft_loss_kernel<MM>, grid, block, kSfSmemBytes, stream, a);                           \
+        return true;                                                                                       \
+    }
+    switch (a.n / 2) {
+        DMST_SF_CASE(32) DMST_SF_CASE(64) DMST_SF_CASE(128) DMST_SF_CASE(256) DMST_SF_CASE(512)
+        DMST_SF_CASE(1024) DMST_SF_CASE(2048) DMST_SF_CASE(4096)
+        default: return false;
+    }
+#undef DMST_SF_CASE
+}
+inline bool sf_grad_launch(const SfGradArgs& a, cudaStream_t stream) {
+    const dim3 block(kSfThreads);
+    constexpr size_t smem = sizeof(float2) * kSfSmemFloat2;
+#define DMST_SF_CASE(MM)                                                                                   \
+    case MM: {                                                                                             \
+        const dim3 grid((a.frames + SfPlan<MM>::FPB - 1) / SfPlan<MM>::FPB, a.rows);                       \
+        DMST_LAUNCH(istft_grad_kernel<MM>, grid, block, smem, stream, a);                                  \
         return true;                                                                                       \
     }
     switch (a.n / 2) {
