@@ -7,7 +7,7 @@ from diffmst_b200 import AdvancedMixConsole, MRSTFTLoss
 torch.manual_seed(0)
 B, N, T = 2, 3, 20011   # ragged: 3 forward tiles / 5 backward tiles, T % 4 != 0
 con = AdvancedMixConsole(44100).cuda(); con.check_ranges = "async"
-loss_fn = MRSTFTLoss(fft_sizes=[512, 2048], hop_sizes=[256, 1024], win_lengths=[512, 2048])
+loss_fn = MRSTFTLoss(fft_sizes=[512, 2048, 8192, 600], hop_sizes=[256, 1024, 4096, 150], win_lengths=[512, 2048, 8192, 400])   # fused front end (three plans) + the library-FFT path
 x = (torch.randn(B, N, T) * 0.1).cuda()
 fp = torch.rand(B, 25).cuda()
 target = (torch.randn(B, 2, T) * 0.1).cuda()
