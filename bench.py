@@ -458,11 +458,11 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# our kernels per step: console forward 4 (2 x prepare, fused chain kernel, fx-bus range check), MRSTFT 8 (per
-# resolution the fused STFT + loss kernel and the gradient kernel; the loss totals; one overlap-add for all at
-# backward), console backward 5 (recursion-table prepare, master chain kernel, track chain kernel beside it, two
-# epilogues); cuFFT's 3 inverse transforms and torch's glue kernels are not counted
-GPU_LAUNCHES_PER_STEP = 17
+# our kernels per step: console forward 3 (prepare, fused chain kernel, range verdict), MRSTFT 8 (per
+# resolution the fused STFT + loss kernel and the fused gradient + inverse-FFT kernel; the loss totals; one overlap-add for all at
+# backward), console backward 4 (recursion-table prepare, master chain kernel, track chain kernel beside it, one
+# epilogue); torch glue kernels are not counted
+GPU_LAUNCHES_PER_STEP = 15
 
 
 def main():

@@ -327,10 +327,9 @@ inline int console_forward(const ConsoleCall& k, float* mix, float* mixed, int* 
     pt.zero[0] = reinterpret_cast<int4*>(w.header); pt.zero_n16[0] = 64 * sizeof(int) / 16;
     const size_t zend = w.bflags_end > w.flags_end ? w.bflags_end : w.flags_end;
     pt.zero[1] = reinterpret_cast<int4*>(base + w.flags_begin); pt.zero_n16[1] = (long long)((zend - w.flags_begin + 15) / 16);
-    DMST_LAUNCH(prepare_kernel, dim3(pt.rows), dim3(256), 0, stream, pt);
     fill_prepare(pm, k, true, w, status);
     if (!k.master_params) { pm.kind = 3; pm.np = 0; }
-    DMST_LAUNCH(prepare_kernel, dim3(pm.rows), dim3(256), 0, stream, pm);
+    DMST_LAUNCH(prepare2_kernel, dim3(pt.rows + pm.rows), dim3(256), 0, stream, pt, pm);   // tracks and master bus, one launch
 
     FwdArgs f;
     memset(&f, 0, sizeof(f));
@@ -460,17 +459,16 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
         ScopedTimer tm(3, stream);
         DMST_LAUNCH(kern, dim3(ctas), dim3(kTrackBwdNT), smem, stream, ft);
     }
-    if (gmp && k.master_params) {
-        EpilogueArgs e;
-        memset(&e, 0, sizeof(e));
-        e.params = k.master_params; e.rows = k.B; e.np = DMST_NUM_MASTER_PARAMS; e.kind = 2;
-        for (int i = 0; i < DMST_NUM_MASTER_PARAMS; ++i) { e.lo[i] = k.ranges->master_lo[i]; e.hi[i] = k.ranges->master_hi[i]; }
-        e.sr = (double)k.sr; e.partial = w.m_partial; e.ntiles = w.nt_master; e.flags = am.flags; e.grad = gmp;
-        DMST_LAUNCH(grad_epilogue_kernel, dim3(e.rows), dim3(64), 0, stream, e);
-    }
     {
-        EpilogueArgs e;
+        EpilogueArgs em, e;
+        memset(&em, 0, sizeof(em));
         memset(&e, 0, sizeof(e));
+        const bool with_master = gmp && k.master_params;
+        if (with_master) {
+            em.params = k.master_params; em.rows = k.B; em.np = DMST_NUM_MASTER_PARAMS; em.kind = 2;
+            for (int i = 0; i < DMST_NUM_MASTER_PARAMS; ++i) { em.lo[i] = k.ranges->master_lo[i]; em.hi[i] = k.ranges->master_hi[i]; }
+            em.sr = (double)k.sr; em.partial = w.m_partial; em.ntiles = w.nt_master; em.flags = am.flags; em.grad = gmp;
+        }
         const bool basic = (k.flags & DMST_BASIC_CONSOLE) != 0;
         e.params = k.track_params; e.rows = k.B * k.N;
         e.np = basic ? 2 : DMST_NUM_TRACK_PARAMS; e.kind = basic ? 1 : 0;
@@ -481,7 +479,9 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
             for (int i = 0; i < DMST_NUM_TRACK_PARAMS; ++i) { e.lo[i] = k.ranges->track_lo[i]; e.hi[i] = k.ranges->track_hi[i]; }
         }
         e.sr = (double)k.sr; e.partial = w.t_partial; e.ntiles = epilogue_tiles; e.flags = at.flags; e.grad = gtp;
-        DMST_LAUNCH(grad_epilogue_kernel, dim3(e.rows), dim3(64), 0, stream, e);
+        // master-bus rows and track rows in one launch
+        if (with_master) DMST_LAUNCH(grad_epilogue2_kernel, dim3(em.rows + e.rows), dim3(64), 0, stream, em, e);
+        else DMST_LAUNCH(grad_epilogue_kernel, dim3(e.rows), dim3(64), 0, stream, e);
     }
     return DMST_LAST_ERROR();
 }

@@ -132,9 +132,7 @@ __device__ __forceinline__ M2 mpow_from_squares(const M2* sq, int e) {
 // One warp per (row, job): jobs 0..5 = EQ sections, job 6 = gains / compressor / pan, job 7 =
 // range check.  Lanes split the table entries (lane l builds P^l), everything in float64.
 // grid: rows blocks of 256 threads.
-__global__ void prepare_kernel(PrepareArgs a) {
-    grid_zero(a.zero, a.zero_n16);
-    const int row = blockIdx.x;
+__device__ __forceinline__ void prepare_row(const PrepareArgs& a, const int row) {
     const int job = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* p = a.params + (long long)row * a.np;
     const ParamMap pm = param_map(a.kind);
@@ -213,6 +211,16 @@ __global__ void prepare_kernel(PrepareArgs a) {
         }
     }
 }
+__global__ void prepare_kernel(PrepareArgs a) {
+    grid_zero(a.zero, a.zero_n16);
+    prepare_row(a, blockIdx.x);
+}
+// track rows and master-bus rows in one launch (blocks [0, a.rows) serve a, the rest b; a's clear is the grid's)
+__global__ void prepare2_kernel(PrepareArgs a, PrepareArgs b) {
+    grid_zero(a.zero, a.zero_n16);
+    if ((int)blockIdx.x < a.rows) prepare_row(a, blockIdx.x);
+    else prepare_row(b, blockIdx.x - a.rows);
+}
 
 // Tables of the track backward kernel (console_bwd2.cuh): per (row, section) the two delta-form recursions
 // g = A^-T u and h = (B/b0)^-T u (common.cuh, RecTab), designed in float64 from the denormalised parameters.
@@ -276,8 +284,7 @@ struct EpilogueArgs {
 // one 64-thread block per row: threads 0..kGradCount-1 reduce the tile partials (coalesced,
 // fixed order => deterministic), then threads 0..5 chain one EQ section each and thread 6
 // the gains / compressor / pan through the design Jacobian.
-__global__ void grad_epilogue_kernel(EpilogueArgs a) {
-    const int row = blockIdx.x;
+__device__ __forceinline__ void grad_epilogue_row(const EpilogueArgs& a, const int row) {
     const int tid = threadIdx.x;
     DMST_SHARED_ARRAY(double, acc, kGradCount);
     if (tid < kGradCount) {
@@ -340,6 +347,12 @@ __global__ void grad_epilogue_kernel(EpilogueArgs a) {
         }
         if (a.kind == 0) g[26] = 0.0f;  // fx send: the fx bus is off, no path to the mix
     }
+}
+__global__ void grad_epilogue_kernel(EpilogueArgs a) { grad_epilogue_row(a, blockIdx.x); }
+// master-bus rows and track rows in one launch (blocks [0, a.rows) serve a, the rest b)
+__global__ void grad_epilogue2_kernel(EpilogueArgs a, EpilogueArgs b) {
+    if ((int)blockIdx.x < a.rows) grad_epilogue_row(a, blockIdx.x);
+    else grad_epilogue_row(b, blockIdx.x - a.rows);
 }
 
 }  // namespace dmst
