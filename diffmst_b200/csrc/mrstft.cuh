@@ -257,6 +257,8 @@ struct OlaMultiArgs {
     const float* window[DMST_MRSTFT_MAX_RES];
     int n[DMST_MRSTFT_MAX_RES], hop[DMST_MRSTFT_MAX_RES], win[DMST_MRSTFT_MAX_RES], frames[DMST_MRSTFT_MAX_RES];
     int hop_shift[DMST_MRSTFT_MAX_RES];   // log2(hop) when hop is a power of two (the frame range needs no division), else -1
+    int batch_ok[DMST_MRSTFT_MAX_RES];    // half-overlapping frames, full window, power-of-two hop: the straight-line path
+    long long row_elems[DMST_MRSTFT_MAX_RES];   // frames * n
     float* gx;                 // rows x T (contiguous), or null
     int gx_vec_ok;
     const float* gscale;       // device scalar multiplying the gradient (the upstream gradient of the loss), or null
@@ -294,13 +296,14 @@ __global__ void ola_multi_kernel(OlaMultiArgs a) {
         da[r] = make_float4(0.f, 0.f, 0.f, 0.f); db[r] = da[r];
         if (r < a.n_res) {
             const int n = a.n[r], hop = a.hop[r], frames = a.frames[r], hs = a.hop_shift[r];
-            if ((a.win[r] == n) && hs >= 2 && n == 2 * hop && (t + 3 < a.T)) {
+            if (a.batch_ok[r] && (t + 3 < a.T)) {   // (host: win == n, hop a power of two >= 4, n == 2 hop, frames * n < 2^31)
                 batched[r] = true;
-                const float* df = a.dframes[r] + (long long)row * frames * n;
-                const int j = t + (n >> 1);
-                const int f1 = j >> hs, i1 = j - (f1 << hs);   // i1 in [0, hop), a multiple of 4
-                if (f1 < frames) da[r] = __ldg(reinterpret_cast<const float4*>(df + (long long)f1 * n + i1));
-                if (f1 >= 1 && f1 - 1 < frames) db[r] = __ldg(reinterpret_cast<const float4*>(df + (long long)(f1 - 1) * n + i1 + hop));
+                const float* df = a.dframes[r] + (long long)row * a.row_elems[r];
+                const int j = t + hop;                          // padded position (pad = n/2 = hop)
+                const int f1 = j >> hs, i1 = j & (hop - 1);     // i1 in [0, hop), a multiple of 4
+                const int o1 = (f1 << (hs + 1)) + i1;           // f1 * n + i1 (32-bit: the host checked frames * n < 2^31)
+                if (f1 < frames) da[r] = __ldg(reinterpret_cast<const float4*>(df + o1));
+                if (f1 >= 1 && f1 - 1 < frames) db[r] = __ldg(reinterpret_cast<const float4*>(df + o1 - hop));   // (f1-1) n + i1 + hop
             }
         }
     }
@@ -500,6 +503,9 @@ inline int mr_launch_ola(OlaMultiArgs& oa, const dmst_mrstft_cfg* c, int rows, i
         const int h = r < c->n_res ? c->hop_size[r] : 0;
         oa.hop_shift[r] = -1;
         if (h > 0 && (h & (h - 1)) == 0) { int sft = 0; while ((1 << sft) < h) ++sft; oa.hop_shift[r] = sft; }
+        oa.row_elems[r] = (long long)oa.frames[r] * oa.n[r];
+        oa.batch_ok[r] = r < c->n_res && oa.win[r] == oa.n[r] && oa.hop_shift[r] >= 2 && oa.n[r] == 2 * h &&
+                         oa.row_elems[r] < (1ll << 31);
     }
     oa.gx = grad_x; oa.gx_vec_ok = grad_x && ((reinterpret_cast<uintptr_t>(grad_x) & 15) == 0) && (T % 4 == 0);
     const dim3 grid(grad_x ? ((T + 3) / 4 + 255) / 256 : 1, grad_x ? rows : 1);

@@ -26,7 +26,7 @@ mr = table(list(csv.reader(open(mr_path)))) if os.path.exists(mr_path) else []
 lr = [r for r in csv.reader(open(f'gpurun_out/launches_step_{tag}.csv')) if len(r) > 5]
 h2 = lr[0]; ki = h2.index('Kernel Name'); vi = h2.index('Metric Value')
 names = [(r[ki], float(r[vi].replace(',', ''))) for r in lr[1:]]
-st = [i for i, (n, _) in enumerate(names) if 'prepare_kernel' in n][-2]
+st = [i for i, (n, _) in enumerate(names) if 'prepare2_kernel' in n][-1]   # first kernel of the last step
 step = names[st:]
 tot = sum(v for _, v in step)
 md = [f'# profiles/ - round {tag} (B200, ncu, `--clock-control none`)\n',
@@ -34,10 +34,10 @@ md = [f'# profiles/ - round {tag} (B200, ncu, `--clock-control none`)\n',
       'Commands (under gpurun):\n```\n'
       f'ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step_{tag}.csv python scripts/prof_step.py 3\n'
       f'ncu --set full --clock-control none --import-source on -k regex:"console_fwd|chain_bwd|track_bwd2" -s 3 -c 3 -o gpurun_out/prof_{tag} python scripts/prof_once.py 8 16 262144 2\n'
-      f'ncu --set full --clock-control none --import-source on -k regex:"stft_loss|mr_grad|ola_multi" -s 8 -c 8 -o gpurun_out/prof_mr_{tag} python scripts/prof_mrstft.py 2\n'
+      f'ncu --set full --clock-control none --import-source on -k regex:"stft_loss|istft_grad|ola_multi" -s 8 -c 8 -o gpurun_out/prof_mr_{tag} python scripts/prof_mrstft.py 2\n'
       'python scripts/timeline_step.py   # torch.profiler / CUPTI timeline of the graph-replayed step: what overlaps\n'
       'python scripts/sweep_eq_comp.py ; python tests/tools/conv_bench.py\npython bench.py --steps 50 --warmup 5 ; python bench.py --impl reference --steps 3 --warmup 1\n```\n',
-      '## 1. Launch list of one step (ncu per-launch times are cold-cache and serialised: compare shares)\n',
+      '## 1. Launch list of one step (ncu per-launch times are cold-cache and SERIALISED: under ncu the three MRSTFT resolutions run one after the other and the master-bus backward kernel, which in the step runs on 4 B = 32 SMs beside the track kernel, is timed alone on those 32 SMs; `timeline_step_r2.txt` has the real overlap)\n',
       '| us | share | kernel |\n|---:|---:|---|']
 for n, v in step:
     md.append(f'| {v/1000:.1f} | {100*v/tot:.1f}% | `{n[:110]}` |')
