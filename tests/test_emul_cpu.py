@@ -192,3 +192,47 @@ def test_emulated_fused_stft_front_end_matches_numpy(emul_console, cfg):
     ref = np.array([(d ** 2).sum(), pyr.sum(), np.abs(0.5 * (np.log(pxr) - np.log(pyr))).sum(), np.abs(d).sum()])
     got = partial.astype(np.float64).sum((0, 1))
     assert (np.abs(got - ref) / ref).max() <= 2e-6
+
+
+@pytest.mark.parametrize("cfg", [(512, 2, 20), (2048, 1, 7), (8192, 1, 3), (64, 1, 70), (128, 1, 40), (256, 2, 17),
+                                 (1024, 1, 9), (4096, 1, 2)])
+@pytest.mark.parametrize("terms", [(1, 1), (0, 0)])
+def test_emulated_fused_gradient_inverse_fft_matches_closed_form(emul_console, cfg, terms):
+    """stft_fused.cuh::istft_grad_kernel (spectrum + clamped target power -> half-spectrum gradient -> inverse real FFT
+    of every frame) on the host emulator against the closed form r[n] = Re sum_k g[k] exp(+2 pi i k n / N) in float64,
+    for every radix plan, with and without the log / linear magnitude terms, including a clamped bin."""
+    import ctypes
+    n, rows, frames = cfg
+    use_log, use_lin = terms
+    lib = emul_console.load()
+    rng = np.random.default_rng(n + frames)
+    M = n // 2
+    bins = M + 1
+    X = rng.standard_normal((rows, frames, bins, 2)).astype(np.float32)
+    X[0, 0, 3] = 0   # |X|^2 below eps: the clamp passes no gradient
+    Y = rng.standard_normal((rows, frames, bins, 2))
+    eps = 1e-8
+    PY = np.maximum((Y ** 2).sum(-1), eps).astype(np.float32)
+    rc = (rng.random(rows) * 0.01).astype(np.float32)
+    scal = np.array([3e-4, 2e-4], np.float32)
+    j = np.arange(M)
+    twm = np.stack([np.cos(2 * np.pi * j / M), -np.sin(2 * np.pi * j / M)], -1).astype(np.float32)
+    k = np.arange(M // 2 + 1)
+    twn = np.stack([np.cos(2 * np.pi * k / n), -np.sin(2 * np.pi * k / n)], -1).astype(np.float32)
+    out = np.zeros((rows, frames, n), np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rcode = lib.dmst_emul_istft_grad(p(X), p(PY), p(out), rows, n, frames, p(twm), p(twn), ctypes.c_float(eps), p(rc),
+                                     p(scal), use_log, use_lin)
+    assert rcode == 0
+    Xc = X[..., 0].astype(np.float64) + 1j * X[..., 1].astype(np.float64)
+    px, py = np.abs(Xc) ** 2, PY.astype(np.float64)
+    mx, my = np.sqrt(np.maximum(px, 1e-300)), np.sqrt(py)
+    gsc = rc.astype(np.float64)[:, None, None] * (mx - my)
+    if use_log:
+        gsc = gsc + scal[0] * np.sign(px - py) / mx
+    if use_lin:
+        gsc = gsc + scal[1] * np.sign(mx - my)
+    g = np.where(px >= eps, gsc / mx, 0.0) * Xc
+    E = np.exp(2j * np.pi * np.outer(np.arange(bins), np.arange(n)) / n)
+    ref = np.real(g @ E)
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
