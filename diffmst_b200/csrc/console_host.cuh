@@ -37,10 +37,19 @@ static_assert(kTrackTile % kTrackBwd2Tile == 0, "backward tiles nest in forward 
 constexpr int kMasterTile = kMasterL * kMasterNT;
 constexpr int kMasterTileShift = 12;
 static_assert((1 << kMasterTileShift) == kMasterTile, "power-of-two master tile");
-// CTAs of the master backward kernel per bus while the track kernel runs beside it (see console_backward): four
-// tiles of a bus in flight keep its chain of tiles busy (measured on B200, batch 8: 16 CTAs 1.46 ms per step,
-// 24 1.236, 32 1.198, 48 1.204, 64 1.207, all 148 1.217; without the overlap 1.239)
-constexpr int kMasterBwdOverlapCtasPerBus = 4, kMasterBwdOverlapMinCtas = 16;
+// CTAs of the master backward kernel while the track kernel runs beside it (see console_backward).  Both kernels are
+// work bound once the master chain has a few tiles in flight: a master tile costs about 25 us of one CTA, a track tile
+// 7.3 us of one SM (measured on B200), so the two finish together when (SMs - C) / C = 0.293 N; C is set 15 % above
+// that, because a master kernel that finishes last stalls the track kernel, while one that finishes early only idles
+// its own SMs.  Measured, ms per step at B = 8, N = 16 (graph replay): 16 CTAs 1.46, 24 1.236, 32 1.198, 48 1.204,
+// 64 1.207, all 148 1.217, no overlap 1.239; console forward + backward alone at B = 16, N = 4: 32 CTAs 1.04 ms,
+// 48 0.80, 64 0.69, 96 0.73, 148 0.76.
+inline int master_bwd_overlap_ctas(int sms, int B, int N) {
+    int c = (int)(sms * 1.15 / (1.0 + 0.293 * N) + 0.5);
+    if (c > 24 * B) c = 24 * B;   // (more than ~24 tiles of one chain in flight only wait for each other)
+    if (c < 8) c = 8;
+    return c;
+}
 static_assert(kTrackFwdL * kTrackFwdNT == kTrackBwdL * kTrackBwdNT, "forward/backward tiles must agree");
 static_assert(kTrackBwdL == kBwdChunk && kTrackFwdL % kBwdChunk == 0, "checkpoint spacing");
 
@@ -418,8 +427,7 @@ inline int console_backward(const ConsoleCall& k, const float* gmix, const float
         if (max_ctas <= 0) return DMST_EINVAL;
         int ctas = max_ctas;
         if (params_only && overlap) {
-            ctas = kMasterBwdOverlapCtasPerBus * am.nrows;
-            if (ctas < kMasterBwdOverlapMinCtas) ctas = kMasterBwdOverlapMinCtas;
+            ctas = master_bwd_overlap_ctas(max_ctas, k.B, k.N);   // (one CTA per SM: max_ctas = SMs)
             if (ctas > max_ctas) ctas = max_ctas;
         }
         if (const char* e = getenv("DMST_MASTER_BWD_CTAS")) { const int c = atoi(e); if (c > 0) ctas = c < max_ctas ? c : max_ctas; }  // tuning aid
