@@ -90,11 +90,12 @@ struct RowTab : CompTab {
 constexpr int kBwd2Chunk = 32;     // samples per thread in the EQ-gradient phase
 // The two recursions of a section run in lock step as the halves of packed float2 operations
 // (fma.rn.f32x2 / add.rn.f32x2: one issue slot for both): .x = g (poles), .y = h (zeros), both in the form
-//     t = nc0 s + u,   v' = k2 v + t,   s' = s + v',   and off the recurrence  w = nd2 v + t  (= v' - v, the second
-//     difference, with -(1 - c2) held as its own float32),      nc0 = -c0, k2 = c2, nd2 = -(1 - c2).
+//     t = nc0 s + u,   v' = k2 v + t,   s' = s + v',      nc0 = -c0, k2 = c2
+// (the second difference v' - v the b2 gradient needs is never formed: its correlation with e is summed by parts into
+// a correlation of v with e[n] - e[n-1], console_bwd2.cuh).
 struct PairTab {
     float2 nc0;          // -c0
-    float2 nd2;          // -(1 - c2)
+    float2 nd2;          // -(1 - c2): the second difference as nd2 v + t (kept in the table; the kernel no longer forms it)
     float2 scale;        // factor of each recursion's sums in the tile partials: (1, 1/b0)
     float2 k2;           // c2
     float2 P2[6][4];     // P^(2^j), j = 0..4 warp scan, P2[5] = P^32 across a warp; P = M^32, M row-major
