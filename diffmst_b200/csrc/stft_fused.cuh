@@ -1,20 +1,24 @@
-// Fused STFT front end of the multi-resolution STFT loss: framing (reflect padding, window), the real FFT of
-// every frame of BOTH signals, and the loss reductions, in one kernel.  Replaces frame4_kernel + cuFFT R2C +
-// mr_loss_kernel for power-of-two FFT sizes 64..8192 (auraloss.freq.STFTLoss.stft + the three loss terms,
-// SURVEY.md Appendix B; instantiated at configs/models/naive.yaml:54-68, called at mst/system.py:332).
+// Fused STFT kernels of the multi-resolution STFT loss, with their own FFT (no library call), for power-of-two FFT
+// sizes 64..8192 (auraloss.freq.STFTLoss.stft + the three loss terms and their gradient, SURVEY.md Appendix B;
+// instantiated at configs/models/naive.yaml:54-68, called at mst/system.py:332):
 //
-// Why: the three-kernel path writes the frames (2x the signal), reads them back, writes both spectra and reads
-// them again: 300 MB of DRAM traffic per resolution at the headline shape for 84 MB of necessary traffic (read
-// the signals once through L2, write the spectrum of the prediction and |Y|^2 of the target for the gradient
-// pass).  Here a frame never leaves the SM between the signal and the loss sums.
+//   stft_loss_kernel   framing (reflect padding, window), the real FFT of every frame of BOTH signals and the loss
+//                      reductions; replaces frame4_kernel + cuFFT R2C + mr_loss_kernel.
+//   istft_grad_kernel  spectrum of the prediction + max(|Y|^2, eps) -> half-spectrum gradient -> inverse real FFT of
+//                      every frame; replaces mr_grad_kernel + cuFFT C2R.
+//
+// Why: the library path writes the frames (2x the signal), reads them back, writes both spectra and reads them again:
+// 300 MB of DRAM traffic per resolution at the headline shape for 84 MB of necessary traffic (read the signals once
+// through L2, write the spectrum of the prediction and |Y|^2 of the target for the gradient pass).  Here a frame never
+// leaves the SM between the signal and the loss sums.
 //
 // Layout: a block of 256 threads owns 4096 complex points = FPB = 8192 / n frames of one row; a real FFT of
 // length n is a complex FFT of length M = n/2 over z[m] = x[2m] + i x[2m+1] followed by the even/odd split.
 // The complex FFT is a Cooley-Tukey decomposition M = 16 * R2 [* R3]: every thread holds 16 points in
 // registers per stage (16 / R butterflies of radix R), stages exchange through shared memory IN PLACE (a
-// butterfly reads and writes the same R addresses, so one barrier per stage), the index padding i + i/16
-// keeps all strides that occur (1, 4, 16, M/16) free of bank conflicts.  Twiddles come from float64-built
-// tables (w_M^j and w_n^k).
+// butterfly reads and writes the same R addresses, so one barrier per stage), the index padding i + i/16 + i/256
+// keeps all strides that occur free of bank conflicts.  Twiddles come from float64-built tables (w_M^j and w_n^k).
+// The inverse transform is the same stage code run on the conjugated input, result conjugated.
 #pragma once
 #include "common.cuh"
 #include "stft.cuh"
