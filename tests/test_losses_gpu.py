@@ -183,3 +183,30 @@ def test_loss_full_size_properties():
     assert all(torch.isfinite(v) for v in out.values())
     same = afl(y, y)
     assert all(float(v) == 0.0 for v in same.values())
+
+
+def test_mrstft_one_call_form_of_the_c_abi_matches_the_autograd_node():
+    """dmst_mrstft_forward with a gradient buffer (loss and d loss / d x in ONE call, what a non-autograd host would
+    bind) against the two-call form the autograd node uses (dmst_mrstft_forward_keep + dmst_mrstft_backward)."""
+    import ctypes
+    from diffmst_b200 import MRSTFTLoss, _lib
+    from diffmst_b200.console import _ptr
+    g = torch.Generator().manual_seed(25)
+    x = (torch.randn(2, 2, 30000, generator=g) * 0.1).cuda()
+    y = (torch.randn(2, 2, 30000, generator=g) * 0.1 + 0.3 * x.cpu()).cuda()
+    f = MRSTFTLoss(**RES)
+    xr = x.clone().requires_grad_(True)
+    loss = f(xr, y)
+    loss.backward()
+    lib, cfg, win = _lib.lib(), f._cfg(), f._windows_on(x.device)
+    rows, T = 4, 30000
+    n = lib.dmst_mrstft_workspace_bytes(ctypes.byref(cfg), rows, T)
+    ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+    out = torch.empty(1 + 3 * cfg.n_res, device=x.device)
+    gx = torch.empty(rows, T, device=x.device)
+    rc = lib.dmst_mrstft_forward(_ptr(x), T, _ptr(y), T, _ptr(win), ctypes.byref(cfg), rows, T, _ptr(out), _ptr(gx),
+                                 _ptr(ws), n, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    assert float(out[0]) == float(loss.detach())
+    assert torch.equal(gx.view_as(x), xr.grad)
+    assert torch.equal(out[1:].view(-1, 3), f.last_terms)
