@@ -295,7 +295,7 @@ __global__ void ola_multi_kernel(OlaMultiArgs a) {
         batched[r] = false;
         da[r] = make_float4(0.f, 0.f, 0.f, 0.f); db[r] = da[r];
         if (r < a.n_res) {
-            const int n = a.n[r], hop = a.hop[r], frames = a.frames[r], hs = a.hop_shift[r];
+            const int hop = a.hop[r], frames = a.frames[r], hs = a.hop_shift[r];
             if (a.batch_ok[r] && (t + 3 < a.T)) {   // (host: win == n, hop a power of two >= 4, n == 2 hop, frames * n < 2^31)
                 batched[r] = true;
                 const float* df = a.dframes[r] + (long long)row * a.row_elems[r];
